@@ -1,0 +1,269 @@
+/* seedrl_b200.h -- C-ABI of libseedrl_b200.so: the B200 (sm_100a) hot path of a
+ * SEED-RL V-trace learner.  Plain C, no torch / C++ types in any signature.
+ *
+ * Conventions (all entry points):
+ *   - return 0 on success, non-zero error code otherwise; the message is
+ *     available from seedrl_last_error() (thread-local).
+ *   - every device pointer is caller-owned (torch or cudaMalloc), never freed
+ *     or retained beyond the call unless a handle documents it.
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, not synced.
+ *   - tensors are dense, row-major, fp32 unless stated; time-major [T, B, ...]
+ *     exactly like the reference's learner (agents/vtrace/learner.py:418-432).
+ *   - there is NO CPU fallback anywhere behind this ABI.
+ *
+ * Each entry point cites the reference interface it replaces
+ * (paths relative to google-research/seed_rl).
+ */
+#ifndef SEEDRL_B200_H_
+#define SEEDRL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEEDRL_OK 0
+#define SEEDRL_ERR_INVALID_ARGUMENT 3   /* tensorflow.error.Code values, so the  */
+#define SEEDRL_ERR_OUT_OF_RANGE 11      /* RPC layer can forward them unchanged  */
+#define SEEDRL_ERR_INTERNAL 13          /* (grpc/service.proto:51-56)            */
+#define SEEDRL_ERR_CANCELLED 1
+#define SEEDRL_ERR_UNAVAILABLE 14
+
+typedef void* seedrl_stream_t;
+
+const char* seedrl_last_error(void);
+int seedrl_abi_version(void);
+/* Number of kernels launched by this library since load (bench.py's
+ * `gpu_launches` evidence). */
+uint64_t seedrl_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * (a1) V-trace targets.   Replaces common/vtrace.py:34-148
+ * `from_importance_weights`.  Inputs [T, B] (B may be a flattened B*C for the
+ * "extra trailing dims" case, vtrace.py:49-51), bootstrap [B].  A NaN clip
+ * threshold means `None` (no clipping, vtrace.py:111-114,138-142).
+ * Outputs vs, pg_advantages [T, B].
+ */
+int seedrl_vtrace_from_importance_weights(
+    int T, int B,
+    const float* target_action_log_probs, const float* behaviour_action_log_probs,
+    const float* discounts, const float* rewards, const float* values,
+    const float* bootstrap_value,
+    float clip_rho_threshold, float clip_pg_rho_threshold, float lambda_,
+    float* vs, float* pg_advantages, seedrl_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * (a3) Categorical distribution.  Replaces
+ * common/parametric_distribution.py:66-74,83-97 (tfd.Categorical log_prob /
+ * entropy) and the sampling of dmlab/networks.py:121-122.
+ * logits [N, A]; actions int64 [N] (tf.int64, dmlab/networks.py:121).
+ */
+int seedrl_categorical_log_prob(int N, int A, const float* logits,
+                                const int64_t* actions, float* log_prob,
+                                seedrl_stream_t stream);
+int seedrl_categorical_entropy(int N, int A, const float* logits, float* entropy,
+                               seedrl_stream_t stream);
+/* Gumbel-max sample: action = argmax_k(logits[k] + g[k]).  If gumbel_noise is
+ * non-NULL ([N, A] fp32) it is used as g (bit-exact, test mode); otherwise g is
+ * drawn in-kernel from Philox4x32-10 keyed by (seed, offset). */
+int seedrl_categorical_sample(int N, int A, const float* logits,
+                              const float* gumbel_noise, uint64_t seed,
+                              uint64_t offset, int64_t* actions,
+                              seedrl_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * (a2) Fused V-trace loss: the part of agents/vtrace/learner.py:82-157
+ * `compute_loss` after the network unroll, PLUS its analytic gradient
+ * (what tape.gradient, learner.py:264, produces for the network outputs).
+ */
+typedef struct seedrl_loss_config {
+  float discounting;        /* FLAGS.discounting  learner.py:59  */
+  float lambda_;            /* FLAGS.lambda_      learner.py:60  */
+  float baseline_cost;      /* learner.py:57 */
+  float kl_cost;            /* learner.py:58 */
+  float max_abs_reward;     /* learner.py:61; 0 disables clipping */
+  float clip_rho_threshold;     /* compute_loss uses the default 1.0; NaN = None */
+  float clip_pg_rho_threshold;  /* compute_loss uses the default 1.0; NaN = None */
+  float target_entropy;     /* learner.py:52; used iff has_target_entropy */
+  int32_t has_target_entropy;
+  float entropy_cost_adjustment_speed; /* `mul`, learner.py:54,226 */
+} seedrl_loss_config;
+
+/* Indices into loss_terms[SEEDRL_LOSS_TERMS] (device, fp32), in the order the
+ * reference logs them (learner.py:138-157). */
+enum {
+  SEEDRL_LT_TOTAL = 0, SEEDRL_LT_POLICY = 1, SEEDRL_LT_V = 2, SEEDRL_LT_ENTROPY = 3,
+  SEEDRL_LT_KL = 4, SEEDRL_LT_ENTROPY_ADJ = 5, SEEDRL_LT_V_MEAN = 6,
+  SEEDRL_LT_V_L2_ERROR = 7, SEEDRL_LT_MEAN_ENTROPY = 8, SEEDRL_LT_ENTROPY_COST = 9,
+  SEEDRL_LT_MEAN_KL = 10, SEEDRL_LT_MAX_ACTION_ABS = 11,
+  SEEDRL_LOSS_TERMS = 16
+};
+
+/* T1 = unroll_length + 1 rows, as in compute_loss.
+ *   learner_logits [T1,B,A], learner_baseline [T1,B]   (network outputs)
+ *   behaviour_logits [T1,B,A], actions int64 [T1,B]     (agent_outputs)
+ *   rewards [T1,B], done uint8 [T1,B]                    (env_outputs)
+ *   entropy_cost_param: device scalar; entropy_cost = exp(mul * param)
+ *                       (learner.py:225-234)
+ * Outputs: loss_terms[16]; dlogits [T1,B,A] and dbaseline [T1,B] = d total_loss
+ * / d learner outputs (row T1-1 is zero: the bootstrap only enters through
+ * stop_gradient'ed V-trace outputs); d_entropy_cost_param (device scalar);
+ * optional vs / pg_advantages [T1-1,B] (may be NULL).
+ * `scratch` must hold seedrl_vtrace_loss_scratch_bytes(T1,B,A) bytes and be
+ * ZERO-INITIALISED ONCE by the caller; every launch leaves it zeroed again
+ * (self-resetting completion ticket), so it can be reused without a memset. */
+size_t seedrl_vtrace_loss_scratch_bytes(int T1, int B, int A);
+int seedrl_vtrace_loss_fwd_bwd(
+    int T1, int B, int A,
+    const float* learner_logits, const float* learner_baseline,
+    const float* behaviour_logits, const int64_t* actions,
+    const float* rewards, const uint8_t* done,
+    const seedrl_loss_config* cfg, const float* entropy_cost_param,
+    float* loss_terms, float* dlogits, float* dbaseline,
+    float* d_entropy_cost_param, float* vs_out, float* pg_advantages_out,
+    void* scratch, seedrl_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * (a4) Optimizer apply.  Replaces optimizer.apply_gradients
+ * (agents/vtrace/learner.py:272-273) with tf.keras Adam semantics
+ * (dmlab/vtrace_main.py:46-51): ONE launch over the flat parameter arena.
+ *   lr_t = lr*sqrt(1-b2^t)/(1-b1^t) is computed by the caller's host code from
+ *   `iterations`; here: m=b1 m+(1-b1) g; v=b2 v+(1-b2) g^2;
+ *   p -= lr_t * m/(sqrt(v)+eps).   g is pre-multiplied by grad_scale (1 for the
+ *   reference's cross-replica SUM, 1/N for a mean).
+ * clamp_index >= 0 clamps that one element to [clamp_lo, clamp_hi] after the
+ * update (the entropy_cost_param constraint, learner.py:229-231). */
+int seedrl_adam_apply(size_t n, float* params, const float* grads, float* m,
+                      float* v, float lr_t, float beta1, float beta2, float eps,
+                      float grad_scale, int64_t clamp_index, float clamp_lo,
+                      float clamp_hi, seedrl_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * (a5) Policy network.  Replaces dmlab/networks.py:63-171 `ImpalaDeep`
+ * (__call__/_unroll/_torso/_head, _Stack) and common/utils.py:714-732
+ * batch_apply; SEEDRL_NET_SHALLOW is the IMPALA-paper shallow net (not in the
+ * reference).  Parameters live in ONE flat fp32 arena in
+ * tf.Module.trainable_variables order with Keras layouts (conv HWIO, dense
+ * [in,out], LSTM [in,4H] gates i,f,c,o) followed by the scalar
+ * entropy_cost_param; seedrl_net_param_* describe it.
+ */
+enum { SEEDRL_NET_DEEP = 0, SEEDRL_NET_SHALLOW = 1 };
+
+typedef struct seedrl_net_config {
+  int32_t net;            /* SEEDRL_NET_* */
+  int32_t num_actions;    /* A */
+  int32_t obs_h, obs_w, obs_c;   /* uint8 NHWC observation */
+} seedrl_net_config;
+
+typedef struct seedrl_net seedrl_net;   /* opaque: layer table + offsets only */
+
+int seedrl_net_create(const seedrl_net_config* cfg, seedrl_net** out);
+void seedrl_net_destroy(seedrl_net* net);
+int seedrl_net_num_param_tensors(const seedrl_net* net);       /* 39 for deep */
+size_t seedrl_net_num_params(const seedrl_net* net);          /* excl. entropy param */
+/* Length (floats) of the flat arena: every tensor start is aligned to 64 floats,
+ * the last slot is the scalar entropy_cost_param (param index == num tensors). */
+size_t seedrl_net_arena_floats(const seedrl_net* net);
+/* name is written into buf (NUL-terminated); shape into dims[0..3], rank returned. */
+int seedrl_net_param_info(const seedrl_net* net, int index, char* name_buf,
+                          size_t name_buf_len, int64_t* dims, size_t* offset);
+/* Bytes of activation workspace for an unroll of T1 x B frames kept for backward. */
+size_t seedrl_net_workspace_bytes(const seedrl_net* net, int T1, int B);
+
+/* Forward unroll (is_training=True, unroll=True): inputs time-major,
+ *   prev_actions int64 [T1,B], reward [T1,B], done uint8 [T1,B],
+ *   observation uint8 [T1,B,H,W,C], h0/c0 [B,256].
+ * outputs policy_logits [T1,B,A], baseline [T1,B], h_out/c_out [B,256]. */
+int seedrl_net_forward(const seedrl_net* net, const float* params, int T1, int B,
+                       const int64_t* prev_actions, const float* reward,
+                       const uint8_t* done, const uint8_t* observation,
+                       const float* h0, const float* c0,
+                       float* policy_logits, float* baseline,
+                       float* h_out, float* c_out,
+                       void* workspace, size_t workspace_bytes,
+                       seedrl_stream_t stream);
+/* Backward of the same unroll (must follow seedrl_net_forward on the same
+ * workspace).  grads (flat arena layout, same offsets as params) is OVERWRITTEN
+ * with d loss / d params. */
+int seedrl_net_backward(const seedrl_net* net, const float* params, int T1, int B,
+                        const int64_t* prev_actions, const float* reward,
+                        const uint8_t* done, const uint8_t* observation,
+                        const float* dlogits, const float* dbaseline,
+                        float* grads, void* workspace, size_t workspace_bytes,
+                        seedrl_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * (a7/a8) Per-environment state on the GPU.  Replaces
+ * common/utils.py:119-257 UnrollStore.append/reset (scatter_nd_update on host
+ * variables) and :461-543 Aggregator.{reset,add,read,replace} for one field.
+ * `state` is [num_envs, full_length, row_bytes] bytes; `index` int32 [num_envs].
+ */
+int seedrl_store_append_field(uint8_t* state, const int32_t* index,
+                              const int32_t* env_ids, int n, int full_length,
+                              size_t row_bytes, const uint8_t* values,
+                              seedrl_stream_t stream);
+/* index[env]++ for env in env_ids; writes completed env ids (index reached
+ * full_length) compacted IN env_ids ORDER into completed_ids and their count
+ * into *num_completed (device int32). */
+int seedrl_store_advance(int32_t* index, const int32_t* env_ids, int n,
+                         int full_length, int32_t* completed_ids,
+                         int32_t* num_completed, seedrl_stream_t stream);
+/* For each completed env: copy its full unroll rows to `unrolls`
+ * ([n_completed, full_length, row_bytes], env-major like the reference, or
+ * time-major [full_length, n_completed, row_bytes] if time_major != 0, which
+ * removes make_time_major, common/utils.py:735-761), then move the last
+ * `overlap+1` rows to the front. */
+int seedrl_store_gather_field(uint8_t* state, const int32_t* completed_ids,
+                              int n_completed, int full_length, size_t row_bytes,
+                              int overlap, int time_major, uint8_t* unrolls,
+                              seedrl_stream_t stream);
+int seedrl_store_finish(int32_t* index, const int32_t* completed_ids,
+                        int n_completed, int overlap, seedrl_stream_t stream);
+int seedrl_store_reset(uint8_t* state, int32_t* index, const int32_t* env_ids,
+                       int n, int full_length, size_t row_bytes, int overlap,
+                       seedrl_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * (a10) Inference batcher (host side).  Replaces the server-side dynamic
+ * batcher grpc/ops/grpc.cc:591-861 (`DynamicFn`, `Computation`): callers claim
+ * k contiguous slots of a fixed-size batch, copy their payload straight into a
+ * pinned host slab, and block until the batch has been computed; the learner
+ * thread waits for a full batch, runs it, publishes outputs and releases.
+ * >= 2 batches in flight (grpc.cc:656-661).  No torch, no CUDA calls except
+ * cudaHostAlloc/cudaFreeHost for the slabs.
+ */
+typedef struct seedrl_batcher seedrl_batcher;
+/* in/out_row_bytes: bytes per batch row for each input / output field. */
+int seedrl_batcher_create(int batch_size, int num_slabs, int n_in,
+                          const size_t* in_row_bytes, int n_out,
+                          const size_t* out_row_bytes, int pinned,
+                          seedrl_batcher** out);
+void seedrl_batcher_destroy(seedrl_batcher* b);
+/* Caller side: claim k rows; returns slab id + first row (grpc.cc:638-663).
+ * k > batch_size or a claim that would straddle a batch => OUT_OF_RANGE
+ * (the reference CHECK-fails, grpc.cc:653). */
+int seedrl_batcher_claim(seedrl_batcher* b, int k, int* slab, int* row);
+void* seedrl_batcher_input_ptr(seedrl_batcher* b, int slab, int field, int row);
+void* seedrl_batcher_output_ptr(seedrl_batcher* b, int slab, int field, int row);
+/* Caller side: mark k rows written; when the slab is full the compute side wakes. */
+int seedrl_batcher_commit(seedrl_batcher* b, int slab, int k);
+/* Caller side: block until the slab's outputs are published (or shutdown ->
+ * SEEDRL_ERR_CANCELLED "Server shutdown.", grpc.cc:771-787).  The caller then reads
+ * its rows through seedrl_batcher_output_ptr and calls seedrl_batcher_release once
+ * per successful claim; the slab is recycled when every claimant has released. */
+int seedrl_batcher_wait_outputs(seedrl_batcher* b, int slab, int* status);
+int seedrl_batcher_release(seedrl_batcher* b, int slab);
+/* Compute side: block until some slab is full; returns its id
+ * (SEEDRL_ERR_CANCELLED after shutdown). timeout_ms < 0 = forever. */
+int seedrl_batcher_next_full(seedrl_batcher* b, int timeout_ms, int* slab);
+/* Compute side: outputs are in place; wake the callers.  status != 0 is
+ * propagated to every caller of this batch. */
+int seedrl_batcher_publish(seedrl_batcher* b, int slab, int status);
+int seedrl_batcher_shutdown(seedrl_batcher* b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* SEEDRL_B200_H_ */

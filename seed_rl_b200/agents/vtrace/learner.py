@@ -1,0 +1,218 @@
+"""V-trace learner -- mirror of the reference's `agents/vtrace/learner.py`:
+
+  flags                         learner.py:38-68   (same names and defaults)
+  compute_loss                  learner.py:73-159
+  Unroll                        learner.py:162-163
+  minimize (LearnerStep)        learner.py:255-280
+  learner_loop                  learner.py:170-483 (see learner_loop.py for the RPC wiring)
+
+Device work per step = seedrl_net_forward -> seedrl_vtrace_loss_fwd_bwd ->
+seedrl_net_backward -> [one NCCL all-reduce(SUM) of the flat gradient arena]
+-> seedrl_adam_apply.  There is no autograd tape: the loss kernel emits the analytic
+gradient w.r.t. the network outputs and the network backward is an explicit schedule.
+"""
+import collections
+import math
+
+from absl import flags
+import torch
+
+from seed_rl_b200 import _lib
+from seed_rl_b200.common import common_flags  # pylint: disable=unused-import
+from seed_rl_b200.common import utils
+
+# Training.
+flags.DEFINE_integer('save_checkpoint_secs', 1800, 'Checkpoint save period in seconds.')
+flags.DEFINE_integer('total_environment_frames', int(1e9),
+                     'Total environment frames to train for.')
+flags.DEFINE_integer('batch_size', 32, 'Batch size for training.')
+flags.DEFINE_integer('inference_batch_size', -1, 'Batch size for inference, -1 for auto-tune.')
+flags.DEFINE_integer('unroll_length', 100, 'Unroll length in agent steps.')
+flags.DEFINE_integer('num_training_tpus', 1, 'Unused on B200 (kept for flag compatibility).')
+flags.DEFINE_string('init_checkpoint', None,
+                    'Path to the checkpoint used to initialize the agent.')
+# Loss settings.
+flags.DEFINE_float('entropy_cost', 0.00025, 'Entropy cost/multiplier.')
+flags.DEFINE_float('target_entropy', None, 'If not None, the entropy cost is '
+                   'automatically adjusted to reach the desired entropy level.')
+flags.DEFINE_float('entropy_cost_adjustment_speed', 10., 'Controls how fast '
+                   'the entropy cost coefficient is adjusted.')
+flags.DEFINE_float('baseline_cost', .5, 'Baseline cost/multiplier.')
+flags.DEFINE_float('kl_cost', 0., 'KL(old_policy|new_policy) loss multiplier.')
+flags.DEFINE_float('discounting', .99, 'Discounting factor.')
+flags.DEFINE_float('lambda_', 1., 'Lambda.')
+flags.DEFINE_float('max_abs_reward', 0., 'Maximum absolute reward when calculating loss.'
+                   'Use 0. to disable clipping.')
+# Logging
+flags.DEFINE_integer('log_batch_frequency', 100, 'We average that many batches '
+                     'before logging batch statistics like entropy.')
+flags.DEFINE_integer('log_episode_frequency', 1, 'We average that many episodes'
+                     ' before logging average episode return and length.')
+# B200 additions
+flags.DEFINE_enum('grad_reduce', 'sum', ['sum', 'mean'],
+                  'Cross-replica gradient reduction. The reference SUMs '
+                  '(tests/utils_test.py:609-650).')
+
+FLAGS = flags.FLAGS
+
+LossSettings = collections.namedtuple(
+    'LossSettings',
+    'discounting lambda_ baseline_cost entropy_cost kl_cost max_abs_reward '
+    'target_entropy entropy_cost_adjustment_speed')
+
+
+def loss_settings_from_flags():
+  return LossSettings(FLAGS.discounting, FLAGS.lambda_, FLAGS.baseline_cost,
+                      FLAGS.entropy_cost, FLAGS.kl_cost, FLAGS.max_abs_reward,
+                      FLAGS.target_entropy, FLAGS.entropy_cost_adjustment_speed)
+
+
+def default_loss_settings(**kw):
+  d = dict(discounting=.99, lambda_=1., baseline_cost=.5, entropy_cost=0.00025, kl_cost=0.,
+           max_abs_reward=0., target_entropy=None, entropy_cost_adjustment_speed=10.)
+  d.update(kw)
+  return LossSettings(**d)
+
+
+class _NullLogger(object):
+  def log_session(self):
+    return []
+
+  def log(self, session, name, value):
+    session.append((name, value))
+
+
+_LOG_NAMES = [  # learner.py:138-157
+    ('V/value function', 'v_mean'), ('V/L2 error', 'v_l2_error'),
+    ('losses/policy', 'policy'), ('losses/V', 'V'), ('losses/entropy', 'entropy'),
+    ('losses/kl', 'kl'), ('losses/total', 'total'),
+    ('policy/max_action_abs(before_tanh)', 'max_action_abs'),
+    ('policy/entropy', 'mean_entropy'), ('policy/entropy_cost', 'entropy_cost'),
+    ('policy/kl(old|new)', 'mean_kl')]
+
+_scratch_cache = {}
+
+
+def _loss_scratch(T1, B, A, device):
+  key = (T1, B, A, str(device))
+  if key not in _scratch_cache:
+    n = int(_lib.lib().seedrl_vtrace_loss_scratch_bytes(T1, B, A))
+    _scratch_cache[key] = torch.zeros(n, dtype=torch.uint8, device=device)   # zeroed ONCE
+  return _scratch_cache[key]
+
+
+def vtrace_loss_fwd_bwd(settings, learner_logits, learner_baseline, behaviour_logits,
+                        actions, rewards, done, entropy_cost_param, want_vtrace=False):
+  """The fused kernel of compute_loss (learner.py:82-157) + its gradient.  All inputs
+  have T+1 rows.  Returns dict(loss_terms[16], dlogits, dbaseline, d_entropy_cost_param,
+  vs, pg_advantages)."""
+  f32 = torch.float32
+  ll = _lib.require_cuda(learner_logits, f32, 'learner_logits')
+  lb = _lib.require_cuda(learner_baseline, f32, 'learner_baseline')
+  bl = _lib.require_cuda(behaviour_logits, f32, 'behaviour_logits')
+  act = _lib.require_cuda(actions, torch.int64, 'actions')
+  rew = _lib.require_cuda(rewards, f32, 'rewards')
+  dn = _lib.require_cuda(done, torch.bool, 'done')
+  ecp = _lib.require_cuda(entropy_cost_param, f32, 'entropy_cost_param')
+  if ll.dim() != 3 or lb.dim() != 2:
+    raise ValueError('learner outputs must be [T+1,B,A] and [T+1,B]')
+  T1, B, A = (int(x) for x in ll.shape)
+  for t, shp, nm in ((lb, (T1, B), 'learner_baseline'), (bl, (T1, B, A), 'behaviour_logits'),
+                     (act, (T1, B), 'actions'), (rew, (T1, B), 'rewards'), (dn, (T1, B), 'done')):
+    if tuple(t.shape) != shp:
+      raise ValueError('%s has shape %s, expected %s' % (nm, tuple(t.shape), shp))
+  dev = ll.device
+  cfg = _lib.LossConfig(
+      settings.discounting, settings.lambda_, settings.baseline_cost, settings.kl_cost,
+      settings.max_abs_reward or 0.0, 1.0, 1.0,     # compute_loss uses vtrace's default clips
+      settings.target_entropy or 0.0, 1 if settings.target_entropy else 0,
+      settings.entropy_cost_adjustment_speed)
+  out = dict(
+      loss_terms=torch.empty(_lib.LOSS_TERMS, dtype=f32, device=dev),
+      dlogits=torch.empty_like(ll), dbaseline=torch.empty_like(lb),
+      d_entropy_cost_param=torch.empty((), dtype=f32, device=dev),
+      vs=torch.empty([T1 - 1, B], dtype=f32, device=dev) if want_vtrace else None,
+      pg_advantages=torch.empty([T1 - 1, B], dtype=f32, device=dev) if want_vtrace else None)
+  import ctypes
+  _lib.check(_lib.lib().seedrl_vtrace_loss_fwd_bwd(
+      T1, B, A, _lib.ptr(ll), _lib.ptr(lb), _lib.ptr(bl), _lib.ptr(act), _lib.ptr(rew),
+      _lib.ptr(dn), ctypes.byref(cfg), _lib.ptr(ecp), _lib.ptr(out['loss_terms']),
+      _lib.ptr(out['dlogits']), _lib.ptr(out['dbaseline']),
+      _lib.ptr(out['d_entropy_cost_param']), _lib.ptr(out['vs']),
+      _lib.ptr(out['pg_advantages']), _lib.ptr(_loss_scratch(T1, B, A, dev)),
+      _lib.stream_ptr()))
+  return out
+
+
+def compute_loss(logger, parametric_action_distribution, agent, agent_state,
+                 prev_actions, env_outputs, agent_outputs, settings=None):
+  """reference learner.py:73-159.  Returns (total_loss, log session).  The gradient of
+  total_loss w.r.t. the network outputs is left on the agent for `minimize`."""
+  settings = settings or loss_settings_from_flags()
+  learner_outputs, _ = agent(prev_actions, env_outputs, agent_state,
+                             unroll=True, is_training=True)                 # :75-79
+  r = vtrace_loss_fwd_bwd(settings, learner_outputs.policy_logits, learner_outputs.baseline,
+                          agent_outputs.policy_logits, agent_outputs.action,
+                          env_outputs[0], env_outputs[1], agent.entropy_cost_param)
+  agent._loss_grads = r
+  logger = logger or _NullLogger()
+  session = logger.log_session()
+  lt = r['loss_terms']
+  for name, key in _LOG_NAMES:
+    logger.log(session, name, lt[_lib.LT[key]])
+  return lt[_lib.LT['total']], session
+
+
+Unroll = collections.namedtuple(
+    'Unroll', 'agent_state prev_actions env_outputs agent_outputs')
+
+
+class LearnerStep(object):
+  """`minimize` of reference learner.py:255-280 for one replica (= one GPU/process)."""
+
+  def __init__(self, agent, optimizer, parametric_action_distribution=None, settings=None,
+               logger=None, process_group=None, grad_reduce='sum'):
+    self.agent = agent
+    self.optimizer = optimizer
+    self.dist = parametric_action_distribution
+    self.settings = settings or default_loss_settings()
+    self.logger = logger
+    self.pg = process_group
+    self.grad_reduce = grad_reduce
+    import torch.distributed as td
+    self.world = td.get_world_size(process_group) if (td.is_available() and td.is_initialized()) else 1
+    if not hasattr(agent, '_entropy_mul'):
+      agent.init_entropy_cost(self.settings.entropy_cost,
+                              self.settings.entropy_cost_adjustment_speed)       # :225-234
+    optimizer._create_slots(agent.params)                                        # :244-245
+    self.last_loss_terms = None
+
+  def compute_gradients(self, unroll):
+    loss, logs = compute_loss(self.logger, self.dist, self.agent, unroll.agent_state,
+                              unroll.prev_actions, unroll.env_outputs, unroll.agent_outputs,
+                              self.settings)
+    r = self.agent._loss_grads
+    grads = self.agent.backward(r['dlogits'], r['dbaseline'])                     # :264
+    grads[self.agent.entropy_cost_param_index] = r['d_entropy_cost_param']
+    self.last_loss_terms = r['loss_terms']
+    return loss, logs
+
+  def apply_gradients(self):
+    grads = self.agent.grads
+    scale = 1.0
+    if self.world > 1:
+      import torch.distributed as td
+      # ONE collective per step: SUM over replicas (reference tests/utils_test.py:640-650)
+      td.all_reduce(grads, op=td.ReduceOp.SUM, group=self.pg)
+      if self.grad_reduce == 'mean':
+        scale = 1.0 / self.world
+    mul = self.settings.entropy_cost_adjustment_speed
+    self.optimizer.apply_gradients(
+        self.agent.params, grads, grad_scale=scale,
+        clamp_index=self.agent.entropy_cost_param_index,
+        clamp_lo=-20.0 / mul, clamp_hi=20.0 / mul)                                # :229-231
+
+  def minimize(self, unroll):
+    loss, logs = self.compute_gradients(unroll)
+    self.apply_gradients()
+    return loss, logs

@@ -1,0 +1,338 @@
+"""Runtime utilities on the hot path -- mirror of the reference's `common/utils.py`
+for the pieces the V-trace learner uses:
+
+  EnvOutput                     utils.py:41-42
+  UnrollStore                   utils.py:119-257   (GPU-resident, scatter/gather kernels)
+  Aggregator                    utils.py:461-543   (GPU-resident tables)
+  StructuredFIFOQueue           utils.py:680-711   (host queue of GPU-resident nests)
+  batch_apply / make_time_major utils.py:714-761   (views; no data movement)
+  validate_learner_config       utils.py:989-1002
+
+PrioritizedReplay / HER / TPU encode are out of scope.
+"""
+import collections
+import threading
+
+import numpy as np
+import torch
+
+from seed_rl_b200 import _lib
+
+EnvOutput = collections.namedtuple(
+    'EnvOutput', 'reward done observation abandoned episode_step')
+
+TensorSpec = collections.namedtuple('TensorSpec', 'shape dtype name')
+TensorSpec.__new__.__defaults__ = (None,)
+
+
+# ---- a minimal tf.nest -----------------------------------------------------------
+def _is_leaf(x):
+  return isinstance(x, TensorSpec) or not isinstance(x, (tuple, list))
+
+
+def flatten(nest):
+  if _is_leaf(nest):
+    return [nest]
+  out = []
+  for e in nest:
+    out.extend(flatten(e))
+  return out
+
+
+def pack_sequence_as(structure, flat):
+  it = iter(flat)
+
+  def rec(s):
+    if _is_leaf(s):
+      return next(it)
+    vals = [rec(e) for e in s]
+    if hasattr(s, '_fields'):
+      return type(s)(*vals)
+    return type(s)(vals)
+
+  out = rec(structure)
+  return out
+
+
+def map_structure(fn, *nests):
+  flats = [flatten(n) for n in nests]
+  for f in flats[1:]:
+    if len(f) != len(flats[0]):
+      raise ValueError("The two structures don't have the same nested structure.")
+  return pack_sequence_as(nests[0], [fn(*xs) for xs in zip(*flats)])
+
+
+def assert_same_structure(a, b):
+  if len(flatten(a)) != len(flatten(b)):
+    raise ValueError("The two structures don't have the same nested structure.")
+
+
+_TORCH_DTYPES = {
+    'float32': torch.float32, 'float64': torch.float64, 'int32': torch.int32,
+    'int64': torch.int64, 'uint8': torch.uint8, 'bool': torch.bool, 'int8': torch.int8,
+}
+
+
+def as_torch_dtype(d):
+  if isinstance(d, torch.dtype):
+    return d
+  return _TORCH_DTYPES[np.dtype(d).name]
+
+
+def _ids_to_device(env_ids, device):
+  """Returns (int32 cuda tensor, host numpy copy or None)."""
+  host = None
+  if isinstance(env_ids, torch.Tensor):
+    if env_ids.device.type != 'cuda':
+      host = env_ids.numpy()
+  else:
+    host = np.asarray(env_ids)
+  if host is not None:
+    dev = torch.as_tensor(host.astype(np.int32)).to(device, non_blocking=True)
+  else:
+    dev = env_ids.to(torch.int32)
+  return dev.contiguous(), host
+
+
+def _check_no_duplicates(env_ids_dev, env_ids_host, what):
+  if env_ids_host is not None:
+    dup = len(np.unique(env_ids_host)) != len(env_ids_host)
+  else:
+    dup = torch.unique(env_ids_dev).numel() != env_ids_dev.numel()
+  if dup:
+    # tf.debugging.assert_equal(..., message=...), utils.py:173-176 / 533-540
+    raise ValueError('Duplicate environment ids in %s' % what)
+
+
+class UnrollStore(object):
+  """Combines individual environment steps into unrolls (reference utils.py:119-257),
+  with the per-env ring buffers resident in HBM."""
+
+  def __init__(self, num_envs, unroll_length, timestep_specs,
+               num_overlapping_steps=0, name='UnrollStore', device='cuda',
+               time_major=False):
+    self.name = name
+    self._specs = timestep_specs
+    self._flat_specs = flatten(timestep_specs)
+    self._full_length = num_overlapping_steps + unroll_length + 1     # :129
+    self._unroll_length = unroll_length
+    self._num_overlapping_steps = num_overlapping_steps
+    self._num_envs = num_envs
+    self._time_major = time_major
+    self._device = torch.device(device)
+    self._state = [
+        torch.zeros([num_envs, self._full_length] + list(s.shape),
+                    dtype=as_torch_dtype(s.dtype), device=self._device)
+        for s in self._flat_specs]                                    # :131-139
+    self._index = torch.full([num_envs], num_overlapping_steps, dtype=torch.int32,
+                             device=self._device)                     # :142-145
+    self._completed = torch.empty([num_envs], dtype=torch.int32, device=self._device)
+    self._ncomp = torch.zeros([1], dtype=torch.int32, device=self._device)
+
+  @property
+  def unroll_specs(self):
+    return map_structure(
+        lambda s: TensorSpec([self._full_length] + list(s.shape), s.dtype, s.name),
+        self._specs)
+
+  def _row_bytes(self, i):
+    s = self._state[i]
+    return int(s[0, 0].numel()) * s.element_size()
+
+  def append(self, env_ids, values, check_duplicates=True):
+    """Appends values; returns (completed env ids int64 [n], completed unrolls)."""
+    L = _lib.lib()
+    ids, host = _ids_to_device(env_ids, self._device)
+    if check_duplicates:
+      _check_no_duplicates(ids, host, 'store %s' % self.name)
+    flat_values = flatten(values)
+    assert_same_structure(values, self._specs)
+    n = int(ids.numel())
+    st = _lib.stream_ptr()
+    keep = []
+    for i, (s, v) in enumerate(zip(self._state, flat_values)):
+      v = _lib.require_cuda(v, s.dtype, 'values')
+      if v.shape[0] != n:                                             # :178-184
+        raise ValueError('Batch dimension must equal the number of environments in store %s.'
+                         % self.name)
+      keep.append(v)
+      _lib.check(L.seedrl_store_append_field(
+          _lib.ptr(s), _lib.ptr(self._index), _lib.ptr(ids), n, self._full_length,
+          self._row_bytes(i), _lib.ptr(v), st))                       # :187-190
+    _lib.check(L.seedrl_store_advance(
+        _lib.ptr(self._index), _lib.ptr(ids), n, self._full_length,
+        _lib.ptr(self._completed), _lib.ptr(self._ncomp), st))        # :194
+    return self._complete_unrolls()
+
+  def _complete_unrolls(self):
+    L = _lib.lib()
+    st = _lib.stream_ptr()
+    nc = int(self._ncomp.item())        # the only host sync: sizes the outputs
+    done_ids = self._completed[:nc]
+    unrolls = []
+    for i, s in enumerate(self._state):
+      tail = list(s.shape[2:])
+      shape = ([self._full_length, nc] if self._time_major else [nc, self._full_length]) + tail
+      u = torch.empty(shape, dtype=s.dtype, device=self._device)
+      _lib.check(L.seedrl_store_gather_field(
+          _lib.ptr(s), _lib.ptr(done_ids), nc, self._full_length, self._row_bytes(i),
+          self._num_overlapping_steps, 1 if self._time_major else 0, _lib.ptr(u), st))
+      unrolls.append(u)
+    _lib.check(L.seedrl_store_finish(_lib.ptr(self._index), _lib.ptr(done_ids), nc,
+                                     self._num_overlapping_steps, st))
+    return done_ids.to(torch.int64), pack_sequence_as(self._specs, unrolls)
+
+  def reset(self, env_ids):
+    """Reset after actor preemption (reference utils.py:198-225)."""
+    L = _lib.lib()
+    ids, _ = _ids_to_device(env_ids, self._device)
+    n = int(ids.numel())
+    if n == 0:
+      return
+    st = _lib.stream_ptr()
+    _lib.check(L.seedrl_store_reset(None, _lib.ptr(self._index), _lib.ptr(ids), n,
+                                    self._full_length, 0, self._num_overlapping_steps, st))
+    for i, s in enumerate(self._state):
+      _lib.check(L.seedrl_store_reset(_lib.ptr(s), None, _lib.ptr(ids), n, self._full_length,
+                                      self._row_bytes(i), self._num_overlapping_steps, st))
+
+
+class Aggregator(object):
+  """Per-environment state tables (reference utils.py:461-543), kept as HBM-resident
+  tensors; reset/add/read/replace are single indexed row operations."""
+
+  def __init__(self, num_envs, specs, name='Aggregator', device='cuda'):
+    self.name = name
+    self._specs = specs
+    self._device = torch.device(device)
+    self._state = [
+        torch.zeros([num_envs] + list(s.shape), dtype=as_torch_dtype(s.dtype),
+                    device=self._device) for s in flatten(specs)]
+
+  def _ids(self, env_ids):
+    if isinstance(env_ids, torch.Tensor):
+      return env_ids.to(self._device).long()
+    return torch.as_tensor(np.asarray(env_ids, np.int64)).to(self._device)
+
+  def reset(self, env_ids):                                           # :481-485
+    ids = self._ids(env_ids)
+    for s in self._state:
+      s[ids] = 0
+
+  def add(self, env_ids, values):                                     # :488-501
+    assert_same_structure(values, self._specs)
+    ids = self._ids(env_ids)
+    for s, v in zip(self._state, flatten(values)):
+      v = torch.as_tensor(v, device=self._device).to(s.dtype)
+      if v.dim() < s.dim():
+        v = v.expand([ids.numel()] + list(s.shape[1:]))
+      s.index_add_(0, ids, v.contiguous())
+
+  def read(self, env_ids):                                            # :504-516
+    ids = self._ids(env_ids)
+    return pack_sequence_as(self._specs, [s.index_select(0, ids) for s in self._state])
+
+  def replace(self, env_ids, values, debug_op_name='', debug_tensors=None):  # :519-543
+    ids = self._ids(env_ids)
+    if ids.dim() != 1:
+      raise ValueError('Invalid rank for aggregator %s' % self.name)
+    if torch.unique(ids).numel() != ids.numel():
+      raise ValueError('Duplicate environment ids in Aggregator: %s with op name "%s"' %
+                       (self.name, debug_op_name))
+    assert_same_structure(values, self._specs)
+    for s, v in zip(self._state, flatten(values)):
+      v = torch.as_tensor(v, device=self._device).to(s.dtype)
+      if v.dim() < s.dim():
+        v = v.expand([ids.numel()] + list(s.shape[1:]))
+      s[ids] = v
+
+
+class QueueClosedError(RuntimeError):
+  """tf.errors.CancelledError analogue for a closed queue."""
+
+
+class StructuredFIFOQueue(object):
+  """FIFO of nests (reference utils.py:680-711 over tf.queue.FIFOQueue).  Elements
+  stay wherever their tensors live (HBM); capacity gives the same back-pressure as
+  the reference's capacity-1 unroll queue (learner.py:336).  capacity -1 = unbounded."""
+
+  def __init__(self, capacity, specs, shared_name=None, name='structured_fifo_queue'):
+    self._specs = specs
+    self._capacity = capacity
+    self._q = collections.deque()
+    self._cv = threading.Condition()
+    self._closed = False
+
+  def size(self):
+    with self._cv:
+      return len(self._q)
+
+  def close(self, cancel_pending_enqueues=True):
+    with self._cv:
+      self._closed = True
+      self._cv.notify_all()
+
+  def enqueue(self, vals, name=None):
+    assert_same_structure(vals, self._specs)
+    with self._cv:
+      while self._capacity > 0 and len(self._q) >= self._capacity and not self._closed:
+        self._cv.wait()
+      if self._closed:
+        raise QueueClosedError('Queue is closed.')
+      self._q.append(vals)
+      self._cv.notify_all()
+
+  def enqueue_many(self, vals, name=None):
+    assert_same_structure(vals, self._specs)
+    flat = flatten(vals)
+    n = int(flat[0].shape[0]) if flat else 0
+    for i in range(n):
+      self.enqueue(pack_sequence_as(self._specs, [f[i] for f in flat]))
+
+  def dequeue(self, name=None):
+    with self._cv:
+      while not self._q and not self._closed:
+        self._cv.wait()
+      if not self._q:
+        raise QueueClosedError('Queue is closed and empty.')
+      v = self._q.popleft()
+      self._cv.notify_all()
+      return v
+
+  def dequeue_many(self, batch_size, name=None):
+    items = [self.dequeue() for _ in range(batch_size)]
+    return map_structure(lambda *xs: torch.stack([torch.as_tensor(x) for x in xs]), *items)
+
+
+def batch_apply(fn, inputs):
+  """Folds time into batch, runs fn, unfolds (reference utils.py:714-732)."""
+  flat = flatten(inputs)
+  T = int(flat[0].shape[0])
+  batched = map_structure(lambda t: t.reshape([-1] + list(t.shape[2:])), inputs)
+  output = fn(*batched)
+  return map_structure(lambda t: t.reshape([T, -1] + list(t.shape[1:])), output)
+
+
+def make_time_major(x):
+  """Transposes batch and time (reference utils.py:735-761); rank<2 passes through."""
+  def transpose(t):
+    if t.dim() < 2:
+      return t
+    return t.transpose(0, 1).contiguous()
+  return map_structure(transpose, x)
+
+
+def validate_learner_config(config, num_hosts=1):
+  """reference utils.py:989-1002."""
+  assert config.num_envs > 0
+  assert config.env_batch_size > 0
+  if config.inference_batch_size == -1:
+    config.inference_batch_size = max(config.env_batch_size,
+                                      config.num_envs // (2 * num_hosts))
+  assert config.inference_batch_size > 0
+  assert config.inference_batch_size % config.env_batch_size == 0, (
+      'Learner-side batch size (=%d) must be exact multiple of the '
+      'actor-side batch size (=%d).' %
+      (config.inference_batch_size, config.env_batch_size))
+  assert config.num_envs >= config.inference_batch_size * num_hosts, (
+      'Inference batch size is bigger than the number of environments.')

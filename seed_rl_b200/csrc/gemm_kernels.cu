@@ -1,0 +1,272 @@
+// Dense / LSTM kernels (fp32 SIMT path) for dmlab/networks.py:105-118,157-169:
+// Dense(256)+ReLU, the Keras LSTMCell(256) unrolled over time with done-resets,
+// policy/baseline heads -- forward and backward.
+#include "kernels.h"
+
+namespace seedrl {
+
+// ---------------------------------------------------------------------------
+// C[M,N] (=|+=) op(A)[M,K] * op(B)[K,N]   row-major, leading dims lda/ldb/ldc.
+//   TA: A is stored [K,M] (C = A^T B).   TB: B is stored [N,K] (C = A B^T).
+//   a_relu: relu applied to A elements on load.
+//   epilogue: + bias[n]; relu; keep only where mask[m*ldm+n] > 0; accumulate.
+// 64x64x16 tiles, 256 threads, 4x4 outputs per thread.
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
+             const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc, GemmEpi e) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int tx = tid & 15, ty = tid >> 4;   // 16 x 16 threads, each 4x4
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < K; k0 += BK) {
+    // load A tile (BM x BK): 1024 elements, 4 per thread
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int idx = tid + r * 256;
+      int m, k;
+      if (TA) { m = idx & 63; k = idx >> 6; }       // m fastest (contiguous in memory)
+      else    { k = idx & 15; m = idx >> 4; }       // k fastest
+      const int gm = m0 + m, gk = k0 + k;
+      float v = 0.f;
+      if (gm < M && gk < K) v = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+      if (e.a_relu) v = fmaxf(v, 0.f);
+      As[k][m] = v;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int idx = tid + r * 256;
+      int n, k;
+      if (TB) { k = idx & 15; n = idx >> 4; }       // B stored [N,K]: k fastest
+      else    { n = idx & 63; k = idx >> 6; }       // B stored [K,N]: n fastest
+      const int gn = n0 + n, gk = k0 + k;
+      float v = 0.f;
+      if (gn < N && gk < K) v = TB ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
+      Bs[k][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn >= N) continue;
+      float v = acc[i][j];
+      if (e.bias) v += e.bias[gn];
+      if (e.relu) v = fmaxf(v, 0.f);
+      if (e.mask) v = e.mask[(size_t)gm * e.ldm + gn] > 0.f ? v : 0.f;
+      float* c = C + (size_t)gm * ldc + gn;
+      *c = e.accumulate ? *c + v : v;
+    }
+  }
+}
+
+int sgemm(bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+          float* C, int ldc, const GemmEpi& e, cudaStream_t st) {
+  if (M <= 0 || N <= 0) return SEEDRL_OK;
+  dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
+  if (!ta && !tb) sgemm_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, e);
+  else if (ta && !tb) sgemm_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, e);
+  else if (!ta && tb) sgemm_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, e);
+  else sgemm_kernel<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, e);
+  count_launch();
+  SEEDRL_CHECK_LAUNCH();
+  return SEEDRL_OK;
+}
+
+// out[n] = sum_m X[m*ld + n], m < M, n < N.  One CTA per 32 columns; fixed-order
+// (deterministic) reduction.
+__global__ void colsum_kernel(int M, int N, const float* __restrict__ X, int ld,
+                              float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;   // 8 warps
+  const int n = blockIdx.x * 32 + lane;
+  float s = 0.f;
+  if (n < N)
+    for (int m = w; m < M; m += 8) s += X[(size_t)m * ld + n];
+  red[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][lane];
+    out[n] = t;
+  }
+}
+
+int colsum(int M, int N, const float* X, int ld, float* out, cudaStream_t st) {
+  colsum_kernel<<<ceil_div(N, 32), 256, 0, st>>>(M, N, X, ld, out);
+  count_launch();
+  SEEDRL_CHECK_LAUNCH();
+  return SEEDRL_OK;
+}
+
+// ---------------------------------------------------------------------------
+// torso tail, dmlab/networks.py:111-114: core_in[n] = concat(dense_out[n] (256, already
+// relu'd), clip(reward[n], -1, 1), one_hot(prev_action[n], A)).
+__global__ void core_input_tail_kernel(int Nrows, int D, int A, const float* __restrict__ reward,
+                                       const int64_t* __restrict__ prev_action,
+                                       float* __restrict__ core_in /* [N, D+1+A] */) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int W = 1 + A;
+  if (i >= Nrows * W) return;
+  const int n = i / W, j = i - n * W;
+  float v;
+  if (j == 0) v = fminf(fmaxf(reward[n], -1.f), 1.f);
+  else v = (prev_action[n] == (int64_t)(j - 1)) ? 1.f : 0.f;
+  core_in[(size_t)n * (D + W) + D + j] = v;
+}
+
+int core_input_tail(int Nrows, int D, int A, const float* reward, const int64_t* prev_action,
+                    float* core_in, cudaStream_t st) {
+  const int n = Nrows * (1 + A);
+  core_input_tail_kernel<<<ceil_div(n, 256), 256, 0, st>>>(Nrows, D, A, reward, prev_action, core_in);
+  count_launch();
+  SEEDRL_CHECK_LAUNCH();
+  return SEEDRL_OK;
+}
+
+// ---------------------------------------------------------------------------
+// LSTM.  Keras LSTMCell: z = x W + h U + b (gate order i,f,c,o), c' = s(f) c + s(i) tanh(g),
+// h' = s(o) tanh(c').  dmlab/networks.py:160-167: state is reset to zero where done[t]
+// BEFORE consuming step t.
+//
+// hprev_masked[b, :] = done[b] ? 0 : h_src[b, :]
+__global__ void lstm_mask_state_kernel(int B, int Hd, const uint8_t* __restrict__ done,
+                                       const float* __restrict__ h_src, float* __restrict__ h_dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Hd) return;
+  const int b = i / Hd;
+  h_dst[i] = done[b] ? 0.f : h_src[i];
+}
+
+// Pointwise part of step t.  z [B,4H] holds x W + b + h U on entry and the ACTIVATED gates
+// (i,f,g,o) on exit (kept for backward).  c_prev_src is the unmasked previous cell state.
+// Also emits hprev_next = done_next ? 0 : h (the masked recurrent input of step t+1).
+__global__ void lstm_pointwise_fwd_kernel(int B, int Hd, float* __restrict__ z,
+                                          const float* __restrict__ c_prev_src,
+                                          const uint8_t* __restrict__ done_t,
+                                          const uint8_t* __restrict__ done_next,
+                                          float* __restrict__ c_out, float* __restrict__ h_out,
+                                          float* __restrict__ hprev_next) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Hd) return;
+  const int b = i / Hd, u = i - b * Hd;
+  float* zb = z + (size_t)b * 4 * Hd;
+  const float gi = sigmoidf_(zb[u]);
+  const float gf = sigmoidf_(zb[Hd + u]);
+  const float gg = tanhf(zb[2 * Hd + u]);
+  const float go = sigmoidf_(zb[3 * Hd + u]);
+  const float cp = done_t[b] ? 0.f : c_prev_src[i];
+  const float c = gf * cp + gi * gg;
+  const float h = go * tanhf(c);
+  zb[u] = gi; zb[Hd + u] = gf; zb[2 * Hd + u] = gg; zb[3 * Hd + u] = go;
+  c_out[i] = c;
+  h_out[i] = h;
+  if (hprev_next) hprev_next[i] = (done_next && done_next[b]) ? 0.f : h;
+}
+
+// Backward pointwise of step t.
+//   dh = dh_out[t] + (done_next ? 0 : dh_rec)        dh_rec = dZ[t+1] U^T (may be null at t=T)
+//   dc = (done_next ? 0 : dc_next) + dh * o * (1 - tanh(c)^2)
+//   dZ[t] = (di, df, dg, do) pre-activation; dc_prev_out = dc * f (unmasked; the consumer masks)
+__global__ void lstm_pointwise_bwd_kernel(int B, int Hd, const float* __restrict__ gates,
+                                          const float* __restrict__ c_t,
+                                          const float* __restrict__ c_prev_src,
+                                          const uint8_t* __restrict__ done_t,
+                                          const uint8_t* __restrict__ done_next,
+                                          const float* __restrict__ dh_out,
+                                          const float* __restrict__ dh_rec,
+                                          const float* __restrict__ dc_next,
+                                          float* __restrict__ dz, float* __restrict__ dc_prev_out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Hd) return;
+  const int b = i / Hd, u = i - b * Hd;
+  const float* gb = gates + (size_t)b * 4 * Hd;
+  const float gi = gb[u], gf = gb[Hd + u], gg = gb[2 * Hd + u], go = gb[3 * Hd + u];
+  const bool cut = done_next && done_next[b];
+  float dh = dh_out[i];
+  if (dh_rec && !cut) dh += dh_rec[i];
+  const float tc = tanhf(c_t[i]);
+  float dc = dh * go * (1.f - tc * tc);
+  if (dc_next && !cut) dc += dc_next[i];
+  const float cp = done_t[b] ? 0.f : c_prev_src[i];
+  float* dzb = dz + (size_t)b * 4 * Hd;
+  dzb[u] = dc * gg * gi * (1.f - gi);
+  dzb[Hd + u] = dc * cp * gf * (1.f - gf);
+  dzb[2 * Hd + u] = dc * gi * (1.f - gg * gg);
+  dzb[3 * Hd + u] = dh * tc * go * (1.f - go);
+  dc_prev_out[i] = dc * gf;
+}
+
+int lstm_mask_state(int B, int Hd, const uint8_t* done, const float* h_src, float* h_dst,
+                    cudaStream_t st) {
+  lstm_mask_state_kernel<<<ceil_div(B * Hd, 256), 256, 0, st>>>(B, Hd, done, h_src, h_dst);
+  count_launch();
+  SEEDRL_CHECK_LAUNCH();
+  return SEEDRL_OK;
+}
+int lstm_pointwise_fwd(int B, int Hd, float* z, const float* c_prev_src, const uint8_t* done_t,
+                       const uint8_t* done_next, float* c_out, float* h_out, float* hprev_next,
+                       cudaStream_t st) {
+  lstm_pointwise_fwd_kernel<<<ceil_div(B * Hd, 256), 256, 0, st>>>(B, Hd, z, c_prev_src, done_t,
+                                                                   done_next, c_out, h_out, hprev_next);
+  count_launch();
+  SEEDRL_CHECK_LAUNCH();
+  return SEEDRL_OK;
+}
+int lstm_pointwise_bwd(int B, int Hd, const float* gates, const float* c_t, const float* c_prev_src,
+                       const uint8_t* done_t, const uint8_t* done_next, const float* dh_out,
+                       const float* dh_rec, const float* dc_next, float* dz, float* dc_prev_out,
+                       cudaStream_t st) {
+  lstm_pointwise_bwd_kernel<<<ceil_div(B * Hd, 256), 256, 0, st>>>(
+      B, Hd, gates, c_t, c_prev_src, done_t, done_next, dh_out, dh_rec, dc_next, dz, dc_prev_out);
+  count_launch();
+  SEEDRL_CHECK_LAUNCH();
+  return SEEDRL_OK;
+}
+
+// generic helpers ------------------------------------------------------------
+__global__ void fill_kernel(size_t n, float* p, float v) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+int fill(size_t n, float* p, float v, cudaStream_t st) {
+  if (n == 0) return SEEDRL_OK;
+  fill_kernel<<<(unsigned)ceil_div_sz(n, 256), 256, 0, st>>>(n, p, v);
+  count_launch();
+  SEEDRL_CHECK_LAUNCH();
+  return SEEDRL_OK;
+}
+
+// out[n] = baseline column of heads? (kept simple: strided copy)  dst[i] = src[i*ld + col]
+__global__ void copy_col_kernel(int n, const float* __restrict__ src, int ld, int col,
+                                float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[(size_t)i * ld + col];
+}
+
+}  // namespace seedrl

@@ -1,0 +1,504 @@
+// (a5) Policy network graph: dmlab/networks.py:63-171 ImpalaDeep (and the IMPALA-paper
+// shallow net) as a fixed schedule of this library's kernels -- forward unroll
+// (_torso folded over T*B by batch_apply, utils.py:714-732; LSTM over T with
+// done-resets; heads) and the matching backward (what tf.GradientTape computes at
+// agents/vtrace/learner.py:261-264).
+//
+// Parameters: one flat fp32 arena, tensors in tf.Module.trainable_variables order
+// (_baseline, _conv_to_linear, _core, _policy_logits, _stacks...), Keras layouts,
+// every tensor start aligned to 64 floats (256 B), then the scalar entropy_cost_param
+// (learner.py:225-234).
+#include <string.h>
+
+#include <vector>
+
+#include "kernels.h"
+
+namespace seedrl {
+
+constexpr int kHidden = 256;   // LSTMCell(256), Dense(256)
+constexpr size_t kAlignFloats = 64;
+
+struct ParamInfo {
+  std::string name;
+  int rank;
+  int64_t dims[4];
+  size_t offset;   // floats
+  size_t size;     // floats
+};
+
+struct ConvLayer {
+  int cin, cout;
+  int w, b;        // param indices
+};
+struct Stack {
+  int hin, win, cin, c, hout, wout;
+  ConvLayer conv, r00, r01, r10, r11;
+};
+
+}  // namespace seedrl
+
+struct seedrl_net {
+  seedrl_net_config cfg;
+  std::vector<seedrl::ParamInfo> params;   // network tensors, then entropy_cost_param
+  size_t arena_floats;
+  size_t logical_params;
+  int p_base_w, p_base_b, p_dense_w, p_dense_b, p_core_w, p_core_u, p_core_b, p_pol_w, p_pol_b;
+  std::vector<seedrl::Stack> stacks;       // deep
+  int sh_c0w, sh_c0b, sh_c1w, sh_c1b;      // shallow
+  int sh_h1, sh_w1, sh_h2, sh_w2;
+  int flat;                                // conv features fed to Dense(256)
+  int core_in;                             // 256 + 1 + A
+};
+
+namespace seedrl {
+
+static int add_param(seedrl_net* n, const std::string& name, std::initializer_list<int64_t> dims) {
+  ParamInfo p;
+  p.name = name;
+  p.rank = (int)dims.size();
+  size_t sz = 1;
+  int i = 0;
+  for (int64_t d : dims) { p.dims[i++] = d; sz *= (size_t)d; }
+  for (; i < 4; ++i) p.dims[i] = 1;
+  p.size = sz;
+  p.offset = n->arena_floats;
+  n->arena_floats += (sz + kAlignFloats - 1) / kAlignFloats * kAlignFloats;
+  n->params.push_back(p);
+  return (int)n->params.size() - 1;
+}
+
+static ConvLayer add_conv(seedrl_net* n, const std::string& prefix, int k, int cin, int cout) {
+  ConvLayer l;
+  l.cin = cin; l.cout = cout;
+  l.w = add_param(n, prefix + "/kernel", {k, k, cin, cout});
+  l.b = add_param(n, prefix + "/bias", {cout});
+  return l;
+}
+
+// ---- workspace plan -----------------------------------------------------------
+struct Bump {
+  size_t off = 0;
+  size_t take(size_t bytes) {
+    const size_t o = off;
+    off += (bytes + 255) / 256 * 256;
+    return o;
+  }
+};
+
+struct StackBufs { size_t a0, p, idx, c0, o0, c1, o1; };
+
+struct Plan {
+  int N;                       // T1 * B frames
+  std::vector<StackBufs> st;
+  size_t sh_a1, sh_a2;         // shallow conv outputs (post-relu)
+  size_t xc, z, hp, cs, hs, c0buf;
+  // backward scratch
+  size_t dhs, dz, dhrec, dc0, dc1, dd, gA, gB, gC, gFull, wt, partial;
+  size_t total;
+};
+
+static Plan make_plan(const seedrl_net* n, int T1, int B) {
+  Plan p;
+  Bump b;
+  const size_t N = (size_t)T1 * B;
+  p.N = (int)N;
+  size_t pooled_max = 0, full_max = 0;
+  if (n->cfg.net == SEEDRL_NET_DEEP) {
+    for (const Stack& s : n->stacks) {
+      StackBufs sb;
+      const size_t full = N * s.hin * s.win * s.c, pooled = N * s.hout * s.wout * s.c;
+      sb.a0 = b.take(full * 4);
+      sb.p = b.take(pooled * 4);
+      sb.idx = b.take(pooled);
+      sb.c0 = b.take(pooled * 4);
+      sb.o0 = b.take(pooled * 4);
+      sb.c1 = b.take(pooled * 4);
+      sb.o1 = b.take(pooled * 4);
+      p.st.push_back(sb);
+      if (pooled > pooled_max) pooled_max = pooled;
+      if (full > full_max) full_max = full;
+    }
+    p.sh_a1 = p.sh_a2 = 0;
+  } else {
+    const size_t a1 = N * n->sh_h1 * n->sh_w1 * 16, a2 = N * n->sh_h2 * n->sh_w2 * 32;
+    p.sh_a1 = b.take(a1 * 4);
+    p.sh_a2 = b.take(a2 * 4);
+    pooled_max = a1 > a2 ? a1 : a2;
+    full_max = 0;
+  }
+  p.xc = b.take(N * n->core_in * 4);
+  p.z = b.take(N * 4 * kHidden * 4);
+  p.hp = b.take(N * kHidden * 4);
+  p.cs = b.take(N * kHidden * 4);
+  p.hs = b.take(N * kHidden * 4);
+  p.c0buf = b.take((size_t)B * kHidden * 4);
+  p.dhs = b.take(N * kHidden * 4);
+  p.dz = b.take(N * 4 * kHidden * 4);
+  p.dhrec = b.take((size_t)B * kHidden * 4);
+  p.dc0 = b.take((size_t)B * kHidden * 4);
+  p.dc1 = b.take((size_t)B * kHidden * 4);
+  p.dd = b.take(N * kHidden * 4);
+  p.gA = b.take(pooled_max * 4);
+  p.gB = b.take(pooled_max * 4);
+  p.gC = b.take(pooled_max * 4);
+  p.gFull = b.take(full_max * 4);
+  p.wt = b.take(64 * 1024 * 4);
+  p.partial = b.take(conv3x3_wgrad_partial_bytes());
+  p.total = b.off;
+  return p;
+}
+
+#define SEEDRL_TRY(expr)              \
+  do {                                \
+    const int rc__ = (expr);          \
+    if (rc__ != SEEDRL_OK) return rc__; \
+  } while (0)
+
+static inline const float* P(const seedrl_net* n, const float* arena, int idx) {
+  return arena + n->params[idx].offset;
+}
+static inline float* G(const seedrl_net* n, float* arena, int idx) {
+  return arena + n->params[idx].offset;
+}
+template <typename T>
+static inline T* W(void* ws, size_t off) {
+  return reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + off);
+}
+
+}  // namespace seedrl
+
+using namespace seedrl;
+
+extern "C" int seedrl_net_create(const seedrl_net_config* cfg, seedrl_net** out) {
+  SEEDRL_CHECK_ARG(cfg && out, "null pointer");
+  SEEDRL_CHECK_ARG(cfg->net == SEEDRL_NET_DEEP || cfg->net == SEEDRL_NET_SHALLOW, "unknown net");
+  SEEDRL_CHECK_ARG(cfg->num_actions >= 1 && cfg->obs_h > 0 && cfg->obs_w > 0, "bad shape");
+  seedrl_net* n = new seedrl_net();
+  n->cfg = *cfg;
+  n->arena_floats = 0;
+  const int A = cfg->num_actions;
+  n->core_in = kHidden + 1 + A;
+  // tf.Module order: _baseline, _conv_to_linear, _core, _policy_logits, _stacks
+  n->p_base_w = add_param(n, "baseline/kernel", {kHidden, 1});
+  n->p_base_b = add_param(n, "baseline/bias", {1});
+  int flat = 0;
+  if (cfg->net == SEEDRL_NET_DEEP) {
+    if (cfg->obs_c != 4) {
+      delete n;
+      return set_error(SEEDRL_ERR_INVALID_ARGUMENT,
+                       "seedrl_net_create: deep net kernels are built for 4-channel uint8 frames");
+    }
+    int h = cfg->obs_h, w = cfg->obs_w;
+    const int chans[3] = {16, 32, 32};
+    for (int s = 0; s < 3; ++s) { h = (h + 1) / 2; w = (w + 1) / 2; }
+    flat = h * w * chans[2];
+  } else {
+    n->sh_h1 = (cfg->obs_h - 8) / 4 + 1; n->sh_w1 = (cfg->obs_w - 8) / 4 + 1;
+    n->sh_h2 = (n->sh_h1 - 4) / 2 + 1;   n->sh_w2 = (n->sh_w1 - 4) / 2 + 1;
+    flat = n->sh_h2 * n->sh_w2 * 32;
+  }
+  n->flat = flat;
+  n->p_dense_w = add_param(n, "conv_to_linear/kernel", {flat, kHidden});
+  n->p_dense_b = add_param(n, "conv_to_linear/bias", {kHidden});
+  n->p_core_w = add_param(n, "core/kernel", {n->core_in, 4 * kHidden});
+  n->p_core_u = add_param(n, "core/recurrent_kernel", {kHidden, 4 * kHidden});
+  n->p_core_b = add_param(n, "core/bias", {4 * kHidden});
+  n->p_pol_w = add_param(n, "policy_logits/kernel", {kHidden, A});
+  n->p_pol_b = add_param(n, "policy_logits/bias", {A});
+  if (cfg->net == SEEDRL_NET_DEEP) {
+    int h = cfg->obs_h, w = cfg->obs_w, c = cfg->obs_c;
+    const int chans[3] = {16, 32, 32};
+    for (int s = 0; s < 3; ++s) {
+      Stack st;
+      const std::string pre = "stack" + std::to_string(s);
+      st.hin = h; st.win = w; st.cin = c; st.c = chans[s];
+      st.hout = (h + 1) / 2; st.wout = (w + 1) / 2;
+      st.conv = add_conv(n, pre + "/conv", 3, c, st.c);
+      // tf.Module order inside _Stack: _conv, _res_convs0[0..1], _res_convs1[0..1]
+      st.r00 = add_conv(n, pre + "/res_0/conv2d_0", 3, st.c, st.c);
+      st.r10 = add_conv(n, pre + "/res_1/conv2d_0", 3, st.c, st.c);
+      st.r01 = add_conv(n, pre + "/res_0/conv2d_1", 3, st.c, st.c);
+      st.r11 = add_conv(n, pre + "/res_1/conv2d_1", 3, st.c, st.c);
+      n->stacks.push_back(st);
+      h = st.hout; w = st.wout; c = st.c;
+    }
+  } else {
+    ConvLayer c0 = add_conv(n, "conv0", 8, cfg->obs_c, 16);
+    ConvLayer c1 = add_conv(n, "conv1", 4, 16, 32);
+    n->sh_c0w = c0.w; n->sh_c0b = c0.b; n->sh_c1w = c1.w; n->sh_c1b = c1.b;
+  }
+  n->logical_params = 0;
+  for (const ParamInfo& p : n->params) n->logical_params += p.size;
+  add_param(n, "entropy_cost_param", {});
+  *out = n;
+  return SEEDRL_OK;
+}
+
+extern "C" void seedrl_net_destroy(seedrl_net* net) { delete net; }
+extern "C" int seedrl_net_num_param_tensors(const seedrl_net* net) {
+  return net ? (int)net->params.size() - 1 : 0;
+}
+extern "C" size_t seedrl_net_num_params(const seedrl_net* net) { return net ? net->logical_params : 0; }
+extern "C" size_t seedrl_net_arena_floats(const seedrl_net* net) { return net ? net->arena_floats : 0; }
+
+extern "C" int seedrl_net_param_info(const seedrl_net* net, int index, char* name_buf,
+                                     size_t name_buf_len, int64_t* dims, size_t* offset) {
+  if (!net || index < 0 || index >= (int)net->params.size()) return -1;
+  const ParamInfo& p = net->params[index];
+  if (name_buf && name_buf_len) {
+    strncpy(name_buf, p.name.c_str(), name_buf_len - 1);
+    name_buf[name_buf_len - 1] = 0;
+  }
+  if (dims) for (int i = 0; i < 4; ++i) dims[i] = p.dims[i];
+  if (offset) *offset = p.offset;
+  return p.rank;
+}
+
+extern "C" size_t seedrl_net_workspace_bytes(const seedrl_net* net, int T1, int B) {
+  if (!net || T1 <= 0 || B <= 0) return 0;
+  return make_plan(net, T1, B).total;
+}
+
+// ---- forward --------------------------------------------------------------------
+static int torso_forward_deep(const seedrl_net* n, const float* prm, const Plan& pl,
+                              const uint8_t* obs, void* ws, cudaStream_t st) {
+  const int N = pl.N;
+  const void* in = obs;
+  int in_mode = IN_U8;
+  for (size_t s = 0; s < n->stacks.size(); ++s) {
+    const Stack& k = n->stacks[s];
+    const StackBufs& b = pl.st[s];
+    float* a0 = W<float>(ws, b.a0); float* p = W<float>(ws, b.p);
+    float* c0 = W<float>(ws, b.c0); float* o0 = W<float>(ws, b.o0);
+    float* c1 = W<float>(ws, b.c1); float* o1 = W<float>(ws, b.o1);
+    // _Stack.__call__, dmlab/networks.py:46-60
+    SEEDRL_TRY(conv3x3_forward(k.cin, k.c, in_mode, N, k.hin, k.win, in, P(n, prm, k.conv.w),
+                               P(n, prm, k.conv.b), nullptr, nullptr, a0, st));
+    SEEDRL_TRY(maxpool3s2_forward(N, k.hin, k.win, k.c, a0, p, W<uint8_t>(ws, b.idx), st));
+    SEEDRL_TRY(conv3x3_forward(k.c, k.c, IN_RELU, N, k.hout, k.wout, p, P(n, prm, k.r00.w),
+                               P(n, prm, k.r00.b), nullptr, nullptr, c0, st));
+    SEEDRL_TRY(conv3x3_forward(k.c, k.c, IN_RELU, N, k.hout, k.wout, c0, P(n, prm, k.r01.w),
+                               P(n, prm, k.r01.b), nullptr, p, o0, st));
+    SEEDRL_TRY(conv3x3_forward(k.c, k.c, IN_RELU, N, k.hout, k.wout, o0, P(n, prm, k.r10.w),
+                               P(n, prm, k.r10.b), nullptr, nullptr, c1, st));
+    SEEDRL_TRY(conv3x3_forward(k.c, k.c, IN_RELU, N, k.hout, k.wout, c1, P(n, prm, k.r11.w),
+                               P(n, prm, k.r11.b), nullptr, o0, o1, st));
+    in = o1;
+    in_mode = IN_F32;
+  }
+  return SEEDRL_OK;
+}
+
+static int torso_forward_shallow(const seedrl_net* n, const float* prm, const Plan& pl,
+                                 const uint8_t* obs, void* ws, cudaStream_t st) {
+  const int N = pl.N;
+  float* a1 = W<float>(ws, pl.sh_a1);
+  float* a2 = W<float>(ws, pl.sh_a2);
+  SEEDRL_TRY(convgen_forward(N, n->cfg.obs_h, n->cfg.obs_w, n->cfg.obs_c, 16, 8, 4, 1, obs,
+                             P(n, prm, n->sh_c0w), P(n, prm, n->sh_c0b), 1, a1, st));
+  SEEDRL_TRY(convgen_forward(N, n->sh_h1, n->sh_w1, 16, 32, 4, 2, 0, a1, P(n, prm, n->sh_c1w),
+                             P(n, prm, n->sh_c1b), 1, a2, st));
+  return SEEDRL_OK;
+}
+
+extern "C" int seedrl_net_forward(const seedrl_net* n, const float* prm, int T1, int B,
+                                  const int64_t* prev_actions, const float* reward,
+                                  const uint8_t* done, const uint8_t* observation,
+                                  const float* h0, const float* c0, float* policy_logits,
+                                  float* baseline, float* h_out, float* c_out, void* ws,
+                                  size_t ws_bytes, seedrl_stream_t stream) {
+  SEEDRL_CHECK_ARG(n && prm && prev_actions && reward && done && observation && h0 && c0 &&
+                       policy_logits && baseline && ws, "null pointer");
+  SEEDRL_CHECK_ARG(T1 >= 1 && B >= 1, "T1, B must be >= 1");
+  const Plan pl = make_plan(n, T1, B);
+  SEEDRL_CHECK_ARG(ws_bytes >= pl.total, "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = pl.N, A = n->cfg.num_actions, CI = n->core_in;
+  const float* flat_src;
+  int flat_relu;
+  if (n->cfg.net == SEEDRL_NET_DEEP) {
+    SEEDRL_TRY(torso_forward_deep(n, prm, pl, observation, ws, st));
+    flat_src = W<float>(ws, pl.st.back().o1);
+    flat_relu = 1;                         // tf.nn.relu before Flatten, networks.py:105
+  } else {
+    SEEDRL_TRY(torso_forward_shallow(n, prm, pl, observation, ws, st));
+    flat_src = W<float>(ws, pl.sh_a2);
+    flat_relu = 0;                         // already relu'd
+  }
+  float* xc = W<float>(ws, pl.xc);
+  float* z = W<float>(ws, pl.z);
+  float* hp = W<float>(ws, pl.hp);
+  float* cs = W<float>(ws, pl.cs);
+  float* hs = W<float>(ws, pl.hs);
+  float* c0buf = W<float>(ws, pl.c0buf);
+  // Dense(256) + relu written straight into the first 256 columns of the core input
+  GemmEpi e = epi_none();
+  e.bias = P(n, prm, n->p_dense_b); e.relu = 1; e.a_relu = flat_relu;
+  SEEDRL_TRY(sgemm(false, false, N, kHidden, n->flat, flat_src, n->flat, P(n, prm, n->p_dense_w),
+                   kHidden, xc, CI, e, st));
+  SEEDRL_TRY(core_input_tail(N, kHidden, A, reward, prev_actions, xc, st));
+  // input projection for all T at once: z = xc W + b
+  e = epi_none();
+  e.bias = P(n, prm, n->p_core_b);
+  SEEDRL_TRY(sgemm(false, false, N, 4 * kHidden, CI, xc, CI, P(n, prm, n->p_core_w), 4 * kHidden, z,
+                   4 * kHidden, e, st));
+  SEEDRL_CUDA(cudaMemcpyAsync(c0buf, c0, (size_t)B * kHidden * 4, cudaMemcpyDeviceToDevice, st));
+  SEEDRL_TRY(lstm_mask_state(B, kHidden, done, h0, hp, st));
+  GemmEpi eacc = epi_none();
+  eacc.accumulate = 1;
+  for (int t = 0; t < T1; ++t) {
+    float* zt = z + (size_t)t * B * 4 * kHidden;
+    SEEDRL_TRY(sgemm(false, false, B, 4 * kHidden, kHidden, hp + (size_t)t * B * kHidden, kHidden,
+                     P(n, prm, n->p_core_u), 4 * kHidden, zt, 4 * kHidden, eacc, st));
+    const bool last = (t + 1 == T1);
+    SEEDRL_TRY(lstm_pointwise_fwd(B, kHidden, zt, t == 0 ? c0buf : cs + (size_t)(t - 1) * B * kHidden,
+                                  done + (size_t)t * B, last ? nullptr : done + (size_t)(t + 1) * B,
+                                  cs + (size_t)t * B * kHidden, hs + (size_t)t * B * kHidden,
+                                  last ? nullptr : hp + (size_t)(t + 1) * B * kHidden, st));
+  }
+  // heads, networks.py:116-118
+  e = epi_none();
+  e.bias = P(n, prm, n->p_pol_b);
+  SEEDRL_TRY(sgemm(false, false, N, A, kHidden, hs, kHidden, P(n, prm, n->p_pol_w), A, policy_logits,
+                   A, e, st));
+  e.bias = P(n, prm, n->p_base_b);
+  SEEDRL_TRY(sgemm(false, false, N, 1, kHidden, hs, kHidden, P(n, prm, n->p_base_w), 1, baseline, 1,
+                   e, st));
+  if (h_out)
+    SEEDRL_CUDA(cudaMemcpyAsync(h_out, hs + (size_t)(T1 - 1) * B * kHidden, (size_t)B * kHidden * 4,
+                                cudaMemcpyDeviceToDevice, st));
+  if (c_out)
+    SEEDRL_CUDA(cudaMemcpyAsync(c_out, cs + (size_t)(T1 - 1) * B * kHidden, (size_t)B * kHidden * 4,
+                                cudaMemcpyDeviceToDevice, st));
+  return SEEDRL_OK;
+}
+
+// ---- backward -------------------------------------------------------------------
+static int conv_bwd(const seedrl_net* n, const float* prm, float* grd, const ConvLayer& l, int N,
+                    int H, int Wd, const void* x, int x_mode, const float* dy, const float* dmask,
+                    const float* dres, float* dx, void* ws, const Plan& pl, cudaStream_t st) {
+  // weight + bias gradient
+  SEEDRL_TRY(conv3x3_wgrad(l.cin, l.cout, x_mode, N, H, Wd, x, dy, G(n, grd, l.w), G(n, grd, l.b),
+                           W<float>(ws, pl.partial), conv3x3_wgrad_partial_bytes(), st));
+  if (dx) {  // data gradient = conv with flipped, transposed weights
+    float* wt = W<float>(ws, pl.wt);
+    SEEDRL_TRY(conv3x3_flip_weights(l.cin, l.cout, P(n, prm, l.w), wt, st));
+    SEEDRL_TRY(conv3x3_forward(l.cout, l.cin, IN_F32, N, H, Wd, dy, wt, nullptr, dmask, dres, dx, st));
+  }
+  return SEEDRL_OK;
+}
+
+static int torso_backward_deep(const seedrl_net* n, const float* prm, float* grd, const Plan& pl,
+                               const uint8_t* obs, void* ws, cudaStream_t st) {
+  // On entry gA holds d loss / d o1 of the last stack.
+  const int N = pl.N;
+  float* gA = W<float>(ws, pl.gA); float* gB = W<float>(ws, pl.gB);
+  float* gC = W<float>(ws, pl.gC); float* gF = W<float>(ws, pl.gFull);
+  for (int s = (int)n->stacks.size() - 1; s >= 0; --s) {
+    const Stack& k = n->stacks[s];
+    const StackBufs& b = pl.st[s];
+    const float* p = W<float>(ws, b.p);  const float* c0 = W<float>(ws, b.c0);
+    const float* o0 = W<float>(ws, b.o0); const float* c1 = W<float>(ws, b.c1);
+    const int H = k.hout, Wd = k.wout;
+    // block 1: o1 = conv11(relu(c1)) + o0 ; c1 = conv10(relu(o0))
+    SEEDRL_TRY(conv_bwd(n, prm, grd, k.r11, N, H, Wd, c1, IN_RELU, gA, c1, nullptr, gB, ws, pl, st));
+    SEEDRL_TRY(conv_bwd(n, prm, grd, k.r10, N, H, Wd, o0, IN_RELU, gB, o0, gA, gC, ws, pl, st));
+    // block 0: o0 = conv01(relu(c0)) + p ; c0 = conv00(relu(p))
+    SEEDRL_TRY(conv_bwd(n, prm, grd, k.r01, N, H, Wd, c0, IN_RELU, gC, c0, nullptr, gB, ws, pl, st));
+    SEEDRL_TRY(conv_bwd(n, prm, grd, k.r00, N, H, Wd, p, IN_RELU, gB, p, gC, gA, ws, pl, st));
+    // max-pool, then the stack's first conv
+    SEEDRL_TRY(maxpool3s2_backward(N, k.hin, k.win, k.c, gA, W<uint8_t>(ws, b.idx), gF, st));
+    const void* x = s == 0 ? (const void*)obs : (const void*)W<float>(ws, pl.st[s - 1].o1);
+    SEEDRL_TRY(conv_bwd(n, prm, grd, k.conv, N, k.hin, k.win, x, s == 0 ? IN_U8 : IN_F32, gF, nullptr,
+                        nullptr, s == 0 ? nullptr : gA, ws, pl, st));
+  }
+  return SEEDRL_OK;
+}
+
+static int torso_backward_shallow(const seedrl_net* n, const float* prm, float* grd, const Plan& pl,
+                                  const uint8_t* obs, void* ws, cudaStream_t st) {
+  // On entry gA holds d loss / d a2 (already masked by a2 > 0).
+  const int N = pl.N;
+  float* gA = W<float>(ws, pl.gA); float* gB = W<float>(ws, pl.gB);
+  const float* a1 = W<float>(ws, pl.sh_a1);
+  SEEDRL_TRY(convgen_wgrad(N, n->sh_h1, n->sh_w1, 16, 32, 4, 2, 0, a1, gA, G(n, grd, n->sh_c1w),
+                           G(n, grd, n->sh_c1b), W<float>(ws, pl.partial),
+                           conv3x3_wgrad_partial_bytes(), st));
+  SEEDRL_TRY(convgen_dgrad(N, n->sh_h1, n->sh_w1, 16, 32, 4, 2, gA, P(n, prm, n->sh_c1w), a1, gB, st));
+  SEEDRL_TRY(convgen_wgrad(N, n->cfg.obs_h, n->cfg.obs_w, n->cfg.obs_c, 16, 8, 4, 1, obs, gB,
+                           G(n, grd, n->sh_c0w), G(n, grd, n->sh_c0b), W<float>(ws, pl.partial),
+                           conv3x3_wgrad_partial_bytes(), st));
+  return SEEDRL_OK;
+}
+
+extern "C" int seedrl_net_backward(const seedrl_net* n, const float* prm, int T1, int B,
+                                   const int64_t* prev_actions, const float* reward,
+                                   const uint8_t* done, const uint8_t* observation,
+                                   const float* dlogits, const float* dbaseline, float* grd,
+                                   void* ws, size_t ws_bytes, seedrl_stream_t stream) {
+  SEEDRL_CHECK_ARG(n && prm && done && observation && dlogits && dbaseline && grd && ws,
+                   "null pointer");
+  (void)prev_actions; (void)reward;
+  const Plan pl = make_plan(n, T1, B);
+  SEEDRL_CHECK_ARG(ws_bytes >= pl.total, "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = pl.N, A = n->cfg.num_actions, CI = n->core_in;
+  float* xc = W<float>(ws, pl.xc); float* z = W<float>(ws, pl.z);
+  float* hp = W<float>(ws, pl.hp); float* cs = W<float>(ws, pl.cs);
+  float* hs = W<float>(ws, pl.hs); float* c0buf = W<float>(ws, pl.c0buf);
+  float* dhs = W<float>(ws, pl.dhs); float* dz = W<float>(ws, pl.dz);
+  float* dhrec = W<float>(ws, pl.dhrec); float* dd = W<float>(ws, pl.dd);
+  float* dcb[2] = {W<float>(ws, pl.dc0), W<float>(ws, pl.dc1)};
+  // padding floats and the entropy_cost_param slot must not carry garbage into Adam / all-reduce
+  SEEDRL_CUDA(cudaMemsetAsync(grd, 0, n->arena_floats * sizeof(float), st));
+
+  // heads
+  GemmEpi e = epi_none();
+  SEEDRL_TRY(sgemm(true, false, kHidden, A, N, hs, kHidden, dlogits, A, G(n, grd, n->p_pol_w), A, e, st));
+  SEEDRL_TRY(colsum(N, A, dlogits, A, G(n, grd, n->p_pol_b), st));
+  SEEDRL_TRY(sgemm(true, false, kHidden, 1, N, hs, kHidden, dbaseline, 1, G(n, grd, n->p_base_w), 1, e, st));
+  SEEDRL_TRY(colsum(N, 1, dbaseline, 1, G(n, grd, n->p_base_b), st));
+  SEEDRL_TRY(sgemm(false, true, N, kHidden, A, dlogits, A, P(n, prm, n->p_pol_w), A, dhs, kHidden, e, st));
+  GemmEpi eacc = epi_none();
+  eacc.accumulate = 1;
+  SEEDRL_TRY(sgemm(false, true, N, kHidden, 1, dbaseline, 1, P(n, prm, n->p_base_w), 1, dhs, kHidden,
+                   eacc, st));
+  // BPTT
+  for (int t = T1 - 1; t >= 0; --t) {
+    const bool last = (t + 1 == T1);
+    const size_t o = (size_t)t * B * kHidden;
+    SEEDRL_TRY(lstm_pointwise_bwd(B, kHidden, z + (size_t)t * B * 4 * kHidden, cs + o,
+                                  t == 0 ? c0buf : cs + o - (size_t)B * kHidden, done + (size_t)t * B,
+                                  last ? nullptr : done + (size_t)(t + 1) * B, dhs + o,
+                                  last ? nullptr : dhrec, last ? nullptr : dcb[(t + 1) & 1],
+                                  dz + (size_t)t * B * 4 * kHidden, dcb[t & 1], st));
+    if (t > 0)
+      SEEDRL_TRY(sgemm(false, true, B, kHidden, 4 * kHidden, dz + (size_t)t * B * 4 * kHidden,
+                       4 * kHidden, P(n, prm, n->p_core_u), 4 * kHidden, dhrec, kHidden, e, st));
+  }
+  SEEDRL_TRY(sgemm(true, false, kHidden, 4 * kHidden, N, hp, kHidden, dz, 4 * kHidden,
+                   G(n, grd, n->p_core_u), 4 * kHidden, e, st));
+  SEEDRL_TRY(sgemm(true, false, CI, 4 * kHidden, N, xc, CI, dz, 4 * kHidden, G(n, grd, n->p_core_w),
+                   4 * kHidden, e, st));
+  SEEDRL_TRY(colsum(N, 4 * kHidden, dz, 4 * kHidden, G(n, grd, n->p_core_b), st));
+  // d dense_out = (dz W[:256,:]^T) * (dense_out > 0)
+  GemmEpi em = epi_none();
+  em.mask = xc; em.ldm = CI;
+  SEEDRL_TRY(sgemm(false, true, N, kHidden, 4 * kHidden, dz, 4 * kHidden, P(n, prm, n->p_core_w),
+                   4 * kHidden, dd, kHidden, em, st));
+  // Dense(256)
+  const float* flat_src = n->cfg.net == SEEDRL_NET_DEEP ? W<float>(ws, pl.st.back().o1)
+                                                        : W<float>(ws, pl.sh_a2);
+  GemmEpi ea = epi_none();
+  ea.a_relu = n->cfg.net == SEEDRL_NET_DEEP ? 1 : 0;
+  SEEDRL_TRY(sgemm(true, false, n->flat, kHidden, N, flat_src, n->flat, dd, kHidden,
+                   G(n, grd, n->p_dense_w), kHidden, ea, st));
+  SEEDRL_TRY(colsum(N, kHidden, dd, kHidden, G(n, grd, n->p_dense_b), st));
+  GemmEpi ef = epi_none();
+  ef.mask = flat_src; ef.ldm = n->flat;
+  SEEDRL_TRY(sgemm(false, true, N, n->flat, kHidden, dd, kHidden, P(n, prm, n->p_dense_w), kHidden,
+                   W<float>(ws, pl.gA), n->flat, ef, st));
+  if (n->cfg.net == SEEDRL_NET_DEEP) return torso_backward_deep(n, prm, grd, pl, observation, ws, st);
+  return torso_backward_shallow(n, prm, grd, pl, observation, ws, st);
+}

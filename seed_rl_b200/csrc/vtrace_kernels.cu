@@ -1,0 +1,552 @@
+// V-trace kernels for sm_100a.
+//
+//  vtrace_kernel            (a1)  common/vtrace.py:34-148
+//  categorical_*_kernel     (a3)  common/parametric_distribution.py:66-74
+//  vtrace_loss_kernel       (a2)  agents/vtrace/learner.py:82-157 + its gradient
+//
+// Layout is the reference's time-major [T, B(, A)].  All of these are HBM-bound
+// streaming kernels (no reuse beyond one column's time scan), so the design is:
+// coalesced loads across B, the T-scan sequential in registers per column,
+// logits tiles staged through shared memory so that HBM sees only full-line
+// coalesced traffic in both directions.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace seedrl {
+
+// ---------------------------------------------------------------------------
+// (a1) one thread per column b; reverse scan over t with loads issued CH steps
+// ahead of use (memory-level parallelism: 5*CH independent loads in flight).
+template <int CH>
+__global__ void __launch_bounds__(128)
+vtrace_kernel(int T, int B, const float* __restrict__ tlp, const float* __restrict__ blp,
+              const float* __restrict__ disc, const float* __restrict__ rew,
+              const float* __restrict__ val, const float* __restrict__ boot,
+              float clip_rho, float clip_pg, float lambda_, int has_clip_rho,
+              int has_clip_pg, float* __restrict__ vs, float* __restrict__ pg) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float acc = 0.f;
+  const float bootv = boot[b];
+  float vs_next = bootv, v_next = bootv;
+  int t_hi = T;  // exclusive
+  while (t_hi > 0) {
+    const int t_lo = t_hi - CH > 0 ? t_hi - CH : 0;
+    float a_t[CH], a_b[CH], a_d[CH], a_r[CH], a_v[CH];
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const int t = t_hi - 1 - k;
+      if (t >= t_lo) {
+        const size_t o = (size_t)t * B + b;
+        a_t[k] = __ldg(tlp + o); a_b[k] = __ldg(blp + o); a_d[k] = __ldg(disc + o);
+        a_r[k] = __ldg(rew + o); a_v[k] = __ldg(val + o);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < CH; ++k) {
+      const int t = t_hi - 1 - k;
+      if (t >= t_lo) {
+        const float rho = expf(a_t[k] - a_b[k]);                       // vtrace.py:84,110
+        const float crho = has_clip_rho ? fminf(clip_rho, rho) : rho;  // :111-114
+        const float c = fminf(1.0f, rho) * lambda_;                    // :116-117
+        const float v = a_v[k], d = a_d[k], r = a_r[k];
+        const float delta = crho * (r + d * v_next - v);               // :122
+        acc = delta + d * c * acc;                                     // :128
+        const float vs_t = acc + v;                                    // :133
+        const float cpg = has_clip_pg ? fminf(clip_pg, rho) : rho;     // :138-142
+        const size_t o = (size_t)t * B + b;
+        vs[o] = vs_t;
+        pg[o] = cpg * (r + d * vs_next - v);                           // :143-144
+        vs_next = vs_t;
+        v_next = v;
+      }
+    }
+    t_hi = t_lo;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// (a3) one warp per row, lanes strided over A.
+__global__ void categorical_logprob_entropy_kernel(int N, int A, const float* __restrict__ logits,
+                                                   const int64_t* __restrict__ actions,
+                                                   float* __restrict__ logp,
+                                                   float* __restrict__ entropy) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  const float* l = logits + (size_t)warp * A;
+  float m = -INFINITY;
+  for (int j = lane; j < A; j += 32) m = fmaxf(m, l[j]);
+  m = warp_max(m);
+  float se = 0.f, sel = 0.f;
+  for (int j = lane; j < A; j += 32) {
+    const float e = expf(l[j] - m);
+    se += e;
+    sel += e * (l[j] - m);
+  }
+  se = warp_sum(se);
+  sel = warp_sum(sel);
+  const float lse = m + logf(se);
+  if (lane == 0) {
+    if (logp) {
+      int64_t a = actions[warp];
+      a = a < 0 ? 0 : (a >= A ? A - 1 : a);
+      logp[warp] = l[a] - lse;
+    }
+    if (entropy) entropy[warp] = logf(se) - sel / se;   // H = lse - sum p*l
+  }
+}
+
+// Philox4x32-10 (Salmon et al. 2011), counter = (offset, row, block-of-4, 0).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+
+// one thread per row (A is small); first max wins ties like np.argmax.
+__global__ void categorical_sample_kernel(int N, int A, const float* __restrict__ logits,
+                                          const float* __restrict__ noise, uint64_t seed,
+                                          uint64_t offset, int64_t* __restrict__ actions) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const float* l = logits + (size_t)n * A;
+  float best = -INFINITY;
+  int arg = 0;
+  if (noise) {
+    const float* g = noise + (size_t)n * A;
+    for (int j = 0; j < A; ++j) {
+      const float s = l[j] + g[j];
+      if (s > best) { best = s; arg = j; }
+    }
+  } else {
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    for (int j0 = 0; j0 < A; j0 += 4) {
+      const uint4 r = philox4x32_10(
+          make_uint4((uint32_t)offset, (uint32_t)(offset >> 32), (uint32_t)n, (uint32_t)(j0 >> 2)), key);
+      const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int j = j0 + k;
+        if (j < A) {
+          // u in (0,1): (x + 0.5) * 2^-32 ; g = -log(-log u)
+          const float u = ((float)rr[k] + 0.5f) * 2.3283064365386963e-10f;
+          const float uu = fminf(fmaxf(u, 1e-10f), 0.99999994f);
+          const float s = l[j] - logf(-logf(uu));
+          if (s > best) { best = s; arg = j; }
+        }
+      }
+    }
+  }
+  actions[n] = arg;
+}
+
+// ---------------------------------------------------------------------------
+// (a2) fused log-softmax + V-trace + losses + analytic gradient.
+// One CTA owns BB batch columns for all T steps.
+//   phase A  behaviour logits tile -> smem, thread-per-row: beh_logp
+//   phase B  learner   logits tile -> smem (same buffer), thread-per-row:
+//            lse, target logp, entropy
+//   phase C  thread-per-column reverse scan (vs, pg_adv) + loss partial sums
+//   phase D  thread-per-element gradient, written back coalesced
+// Per-CTA partial sums go to scratch[cta][8]; the last CTA to finish (ticket)
+// reduces them in index order (deterministic) and writes loss_terms.
+constexpr int kLossThreads = 256;
+constexpr int kLossPartials = 8;
+
+struct LossParams {
+  int T, B, A, BB, AP;
+  const float* ll;   // learner logits [T+1,B,A]
+  const float* lb;   // learner baseline [T+1,B]
+  const float* bl;   // behaviour logits [T+1,B,A]
+  const int64_t* act;
+  const float* rew;
+  const uint8_t* done;
+  seedrl_loss_config cfg;
+  const float* ecp;
+  float* loss_terms;
+  float* dlogits;
+  float* dbaseline;
+  float* d_ecp;
+  float* vs_out;
+  float* pg_out;
+  float* partials;        // [grid][8]
+  unsigned int* ticket;   // self-resetting
+};
+
+__device__ __forceinline__ float block_reduce_sum(float v, float* red) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (w == 0) {
+    r = l < (blockDim.x >> 5) ? red[l] : 0.f;
+    r = warp_sum(r);
+  }
+  return r;  // valid in warp 0
+}
+__device__ __forceinline__ float block_reduce_max(float v, float* red) {
+  v = warp_max(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) red[w] = v;
+  __syncthreads();
+  float r = 0.f;
+  if (w == 0) {
+    r = l < (blockDim.x >> 5) ? red[l] : -INFINITY;
+    r = warp_max(r);
+  }
+  return r;
+}
+
+__global__ void __launch_bounds__(kLossThreads)
+vtrace_loss_kernel(const LossParams p) {
+  extern __shared__ float smem[];
+  const int T = p.T, B = p.B, A = p.A, BB = p.BB, AP = p.AP;
+  const int b0 = blockIdx.x * BB;
+  const int nb = min(BB, B - b0);
+  const int rows = T * BB;
+  float* s_logits = smem;                      // [T*BB][AP]
+  float* s_tlp = s_logits + (size_t)rows * AP; // [rows] target logp   -> later pg_adv
+  float* s_blp = s_tlp + rows;                 // [rows] behaviour logp -> later v_err
+  float* s_lse = s_blp + rows;                 // [rows]
+  float* s_ent = s_lse + rows;                 // [rows]
+  float* s_rew = s_ent + rows;                 // [rows] clipped reward r_{t+1}
+  float* s_dis = s_rew + rows;                 // [rows] discount
+  float* s_val = s_dis + rows;                 // [(T+1)*BB]
+  int* s_act = reinterpret_cast<int*>(s_val + (T + 1) * BB);  // [rows]
+  float* s_red = reinterpret_cast<float*>(s_act + rows);      // [32]
+  const int tid = threadIdx.x;
+  const float mul = p.cfg.entropy_cost_adjustment_speed;
+  const float ec = expf(mul * __ldg(p.ecp));   // agent.entropy_cost(), learner.py:234
+
+  // ---- small per-row inputs ------------------------------------------------
+  for (int i = tid; i < rows; i += kLossThreads) {
+    const int t = i / BB, c = i - t * BB;
+    if (c < nb) {
+      const size_t g1 = (size_t)(t + 1) * B + b0 + c;      // env_outputs[1:], learner.py:87
+      float r = __ldg(p.rew + g1);
+      if (p.cfg.max_abs_reward != 0.f)                     // :90-92
+        r = fminf(fmaxf(r, -p.cfg.max_abs_reward), p.cfg.max_abs_reward);
+      s_rew[i] = r;
+      s_dis[i] = p.done[g1] ? 0.f : p.cfg.discounting;     // :93
+      int64_t a = p.act[(size_t)t * B + b0 + c];           // agent_outputs[:-1], :86
+      s_act[i] = (int)a;
+    } else {
+      s_rew[i] = 0.f; s_dis[i] = 0.f; s_act[i] = 0;
+    }
+  }
+  for (int i = tid; i < (T + 1) * BB; i += kLossThreads) {
+    const int t = i / BB, c = i - t * BB;
+    s_val[i] = c < nb ? __ldg(p.lb + (size_t)t * B + b0 + c) : 0.f;
+  }
+
+  // ---- phase A: behaviour logits ------------------------------------------
+  for (int t = 0; t < T; ++t) {
+    const float* src = p.bl + ((size_t)t * B + b0) * A;
+    for (int e = tid; e < nb * A; e += kLossThreads) {
+      const int c = e / A, j = e - c * A;
+      s_logits[(size_t)(t * BB + c) * AP + j] = __ldg(src + e);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < rows; i += kLossThreads) {
+    const int c = i % BB;
+    if (c < nb) {
+      const float* l = s_logits + (size_t)i * AP;
+      float m = -INFINITY;
+      for (int j = 0; j < A; ++j) m = fmaxf(m, l[j]);
+      float se = 0.f;
+      for (int j = 0; j < A; ++j) se += expf(l[j] - m);
+      int a = s_act[i];
+      a = a < 0 ? 0 : (a >= A ? A - 1 : a);
+      s_blp[i] = l[a] - (m + logf(se));                    // :97-98
+    }
+  }
+  __syncthreads();
+  // ---- phase B: learner logits --------------------------------------------
+  for (int t = 0; t < T; ++t) {
+    const float* src = p.ll + ((size_t)t * B + b0) * A;
+    for (int e = tid; e < nb * A; e += kLossThreads) {
+      const int c = e / A, j = e - c * A;
+      s_logits[(size_t)(t * BB + c) * AP + j] = __ldg(src + e);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < rows; i += kLossThreads) {
+    const int c = i % BB;
+    if (c < nb) {
+      const float* l = s_logits + (size_t)i * AP;
+      float m = -INFINITY;
+      for (int j = 0; j < A; ++j) m = fmaxf(m, l[j]);
+      float se = 0.f, sel = 0.f;
+      for (int j = 0; j < A; ++j) {
+        const float e = expf(l[j] - m);
+        se += e;
+        sel += e * (l[j] - m);
+      }
+      const float lg = logf(se);
+      int a = s_act[i];
+      a = a < 0 ? 0 : (a >= A ? A - 1 : a);
+      s_lse[i] = m + lg;
+      s_tlp[i] = l[a] - (m + lg);                          // :95-96
+      s_ent[i] = lg - sel / se;                            // :119-120
+    }
+  }
+  __syncthreads();
+
+  // ---- phase C: reverse-time V-trace scan, one thread per column -----------
+  float sum_tp = 0.f, sum_ve2 = 0.f, sum_h = 0.f, sum_kl = 0.f, sum_v = 0.f, max_a = 0.f;
+  if (tid < nb) {
+    const int c = tid;
+    const bool hcr = !isnan(p.cfg.clip_rho_threshold);
+    const bool hcp = !isnan(p.cfg.clip_pg_rho_threshold);
+    const float bootv = s_val[T * BB + c];                 // :82
+    float acc = 0.f, vs_next = bootv, v_next = bootv;
+    for (int t = T - 1; t >= 0; --t) {
+      const int i = t * BB + c;
+      const float tl = s_tlp[i], bp = s_blp[i];
+      const float rho = expf(tl - bp);
+      const float crho = hcr ? fminf(p.cfg.clip_rho_threshold, rho) : rho;
+      const float cc = fminf(1.0f, rho) * p.cfg.lambda_;
+      const float v = s_val[i], d = s_dis[i], r = s_rew[i];
+      const float delta = crho * (r + d * v_next - v);
+      acc = delta + d * cc * acc;
+      const float vs_t = acc + v;
+      const float cpg = hcp ? fminf(p.cfg.clip_pg_rho_threshold, rho) : rho;
+      const float pg = cpg * (r + d * vs_next - v);
+      vs_next = vs_t;
+      v_next = v;
+      const float verr = vs_t - v;                         // :115
+      sum_tp += tl * pg;                                   // :111-112
+      sum_ve2 += verr * verr;                              // :116
+      sum_h += s_ent[i];
+      sum_kl += bp - tl;                                   // :124
+      sum_v += v;
+      max_a = fmaxf(max_a, fabsf((float)s_act[i]));
+      s_tlp[i] = pg;     // reuse: pg_adv
+      s_blp[i] = verr;   // reuse: v_err
+      const size_t g = (size_t)t * B + b0 + c;
+      if (p.vs_out) p.vs_out[g] = vs_t;
+      if (p.pg_out) p.pg_out[g] = pg;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase D: gradients --------------------------------------------------
+  const float invN = 1.0f / ((float)T * (float)B);
+  const float kc = p.cfg.kl_cost;
+  for (int t = 0; t < T; ++t) {
+    float* dst = p.dlogits + ((size_t)t * B + b0) * A;
+    for (int e = tid; e < nb * A; e += kLossThreads) {
+      const int c = e / A, j = e - c * A;
+      const int i = t * BB + c;
+      const float l = s_logits[(size_t)i * AP + j];
+      const float logp = l - s_lse[i];
+      const float pj = expf(logp);
+      int a = s_act[i];
+      a = a < 0 ? 0 : (a >= A ? A - 1 : a);
+      const float onehot = (j == a) ? 1.f : 0.f;
+      // d(-mean(tlp*pg))/dl_j = -pg/N (1[j=a]-p_j); d(kc*mean(blp-tlp)) = -kc/N (1[j=a]-p_j)
+      // d(-ec*mean(H))/dl_j  = ec/N * p_j (log p_j + H)
+      const float g = -(s_tlp[i] + kc) * invN * (onehot - pj) + ec * invN * pj * (logp + s_ent[i]);
+      dst[e] = g;
+    }
+  }
+  {  // last row (bootstrap step): zero gradient
+    float* dst = p.dlogits + ((size_t)T * B + b0) * A;
+    for (int e = tid; e < nb * A; e += kLossThreads) dst[e] = 0.f;
+  }
+  for (int i = tid; i < (T + 1) * BB; i += kLossThreads) {
+    const int t = i / BB, c = i - t * BB;
+    if (c < nb) {
+      // d(bc*0.5*mean((vs-V)^2))/dV = -bc*(vs-V)/N
+      p.dbaseline[(size_t)t * B + b0 + c] = t < T ? -p.cfg.baseline_cost * s_blp[i] * invN : 0.f;
+    }
+  }
+
+  // ---- per-CTA partials, then last-CTA finalisation -------------------------
+  float r;
+  float* part = p.partials + (size_t)blockIdx.x * kLossPartials;
+  r = block_reduce_sum(sum_tp, s_red);  if (tid == 0) part[0] = r;
+  r = block_reduce_sum(sum_ve2, s_red); if (tid == 0) part[1] = r;
+  r = block_reduce_sum(sum_h, s_red);   if (tid == 0) part[2] = r;
+  r = block_reduce_sum(sum_kl, s_red);  if (tid == 0) part[3] = r;
+  r = block_reduce_sum(sum_v, s_red);   if (tid == 0) part[4] = r;
+  r = block_reduce_max(max_a, s_red);   if (tid == 0) part[5] = r;
+  __shared__ bool s_last;
+  if (tid == 0) {
+    __threadfence();
+    const unsigned int prev = atomicAdd(p.ticket, 1u);
+    s_last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float acc6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  // deterministic: thread k sums slices k, k+256, ... then a fixed-order tree.
+  for (unsigned int g = tid; g < gridDim.x; g += kLossThreads) {
+    const volatile float* q = p.partials + (size_t)g * kLossPartials;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) acc6[k] += q[k];
+    acc6[5] = fmaxf(acc6[5], q[5]);
+  }
+  float tot[6];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) tot[k] = block_reduce_sum(acc6[k], s_red);
+  tot[5] = block_reduce_max(acc6[5], s_red);
+  if (tid == 0) {
+    const float policy_loss = -tot[0] * invN;
+    const float mse = tot[1] * invN;
+    const float v_loss = p.cfg.baseline_cost * 0.5f * mse;
+    const float mean_h = tot[2] * invN;
+    const float entropy_loss = -ec * mean_h;
+    const float mean_kl = tot[3] * invN;
+    const float kl_loss = kc * mean_kl;
+    float adj = 0.f, dparam = 0.f;
+    if (p.cfg.has_target_entropy) {                        // :128-132
+      adj = ec * (mean_h - p.cfg.target_entropy);
+      dparam = mul * ec * (mean_h - p.cfg.target_entropy);
+    }
+    float* L = p.loss_terms;
+    L[SEEDRL_LT_TOTAL] = policy_loss + v_loss + entropy_loss + kl_loss + adj;  // :134-135
+    L[SEEDRL_LT_POLICY] = policy_loss;
+    L[SEEDRL_LT_V] = v_loss;
+    L[SEEDRL_LT_ENTROPY] = entropy_loss;
+    L[SEEDRL_LT_KL] = kl_loss;
+    L[SEEDRL_LT_ENTROPY_ADJ] = adj;
+    L[SEEDRL_LT_V_MEAN] = tot[4] * invN;
+    L[SEEDRL_LT_V_L2_ERROR] = sqrtf(mse);
+    L[SEEDRL_LT_MEAN_ENTROPY] = mean_h;
+    L[SEEDRL_LT_ENTROPY_COST] = ec;
+    L[SEEDRL_LT_MEAN_KL] = mean_kl;
+    L[SEEDRL_LT_MAX_ACTION_ABS] = tot[5];
+    for (int k = 12; k < SEEDRL_LOSS_TERMS; ++k) L[k] = 0.f;
+    *p.d_ecp = dparam;
+    *p.ticket = 0u;   // self-reset for the next launch
+  }
+}
+
+static int pick_bb(int T, int A, size_t* smem_bytes) {
+  const int AP = A | 1;
+  for (int BB = 16; BB >= 1; BB >>= 1) {
+    const size_t rows = (size_t)T * BB;
+    const size_t bytes = (rows * AP + rows * 6 + (size_t)(T + 1) * BB + rows + 32) * 4;
+    if (bytes <= 200 * 1024) {
+      *smem_bytes = bytes;
+      return BB;
+    }
+  }
+  return 0;
+}
+
+}  // namespace seedrl
+
+using namespace seedrl;
+
+extern "C" int seedrl_vtrace_from_importance_weights(
+    int T, int B, const float* tlp, const float* blp, const float* disc, const float* rew,
+    const float* val, const float* boot, float clip_rho, float clip_pg, float lambda_,
+    float* vs, float* pg, seedrl_stream_t stream) {
+  SEEDRL_CHECK_ARG(T >= 0 && B >= 0, "T and B must be non-negative");
+  if (T == 0 || B == 0) return SEEDRL_OK;
+  SEEDRL_CHECK_ARG(tlp && blp && disc && rew && val && boot && vs && pg, "null pointer");
+  const int threads = 128;
+  vtrace_kernel<5><<<ceil_div(B, threads), threads, 0, (cudaStream_t)stream>>>(
+      T, B, tlp, blp, disc, rew, val, boot, clip_rho, clip_pg, lambda_, !isnan(clip_rho),
+      !isnan(clip_pg), vs, pg);
+  count_launch();
+  SEEDRL_CHECK_LAUNCH();
+  return SEEDRL_OK;
+}
+
+extern "C" int seedrl_categorical_log_prob(int N, int A, const float* logits,
+                                           const int64_t* actions, float* log_prob,
+                                           seedrl_stream_t stream) {
+  SEEDRL_CHECK_ARG(N >= 0 && A > 0, "bad N/A");
+  if (N == 0) return SEEDRL_OK;
+  SEEDRL_CHECK_ARG(logits && actions && log_prob, "null pointer");
+  categorical_logprob_entropy_kernel<<<ceil_div(N, 8), 256, 0, (cudaStream_t)stream>>>(
+      N, A, logits, actions, log_prob, nullptr);
+  count_launch();
+  SEEDRL_CHECK_LAUNCH();
+  return SEEDRL_OK;
+}
+
+extern "C" int seedrl_categorical_entropy(int N, int A, const float* logits, float* entropy,
+                                          seedrl_stream_t stream) {
+  SEEDRL_CHECK_ARG(N >= 0 && A > 0, "bad N/A");
+  if (N == 0) return SEEDRL_OK;
+  SEEDRL_CHECK_ARG(logits && entropy, "null pointer");
+  categorical_logprob_entropy_kernel<<<ceil_div(N, 8), 256, 0, (cudaStream_t)stream>>>(
+      N, A, logits, nullptr, nullptr, entropy);
+  count_launch();
+  SEEDRL_CHECK_LAUNCH();
+  return SEEDRL_OK;
+}
+
+extern "C" int seedrl_categorical_sample(int N, int A, const float* logits,
+                                         const float* gumbel_noise, uint64_t seed,
+                                         uint64_t offset, int64_t* actions,
+                                         seedrl_stream_t stream) {
+  SEEDRL_CHECK_ARG(N >= 0 && A > 0, "bad N/A");
+  if (N == 0) return SEEDRL_OK;
+  SEEDRL_CHECK_ARG(logits && actions, "null pointer");
+  categorical_sample_kernel<<<ceil_div(N, 128), 128, 0, (cudaStream_t)stream>>>(
+      N, A, logits, gumbel_noise, seed, offset, actions);
+  count_launch();
+  SEEDRL_CHECK_LAUNCH();
+  return SEEDRL_OK;
+}
+
+extern "C" size_t seedrl_vtrace_loss_scratch_bytes(int T1, int B, int A) {
+  size_t smem;
+  const int BB = pick_bb(T1 > 1 ? T1 - 1 : 1, A, &smem);
+  const size_t grid = BB ? (size_t)ceil_div(B, BB) : (size_t)B;
+  return 256 + grid * kLossPartials * sizeof(float);
+}
+
+extern "C" int seedrl_vtrace_loss_fwd_bwd(
+    int T1, int B, int A, const float* learner_logits, const float* learner_baseline,
+    const float* behaviour_logits, const int64_t* actions, const float* rewards,
+    const uint8_t* done, const seedrl_loss_config* cfg, const float* entropy_cost_param,
+    float* loss_terms, float* dlogits, float* dbaseline, float* d_entropy_cost_param,
+    float* vs_out, float* pg_advantages_out, void* scratch, seedrl_stream_t stream) {
+  SEEDRL_CHECK_ARG(T1 >= 2 && B >= 1 && A >= 1, "need T1>=2, B>=1, A>=1");
+  SEEDRL_CHECK_ARG(learner_logits && learner_baseline && behaviour_logits && actions &&
+                       rewards && done && cfg && entropy_cost_param && loss_terms &&
+                       dlogits && dbaseline && d_entropy_cost_param && scratch,
+                   "null pointer");
+  LossParams p;
+  p.T = T1 - 1; p.B = B; p.A = A;
+  size_t smem = 0;
+  p.BB = pick_bb(p.T, A, &smem);
+  SEEDRL_CHECK_ARG(p.BB > 0, "unroll_length * num_actions too large for shared memory");
+  p.AP = A | 1;
+  p.ll = learner_logits; p.lb = learner_baseline; p.bl = behaviour_logits;
+  p.act = actions; p.rew = rewards; p.done = done; p.cfg = *cfg; p.ecp = entropy_cost_param;
+  p.loss_terms = loss_terms; p.dlogits = dlogits; p.dbaseline = dbaseline;
+  p.d_ecp = d_entropy_cost_param; p.vs_out = vs_out; p.pg_out = pg_advantages_out;
+  p.ticket = reinterpret_cast<unsigned int*>(scratch);
+  p.partials = reinterpret_cast<float*>(reinterpret_cast<char*>(scratch) + 256);
+  static bool attr_set = false;
+  if (!attr_set) {
+    SEEDRL_CUDA(cudaFuncSetAttribute(vtrace_loss_kernel,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  vtrace_loss_kernel<<<ceil_div(B, p.BB), kLossThreads, smem, (cudaStream_t)stream>>>(p);
+  count_launch();
+  SEEDRL_CHECK_LAUNCH();
+  return SEEDRL_OK;
+}
