@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- learner env-frames/sec of the V-trace hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            (this framework, CUDA)
+  python bench.py --impl reference --gpus N --steps K ...  (the reference's algorithm on
+                                                            the host CPU cores: oracle port)
+Under torchrun (N > 1) every rank runs one learner replica on its own GPU (batch-axis
+sharding, B=64 unrolls per GPU) with ONE NCCL all-reduce(SUM) of the flat gradient arena
+per step; the timed region is bracketed by barrier + synchronize, timed with CUDA events,
+MAX over ranks; rank 0 prints one JSON line.
+
+A "step" = one `minimize` (reference agents/vtrace/learner.py:255-280) on one synthetic
+unroll batch already resident in HBM: ImpalaDeep unroll forward -> fused V-trace loss ->
+backward -> [all-reduce] -> Adam.  metric = B_global * T * num_action_repeats / step_time
+(== the reference's speed/steps_per_sec, common/utils.py:659-661).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'env-frames/sec (learner, device-timed) on synthetic 84x84x4 T=20 unrolls @1/2/4/8 B200'
+UNIT = 'env-frames/s'
+A = 18
+OBS = (84, 84, 4)
+
+
+def parse_args():
+  p = argparse.ArgumentParser()
+  p.add_argument('--gpus', type=int, default=1)
+  p.add_argument('--steps', type=int, default=20)
+  p.add_argument('--warmup', type=int, default=5)
+  p.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+  p.add_argument('--net', default='deep', choices=['deep', 'shallow'])
+  p.add_argument('--batch', type=int, default=64, help='unrolls per GPU')
+  p.add_argument('--unroll', type=int, default=20)
+  p.add_argument('--cpu-batch', type=int, default=8, help='unrolls per CPU-baseline step')
+  p.add_argument('--no-extras', action='store_true',
+                 help='skip the profiling pass, the loss-kernel sweep and the CPU baseline')
+  return p.parse_args()
+
+
+# ----------------------------------------------------------------------------------------
+def cpu_learner_throughput(net, T, B, steps, warmup, threads=None):
+  """The reference's algorithm (oracle port, torch-CPU fp32) on the host cores."""
+  import torch
+  from oracle import learner_oracle, loss_oracle
+  if threads:
+    torch.set_num_threads(threads)
+  cores = torch.get_num_threads()
+  cfg = loss_oracle.default_config()
+  lr = learner_oracle.CpuLearner(net, A, OBS, cfg, lr=4.8e-4, beta1=0.0, eps=3.125e-7,
+                                 decay_steps=10**6)
+  batch = learner_oracle.synthetic_batch(T, B, A, OBS, seed=1234)
+  for _ in range(warmup):
+    lr.step(batch)
+  t0 = time.perf_counter()
+  for _ in range(steps):
+    lr.step(batch)
+  dt = (time.perf_counter() - t0) / max(steps, 1)
+  return dict(value=B * T / dt, ms_per_step=dt * 1e3, cores=cores,
+              sample='%d steps of B=%d unrolls x T=%d (%s net) after %d warm-up; torch-CPU fp32 '
+                     'oracle port, %d threads' % (steps, B, T, net, warmup, cores))
+
+
+def run_reference(args):
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  r = cpu_learner_throughput(args.net, args.unroll, args.cpu_batch, args.steps, min(args.warmup, 2))
+  line = {
+      'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT,
+      'n_gpus': args.gpus, 'steps': args.steps, 'warmup': min(args.warmup, 2),
+      'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
+      'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'config': workload_config(args, 1, cpu=True),
+      'cpu_baseline': {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
+                       'sample': r['sample']},
+      'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+      'gpu_launches': 0,
+      'note': 'TensorFlow 2.4.1 is not installable here (no network): this arm times the CPU '
+              'oracle, a line-by-line torch-CPU restatement of the reference learner step.'}
+  print(json.dumps(line))
+
+
+def workload_config(args, n, cpu=False):
+  return {
+      'workload': 'Impala%s learner step, T=%d, B=%d unrolls/GPU, synthetic 84x84x4 uint8 '
+                  '(BASELINE configs[3]; per-GPU slice is the configs[1]/[2] shape)' %
+                  ('Deep' if args.net == 'deep' else 'Shallow', args.unroll, args.batch),
+      'net': 'ImpalaDeep (dmlab/networks.py:63-171)' if args.net == 'deep' else 'IMPALA shallow (paper)',
+      'unroll_length': args.unroll, 'batch_per_gpu': args.cpu_batch if cpu else args.batch,
+      'global_batch': (args.cpu_batch if cpu else args.batch * n), 'num_actions': A,
+      'num_action_repeats': 1,
+      'optimizer': 'Adam lr=4.8e-4 beta1=0 eps=3.125e-7 (dmlab/vtrace_main.py:46-51)',
+      'loss': 'gamma=0.99 lambda=1 baseline_cost=0.5 entropy_cost=2.5e-4 kl_cost=0',
+      'grad_reduce': 'sum', 'parallelism': 'dp%d' % n,
+      'l2': 'per-step inputs (37.9 MB uint8 frames) + activations (>2 GB) exceed the 126 MB L2; '
+            'no explicit flush'}
+
+
+# ----------------------------------------------------------------------------------------
+class ClockSampler(object):
+  Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+       'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+       'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, gpu_index):
+    self.gpu = gpu_index
+    self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
+    try:
+      self.p = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                 '-lms', '100', '-i', str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+    except Exception:
+      self.p = None
+
+  def stop(self):
+    out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+    if self.p is None:
+      return out
+    self.p.terminate()
+    try:
+      self.p.wait(5)
+    except Exception:
+      self.p.kill()
+    self.f.flush()
+    rows = [l.strip().split(', ') for l in open(self.f.name) if l.strip()]
+    os.unlink(self.f.name)
+    sm, reasons, mx = [], set(), None
+    for r in rows:
+      try:
+        sm.append(float(r[1])); mx = float(r[2])
+        for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[5:9]):
+          if v.strip() == 'Active':
+            reasons.add(name)
+      except Exception:
+        pass
+    if sm:
+      sm.sort()
+      out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+    return out
+
+
+def conv_bytes_per_step(N, cat):
+  """Algorithmic HBM bytes of one learner step for the conv categories (ImpalaDeep,
+  fp32 activations, uint8 frames): every operand read once, every result written once."""
+  stacks = [(84, 84, 4, 16), (42, 42, 16, 32), (21, 21, 32, 32)]
+  tot, launches = 0, 0
+  for si, (h, w, cin, c) in enumerate(stacks):
+    ho, wo = (h + 1) // 2, (w + 1) // 2
+    full_in = N * h * w * cin * (1 if si == 0 else 4)
+    full_out = N * h * w * c * 4
+    pooled = N * ho * wo * c * 4
+    if cat == 'conv3x3_fwd':
+      tot += full_in + full_out          # stack conv
+      tot += 4 * (2 * pooled) + 2 * pooled   # 4 res convs (in+out) + 2 residual reads
+      launches += 5
+    elif cat == 'conv3x3_dgrad':
+      tot += 4 * (2 * pooled) + 4 * pooled + 2 * pooled   # dy in, dx out, mask reads, 2 residual reads
+      launches += 4
+      if si > 0:
+        tot += full_out + N * h * w * cin * 4
+        launches += 1
+    elif cat == 'conv3x3_wgrad':
+      tot += full_in + full_out + 4 * (2 * pooled)        # x and dy read once per conv
+      launches += 10                                      # kernel + reduce per conv
+  return tot, launches
+
+
+def main():
+  args = parse_args()
+  if args.impl == 'reference':
+    return run_reference(args)
+
+  import numpy as np
+  import torch
+  import torch.distributed as dist
+  from seed_rl_b200 import _lib
+  from seed_rl_b200.agents.vtrace import learner
+  from seed_rl_b200.common import optimizers, utils
+  from seed_rl_b200.dmlab import networks
+
+  if not torch.cuda.is_available():
+    raise SystemExit('bench.py: no CUDA device. The product path has no CPU fallback; use '
+                     '--impl reference for the CPU oracle arm.')
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  torch.cuda.set_device(local)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+  T, B = args.unroll, args.batch
+  T1 = T + 1
+
+  # ---- synthetic batch, seeded per rank, pinned on the host ----------------
+  rng = np.random.default_rng(1234 + rank)
+  host = dict(
+      observation=rng.integers(0, 256, (T1, B) + OBS, dtype=np.uint8),
+      reward=rng.normal(size=(T1, B)).astype(np.float32),
+      done=rng.random((T1, B)) < 0.02,
+      prev_actions=rng.integers(0, A, (T1, B), dtype=np.int64),
+      action=rng.integers(0, A, (T1, B), dtype=np.int64),
+      behaviour_logits=rng.normal(size=(T1, B, A)).astype(np.float32),
+      behaviour_baseline=rng.normal(size=(T1, B)).astype(np.float32),
+      h0=np.zeros((B, 256), np.float32), c0=np.zeros((B, 256), np.float32))
+  pinned = {k: torch.from_numpy(v).pin_memory() for k, v in host.items()}
+  h2d_bytes = sum(v.numel() * v.element_size() for v in pinned.values())
+  dev = {k: torch.empty_like(v, device='cuda') for k, v in pinned.items()}
+
+  def upload():
+    for k in pinned:
+      dev[k].copy_(pinned[k], non_blocking=True)
+
+  def make_unroll():
+    env = utils.EnvOutput(dev['reward'], dev['done'], dev['observation'],
+                          torch.zeros(T1, B, dtype=torch.bool, device='cuda'),
+                          torch.zeros(T1, B, dtype=torch.int32, device='cuda'))
+    ao = networks.AgentOutput(dev['action'], dev['behaviour_logits'], dev['behaviour_baseline'])
+    return learner.Unroll((dev['h0'], dev['c0']), dev['prev_actions'], env, ao)
+
+  upload()
+  unroll = make_unroll()
+  cls = networks.ImpalaDeep if args.net == 'deep' else networks.ImpalaShallow
+  agent = cls(A, OBS, seed=0)            # same seed on every rank: replicas start identical
+  opt = optimizers.Adam(optimizers.PolynomialDecay(4.8e-4, 10**6, 0.0), beta_1=0.0, epsilon=3.125e-7)
+  step = learner.LearnerStep(agent, opt, settings=learner.default_loss_settings(), grad_reduce='sum')
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  def timed(fn, k):
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(k):
+      fn()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device='cuda')
+    if world > 1:
+      dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms) / k
+
+  # ---- kernel-only (inputs resident in HBM) --------------------------------------------
+  for _ in range(max(args.warmup, 3)):
+    step.minimize(unroll)
+  sampler = ClockSampler(local) if rank == 0 else None
+  n0 = _lib.launch_count()
+  ms_step = timed(lambda: step.minimize(unroll), args.steps)
+  launches = (_lib.launch_count() - n0) // args.steps
+  clocks = sampler.stop() if sampler else None
+  value = world * B * T / (ms_step * 1e-3)
+
+  # ---- end to end: pinned host batch -> H2D -> step -> loss to host ---------------------
+  d2h_bytes = 4
+
+  def e2e_step():
+    upload()
+    loss, _ = step.minimize(unroll)
+    float(loss)          # device -> host read of the step's result
+  for _ in range(2):
+    e2e_step()
+  ms_e2e = timed(e2e_step, args.steps)
+  e2e_value = world * B * T / (ms_e2e * 1e-3)
+
+  line = {
+      'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+      'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True,
+      'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+      'config': workload_config(args, world), 'clocks': clocks,
+      'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e,
+              'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes,
+              'api': 'seed_rl_b200.agents.vtrace.learner.LearnerStep.minimize(Unroll)'},
+      'gpu_launches': int(launches * args.steps), 'gpu_launches_per_step': int(launches),
+      'impl': 'b200'}
+
+  peaks = {}
+  try:
+    peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+  except Exception:
+    pass
+  hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+  peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s'
+
+  if not args.no_extras:
+    # ---- profiling pass (separate from the timed regions) --------------------------------
+    L = _lib.lib()
+    ncat = L.seedrl_profile_num_categories()
+    ms_c = (ctypes.c_double * ncat)(); n_c = (ctypes.c_uint64 * ncat)()
+    PSTEPS = 3
+    barrier()
+    _lib.check(L.seedrl_profile_begin(_lib.stream_ptr()))
+    for _ in range(PSTEPS):
+      step.minimize(unroll)
+    _lib.check(L.seedrl_profile_end(ms_c, n_c))
+    barrier()
+    cats = {L.seedrl_profile_category_name(i).decode(): (ms_c[i] / PSTEPS, int(n_c[i]) // PSTEPS)
+            for i in range(ncat)}
+    tot = sum(v[0] for v in cats.values())
+    line['kernel_time_ms_per_step'] = {k: round(v[0], 4) for k, v in cats.items()}
+    line['kernel_launches_per_step'] = {k: v[1] for k, v in cats.items()}
+    if args.net == 'deep':
+      conv_cats = [k for k in ('conv3x3_fwd', 'conv3x3_dgrad', 'conv3x3_wgrad')]
+      dom = max(conv_cats, key=lambda k: cats[k][0])
+      nbytes, nl = conv_bytes_per_step(T1 * B, dom)
+      ms_dom = cats[dom][0]
+      ach = nbytes / (ms_dom * 1e-3) / 1e9
+      line['roofline'] = {
+          'kernel': dom, 'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s',
+          'frac': ach / hbm_peak, 'traffic': None,
+          'algorithmic_bytes_per_launch': nbytes / max(cats[dom][1], 1),
+          'avg_launch_ms': ms_dom / max(cats[dom][1], 1), 'launches_per_step': cats[dom][1],
+          'share_of_step': ms_dom / tot if tot else None, 'peak_source': peak_src,
+          'note': 'fp32 SIMT kernels: FMA-bound today; the HBM roofline is the bound a '
+                  'tensor-core (tcgen05) implementation of this layer would have'}
+
+    if rank == 0 and world == 1:
+      # ---- the fused V-trace loss kernel: B sweep (north star: >= 60% HBM at streaming size)
+      sweep = []
+      st = learner.default_loss_settings()
+      ecp = agent.entropy_cost_param
+      for Bs in (64, 4096, 65536):
+        g = torch.Generator(device='cuda').manual_seed(0)
+        ll = torch.randn(T1, Bs, A, device='cuda', generator=g); lb = torch.randn(T1, Bs, device='cuda', generator=g)
+        bl = torch.randn(T1, Bs, A, device='cuda', generator=g)
+        act = torch.randint(0, A, (T1, Bs), device='cuda', generator=g)
+        rew = torch.randn(T1, Bs, device='cuda', generator=g); dn = torch.rand(T1, Bs, device='cuda', generator=g) < 0.02
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+        for _ in range(3):
+          learner.vtrace_loss_fwd_bwd(st, ll, lb, bl, act, rew, dn, ecp)
+        times = []
+        for _ in range(10):
+          flush.zero_()          # evict L2 (256 MB > 126 MB)
+          e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+          e0.record()
+          learner.vtrace_loss_fwd_bwd(st, ll, lb, bl, act, rew, dn, ecp)
+          e1.record(); torch.cuda.synchronize()
+          times.append(e0.elapsed_time(e1))
+        times.sort()
+        ms = times[len(times) // 2]
+        nb = (161 + 76) * T * Bs + 4 * Bs + 32          # SURVEY 8(d) algorithmic bytes
+        sweep.append({'B': Bs, 'ms': ms, 'algorithmic_bytes': nb, 'GBps': nb / (ms * 1e-3) / 1e9,
+                      'frac_of_hbm_peak': nb / (ms * 1e-3) / 1e9 / hbm_peak})
+        del ll, lb, bl, act, rew, dn, flush
+      line['roofline_vtrace_loss'] = {'bound': 'hbm', 'peak': hbm_peak, 'unit': 'GB/s',
+                                      'peak_source': peak_src, 'l2': 'flushed between launches',
+                                      'timing': 'median of 10 single launches incl. torch wrapper '
+                                                'allocations on the stream', 'sweep': sweep}
+      # ---- CPU baseline beside it (bounded sample) ----------------------------------------
+      r = cpu_learner_throughput(args.net, T, args.cpu_batch, 3, 1)
+      line['cpu_baseline'] = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
+                              'sample': r['sample'], 'ms_per_step': r['ms_per_step']}
+
+  if rank == 0:
+    print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+  main()

@@ -263,6 +263,39 @@ int seedrl_batcher_next_full(seedrl_batcher* b, int timeout_ms, int* slab);
 int seedrl_batcher_publish(seedrl_batcher* b, int slab, int status);
 int seedrl_batcher_shutdown(seedrl_batcher* b);
 
+/* ------------------------------------------------------------------------
+ * Per-category kernel timing for bench.py's profiling pass: between begin and end
+ * every kernel launch of this library is followed by a CUDA event on its stream (a
+ * kernel's time = the gap to the previous event, i.e. back-to-back device time);
+ * end() synchronises and returns summed milliseconds and launch counts per category
+ * (arrays of seedrl_profile_num_categories() entries).  Never on in a timed region. */
+int seedrl_profile_num_categories(void);
+const char* seedrl_profile_category_name(int i);
+int seedrl_profile_begin(seedrl_stream_t stream);
+int seedrl_profile_end(double* ms_per_category, uint64_t* launches_per_category);
+
+/* ------------------------------------------------------------------------
+ * Single-kernel test hooks: let the GPU parity tests localise a failure to one
+ * kernel of the network schedule.  Not part of the drop-in surface.
+ * in_mode: 0 fp32 input, 1 relu(input), 2 uint8 input / 255. */
+int seedrl_debug_conv3x3(int cin, int cout, int in_mode, int N, int H, int W,
+                         const void* in, const float* w, const float* bias,
+                         const float* mask, const float* res, float* out,
+                         seedrl_stream_t stream);
+int seedrl_debug_conv3x3_flip(int cin, int cout, const float* w, float* wt,
+                              seedrl_stream_t stream);
+size_t seedrl_debug_wgrad_partial_bytes(void);
+int seedrl_debug_conv3x3_wgrad(int cin, int cout, int in_mode, int N, int H, int W,
+                               const void* x, const float* dy, float* dw, float* db,
+                               float* partial, size_t partial_bytes,
+                               seedrl_stream_t stream);
+int seedrl_debug_maxpool(int backward, int N, int H, int W, int C, const float* x_or_dy,
+                         float* y_or_dx, uint8_t* idx, seedrl_stream_t stream);
+int seedrl_debug_sgemm(int ta, int tb, int M, int N, int K, const float* A, int lda,
+                       const float* B, int ldb, float* C, int ldc, const float* bias,
+                       const float* mask, int ldm, int relu, int accumulate, int a_relu,
+                       seedrl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

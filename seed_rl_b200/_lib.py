@@ -90,6 +90,19 @@ SIGNATURES = {
     'seedrl_batcher_next_full': (c_int, [P, c_int, ctypes.POINTER(c_int)]),
     'seedrl_batcher_publish': (c_int, [P, c_int, c_int]),
     'seedrl_batcher_shutdown': (c_int, [P]),
+    'seedrl_profile_num_categories': (c_int, []),
+    'seedrl_profile_category_name': (ctypes.c_char_p, [c_int]),
+    'seedrl_profile_begin': (c_int, [P]),
+    'seedrl_profile_end': (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_u64)]),
+    'seedrl_debug_conv3x3': (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),
+    'seedrl_debug_conv3x3_flip': (c_int, [c_int, c_int, P, P, P]),
+    'seedrl_debug_wgrad_partial_bytes': (c_size_t, []),
+    'seedrl_debug_conv3x3_wgrad':
+        (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, c_size_t, P]),
+    'seedrl_debug_maxpool': (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
+    'seedrl_debug_sgemm':
+        (c_int, [c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_int, P, c_int, P, P, c_int,
+                 c_int, c_int, c_int, P]),
 }
 
 _lib = None

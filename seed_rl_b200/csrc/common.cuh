@@ -19,9 +19,7 @@ inline int set_error(int code, const std::string& msg) {
   return code;
 }
 
-inline void count_launch(int n = 1) {
-  g_launch_count.fetch_add((uint64_t)n, std::memory_order_relaxed);
-}
+
 
 #define SEEDRL_CHECK_ARG(cond, msg)                                         \
   do {                                                                      \
@@ -47,6 +45,20 @@ inline void count_launch(int n = 1) {
           SEEDRL_ERR_INTERNAL,                                              \
           std::string(__func__) + ": " #call ": " + cudaGetErrorString(e__)); \
   } while (0)
+
+// Optional per-category kernel timing (CUDA events on the launching stream), used by
+// bench.py's separate profiling pass -- never inside a timed region.
+enum ProfCat { PC_CONV_FWD = 0, PC_CONV_DGRAD, PC_CONV_WGRAD, PC_POOL, PC_GEMM, PC_LSTM_PW,
+               PC_LOSS, PC_ADAM, PC_VTRACE, PC_MISC, PC_COUNT };
+extern bool g_prof_on;
+extern int g_conv_cat;
+// One event AFTER each launch; a kernel's time = gap to the previous event on the stream.
+void prof_mark_(int cat, cudaStream_t st);
+
+inline void count_launch(int cat = PC_MISC, cudaStream_t st = 0) {
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
+  if (g_prof_on) prof_mark_(cat, st);
+}
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 

@@ -200,7 +200,7 @@ static int launch_conv3x3(int N, int H, int W, const void* in, const float* w, c
   const long long grid = (g.Q + Cfg::QC - 1) / Cfg::QC;
   conv3x3_kernel<CIN, COUT, IN_MODE><<<(unsigned)grid, Cfg::kThreads, smem, st>>>(g, in, w, bias,
                                                                                  mask, res, out);
-  count_launch();
+  count_launch(g_conv_cat, st);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
 }
@@ -237,7 +237,7 @@ __global__ void flip_transpose_w_kernel(int cin, int cout, const float* __restri
 int conv3x3_flip_weights(int cin, int cout, const float* w, float* wt, cudaStream_t st) {
   const int n = 9 * cin * cout;
   flip_transpose_w_kernel<<<ceil_div(n, 256), 256, 0, st>>>(cin, cout, w, wt);
-  count_launch();
+  count_launch(PC_MISC, st);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
 }
@@ -408,10 +408,10 @@ static int launch_wgrad(int N, int H, int W, const void* x, const float* dy, flo
   if ((size_t)grid * NW * sizeof(float) > partial_bytes)
     return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "wgrad: partial buffer too small");
   conv3x3_wgrad_kernel<CIN, COUT, IN_MODE><<<grid, Cfg::kThreads, smem, st>>>(g, x, dy, partial);
-  count_launch();
+  count_launch(PC_CONV_WGRAD, st);
   SEEDRL_CHECK_LAUNCH();
   wgrad_reduce_kernel<<<ceil_div(NW, 256), 256, 0, st>>>(grid, 9 * CIN * COUT, COUT, partial, dw, db);
-  count_launch();
+  count_launch(PC_CONV_WGRAD, st);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
 }
@@ -419,7 +419,7 @@ static int launch_wgrad(int N, int H, int W, const void* x, const float* dy, flo
 int wgrad_reduce(int nparts, int nw, int nb, const float* partial, float* dw, float* db,
                  cudaStream_t st) {
   wgrad_reduce_kernel<<<ceil_div(nw + nb, 256), 256, 0, st>>>(nparts, nw, nb, partial, dw, db);
-  count_launch();
+  count_launch(PC_CONV_WGRAD, st);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
 }
@@ -535,7 +535,7 @@ int maxpool3s2_forward(int N, int H, int W, int C, const float* x, float* y, uin
   const long long total = (long long)N * Ho * Wo * (C / 4);
   maxpool3s2_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(N, H, W, C, Ho, Wo, pt, pl,
                                                                          x, y, idx);
-  count_launch();
+  count_launch(PC_POOL, st);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
 }
@@ -548,7 +548,7 @@ int maxpool3s2_backward(int N, int H, int W, int C, const float* dy, const uint8
   const long long total = (long long)N * H * W * (C / 4);
   maxpool3s2_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(N, H, W, C, Ho, Wo, pt, pl,
                                                                          dy, idx, dx);
-  count_launch();
+  count_launch(PC_POOL, st);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
 }

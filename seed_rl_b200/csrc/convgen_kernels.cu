@@ -148,7 +148,7 @@ int convgen_forward(int N, int H, int W, int cin, int cout, int k, int stride, i
   const unsigned grid = (unsigned)((total + 255) / 256);
   if (in_u8) convgen_fwd_kernel<true><<<grid, 256, 0, st>>>(N, H, W, cin, cout, k, stride, Ho, Wo, in, w, bias, relu, out);
   else convgen_fwd_kernel<false><<<grid, 256, 0, st>>>(N, H, W, cin, cout, k, stride, Ho, Wo, in, w, bias, relu, out);
-  count_launch();
+  count_launch(PC_CONV_FWD, st);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
 }
@@ -159,7 +159,7 @@ int convgen_dgrad(int N, int H, int W, int cin, int cout, int k, int stride, con
   const long long total = (long long)N * H * W * cin;
   convgen_dgrad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(N, H, W, cin, cout, k, stride,
                                                                         Ho, Wo, dy, w, mask, dx);
-  count_launch();
+  count_launch(PC_CONV_DGRAD, st);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
 }
@@ -182,7 +182,7 @@ int convgen_wgrad(int N, int H, int W, int cin, int cout, int k, int stride, int
     if (small) convgen_wgrad_kernel<false, 16><<<grid, 256, 0, st>>>(N, H, W, cin, cout, k, stride, Ho, Wo, x, dy, partial);
     else convgen_wgrad_kernel<false, 32><<<grid, 256, 0, st>>>(N, H, W, cin, cout, k, stride, Ho, Wo, x, dy, partial);
   }
-  count_launch();
+  count_launch(PC_CONV_WGRAD, st);
   SEEDRL_CHECK_LAUNCH();
   return wgrad_reduce(grid, nw, cout, partial, dw, db, st);
 }

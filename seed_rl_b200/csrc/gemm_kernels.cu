@@ -92,7 +92,7 @@ int sgemm(bool ta, bool tb, int M, int N, int K, const float* A, int lda, const 
   else if (ta && !tb) sgemm_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, e);
   else if (!ta && tb) sgemm_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, e);
   else sgemm_kernel<true, true><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, e);
-  count_launch();
+  count_launch(PC_GEMM, st);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
 }
@@ -119,7 +119,7 @@ __global__ void colsum_kernel(int M, int N, const float* __restrict__ X, int ld,
 
 int colsum(int M, int N, const float* X, int ld, float* out, cudaStream_t st) {
   colsum_kernel<<<ceil_div(N, 32), 256, 0, st>>>(M, N, X, ld, out);
-  count_launch();
+  count_launch(PC_GEMM, st);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
 }
@@ -144,7 +144,7 @@ int core_input_tail(int Nrows, int D, int A, const float* reward, const int64_t*
                     float* core_in, cudaStream_t st) {
   const int n = Nrows * (1 + A);
   core_input_tail_kernel<<<ceil_div(n, 256), 256, 0, st>>>(Nrows, D, A, reward, prev_action, core_in);
-  count_launch();
+  count_launch(PC_MISC, st);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
 }
@@ -225,7 +225,7 @@ __global__ void lstm_pointwise_bwd_kernel(int B, int Hd, const float* __restrict
 int lstm_mask_state(int B, int Hd, const uint8_t* done, const float* h_src, float* h_dst,
                     cudaStream_t st) {
   lstm_mask_state_kernel<<<ceil_div(B * Hd, 256), 256, 0, st>>>(B, Hd, done, h_src, h_dst);
-  count_launch();
+  count_launch(PC_LSTM_PW, st);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
 }
@@ -234,7 +234,7 @@ int lstm_pointwise_fwd(int B, int Hd, float* z, const float* c_prev_src, const u
                        cudaStream_t st) {
   lstm_pointwise_fwd_kernel<<<ceil_div(B * Hd, 256), 256, 0, st>>>(B, Hd, z, c_prev_src, done_t,
                                                                    done_next, c_out, h_out, hprev_next);
-  count_launch();
+  count_launch(PC_LSTM_PW, st);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
 }
@@ -244,7 +244,7 @@ int lstm_pointwise_bwd(int B, int Hd, const float* gates, const float* c_t, cons
                        cudaStream_t st) {
   lstm_pointwise_bwd_kernel<<<ceil_div(B * Hd, 256), 256, 0, st>>>(
       B, Hd, gates, c_t, c_prev_src, done_t, done_next, dh_out, dh_rec, dc_next, dz, dc_prev_out);
-  count_launch();
+  count_launch(PC_LSTM_PW, st);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
 }
@@ -257,7 +257,7 @@ __global__ void fill_kernel(size_t n, float* p, float v) {
 int fill(size_t n, float* p, float v, cudaStream_t st) {
   if (n == 0) return SEEDRL_OK;
   fill_kernel<<<(unsigned)ceil_div_sz(n, 256), 256, 0, st>>>(n, p, v);
-  count_launch();
+  count_launch(PC_MISC, st);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
 }

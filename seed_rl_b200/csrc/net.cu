@@ -384,7 +384,10 @@ static int conv_bwd(const seedrl_net* n, const float* prm, float* grd, const Con
   if (dx) {  // data gradient = conv with flipped, transposed weights
     float* wt = W<float>(ws, pl.wt);
     SEEDRL_TRY(conv3x3_flip_weights(l.cin, l.cout, P(n, prm, l.w), wt, st));
-    SEEDRL_TRY(conv3x3_forward(l.cout, l.cin, IN_F32, N, H, Wd, dy, wt, nullptr, dmask, dres, dx, st));
+    g_conv_cat = PC_CONV_DGRAD;
+    const int rc = conv3x3_forward(l.cout, l.cin, IN_F32, N, H, Wd, dy, wt, nullptr, dmask, dres, dx, st);
+    g_conv_cat = PC_CONV_FWD;
+    SEEDRL_TRY(rc);
   }
   return SEEDRL_OK;
 }
@@ -501,4 +504,38 @@ extern "C" int seedrl_net_backward(const seedrl_net* n, const float* prm, int T1
                    W<float>(ws, pl.gA), n->flat, ef, st));
   if (n->cfg.net == SEEDRL_NET_DEEP) return torso_backward_deep(n, prm, grd, pl, observation, ws, st);
   return torso_backward_shallow(n, prm, grd, pl, observation, ws, st);
+}
+
+// ---- single-kernel test hooks (exported so the GPU parity tests can localise a
+// failure to one kernel; not used by the product path) ------------------------------
+extern "C" int seedrl_debug_conv3x3(int cin, int cout, int in_mode, int N, int H, int W,
+                                    const void* in, const float* w, const float* bias,
+                                    const float* mask, const float* res, float* out,
+                                    seedrl_stream_t stream) {
+  return conv3x3_forward(cin, cout, in_mode, N, H, W, in, w, bias, mask, res, out,
+                         (cudaStream_t)stream);
+}
+extern "C" int seedrl_debug_conv3x3_flip(int cin, int cout, const float* w, float* wt,
+                                         seedrl_stream_t stream) {
+  return conv3x3_flip_weights(cin, cout, w, wt, (cudaStream_t)stream);
+}
+extern "C" size_t seedrl_debug_wgrad_partial_bytes(void) { return conv3x3_wgrad_partial_bytes(); }
+extern "C" int seedrl_debug_conv3x3_wgrad(int cin, int cout, int in_mode, int N, int H, int W,
+                                          const void* x, const float* dy, float* dw, float* db,
+                                          float* partial, size_t partial_bytes,
+                                          seedrl_stream_t stream) {
+  return conv3x3_wgrad(cin, cout, in_mode, N, H, W, x, dy, dw, db, partial, partial_bytes,
+                       (cudaStream_t)stream);
+}
+extern "C" int seedrl_debug_maxpool(int backward, int N, int H, int W, int C, const float* x_or_dy,
+                                    float* y_or_dx, uint8_t* idx, seedrl_stream_t stream) {
+  if (backward) return maxpool3s2_backward(N, H, W, C, x_or_dy, idx, y_or_dx, (cudaStream_t)stream);
+  return maxpool3s2_forward(N, H, W, C, x_or_dy, y_or_dx, idx, (cudaStream_t)stream);
+}
+extern "C" int seedrl_debug_sgemm(int ta, int tb, int M, int N, int K, const float* A, int lda,
+                                  const float* B, int ldb, float* C, int ldc, const float* bias,
+                                  const float* mask, int ldm, int relu, int accumulate, int a_relu,
+                                  seedrl_stream_t stream) {
+  GemmEpi e{bias, mask, ldm, relu, accumulate, a_relu};
+  return sgemm(ta != 0, tb != 0, M, N, K, A, lda, B, ldb, C, ldc, e, (cudaStream_t)stream);
 }

@@ -72,12 +72,12 @@ extern "C" int seedrl_adam_apply(size_t n, float* params, const float* grads, fl
                                                          beta2, eps, grad_scale,
                                                          (long long)clamp_index, clamp_lo,
                                                          clamp_hi);
-  count_launch();
+  count_launch(PC_ADAM, (cudaStream_t)stream);
   SEEDRL_CHECK_LAUNCH();
   if (clamp_index >= 0) {
     clamp_one_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(params, (long long)clamp_index, clamp_lo,
                                                          clamp_hi);
-    count_launch();
+    count_launch(PC_ADAM, (cudaStream_t)stream);
     SEEDRL_CHECK_LAUNCH();
   }
   return SEEDRL_OK;

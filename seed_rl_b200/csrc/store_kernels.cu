@@ -119,7 +119,7 @@ extern "C" int seedrl_store_append_field(uint8_t* state, const int32_t* index, c
   const int threads = row_bytes >= 4096 ? 256 : (row_bytes >= 512 ? 128 : 32);
   store_append_kernel<<<n, threads, 0, (cudaStream_t)stream>>>(state, index, env_ids, full_length,
                                                                row_bytes, values);
-  count_launch();
+  count_launch(PC_MISC, (cudaStream_t)stream);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
 }
@@ -130,7 +130,7 @@ extern "C" int seedrl_store_advance(int32_t* index, const int32_t* env_ids, int 
   SEEDRL_CHECK_ARG(index && env_ids && completed_ids && num_completed && n >= 0, "bad argument");
   store_advance_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(index, env_ids, n, full_length,
                                                             completed_ids, num_completed);
-  count_launch();
+  count_launch(PC_MISC, (cudaStream_t)stream);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
 }
@@ -146,11 +146,11 @@ extern "C" int seedrl_store_gather_field(uint8_t* state, const int32_t* complete
   const int threads = row_bytes >= 4096 ? 256 : (row_bytes >= 512 ? 128 : 32);
   store_gather_kernel<<<dim3(n_completed, full_length), threads, 0, (cudaStream_t)stream>>>(
       state, completed_ids, n_completed, full_length, row_bytes, time_major, unrolls);
-  count_launch();
+  count_launch(PC_MISC, (cudaStream_t)stream);
   SEEDRL_CHECK_LAUNCH();
   store_carry_kernel<<<dim3(n_completed, j), threads, 0, (cudaStream_t)stream>>>(
       state, completed_ids, n_completed, full_length, row_bytes, j, time_major, unrolls);
-  count_launch();
+  count_launch(PC_MISC, (cudaStream_t)stream);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
 }
@@ -160,7 +160,7 @@ extern "C" int seedrl_store_finish(int32_t* index, const int32_t* completed_ids,
   if (n_completed == 0) return SEEDRL_OK;
   store_set_index_kernel<<<ceil_div(n_completed, 128), 128, 0, (cudaStream_t)stream>>>(
       index, completed_ids, n_completed, 1 + overlap);   // utils.py:254-255
-  count_launch();
+  count_launch(PC_MISC, (cudaStream_t)stream);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
 }
@@ -173,13 +173,13 @@ extern "C" int seedrl_store_reset(uint8_t* state, int32_t* index, const int32_t*
   if (index) {
     store_set_index_kernel<<<ceil_div(n, 128), 128, 0, (cudaStream_t)stream>>>(index, env_ids, n,
                                                                                overlap);  // :207-208
-    count_launch();
+    count_launch(PC_MISC, (cudaStream_t)stream);
     SEEDRL_CHECK_LAUNCH();
   }
   if (state && overlap > 0 && row_bytes > 0) {                                            // :212-225
     store_zero_rows_kernel<<<dim3(n, overlap), 128, 0, (cudaStream_t)stream>>>(state, env_ids,
                                                                               full_length, row_bytes);
-    count_launch();
+    count_launch(PC_MISC, (cudaStream_t)stream);
     SEEDRL_CHECK_LAUNCH();
   }
   return SEEDRL_OK;

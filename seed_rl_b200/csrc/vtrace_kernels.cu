@@ -465,7 +465,7 @@ extern "C" int seedrl_vtrace_from_importance_weights(
   vtrace_kernel<5><<<ceil_div(B, threads), threads, 0, (cudaStream_t)stream>>>(
       T, B, tlp, blp, disc, rew, val, boot, clip_rho, clip_pg, lambda_, !isnan(clip_rho),
       !isnan(clip_pg), vs, pg);
-  count_launch();
+  count_launch(PC_VTRACE, (cudaStream_t)stream);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
 }
@@ -478,7 +478,7 @@ extern "C" int seedrl_categorical_log_prob(int N, int A, const float* logits,
   SEEDRL_CHECK_ARG(logits && actions && log_prob, "null pointer");
   categorical_logprob_entropy_kernel<<<ceil_div(N, 8), 256, 0, (cudaStream_t)stream>>>(
       N, A, logits, actions, log_prob, nullptr);
-  count_launch();
+  count_launch(PC_MISC, (cudaStream_t)stream);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
 }
@@ -490,7 +490,7 @@ extern "C" int seedrl_categorical_entropy(int N, int A, const float* logits, flo
   SEEDRL_CHECK_ARG(logits && entropy, "null pointer");
   categorical_logprob_entropy_kernel<<<ceil_div(N, 8), 256, 0, (cudaStream_t)stream>>>(
       N, A, logits, nullptr, nullptr, entropy);
-  count_launch();
+  count_launch(PC_MISC, (cudaStream_t)stream);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
 }
@@ -504,7 +504,7 @@ extern "C" int seedrl_categorical_sample(int N, int A, const float* logits,
   SEEDRL_CHECK_ARG(logits && actions, "null pointer");
   categorical_sample_kernel<<<ceil_div(N, 128), 128, 0, (cudaStream_t)stream>>>(
       N, A, logits, gumbel_noise, seed, offset, actions);
-  count_launch();
+  count_launch(PC_MISC, (cudaStream_t)stream);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
 }
@@ -546,7 +546,7 @@ extern "C" int seedrl_vtrace_loss_fwd_bwd(
     attr_set = true;
   }
   vtrace_loss_kernel<<<ceil_div(B, p.BB), kLossThreads, smem, (cudaStream_t)stream>>>(p);
-  count_launch();
+  count_launch(PC_LOSS, (cudaStream_t)stream);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
 }
