@@ -27,13 +27,31 @@ def polynomial_decay(initial_lr, step, decay_steps, end_lr=0.0, power=1.0):
 
 
 def keras_adam_step(p, g, m, v, iterations, lr, beta1=0.9, beta2=0.999, eps=1e-7):
-  """One dense Adam step in fp32.  `iterations` = optimizer.iterations BEFORE the
-  step (0 for the first step).  Returns new (p, m, v)."""
+  """One dense Adam step, fp32 throughout like TF's kernels.  `iterations` =
+  optimizer.iterations BEFORE the step (0 for the first step).  Returns new (p, m, v).
+
+  Restates Keras `Adam._prepare_local` (fp32 tensors: beta powers, `1 - beta`,
+  lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t)) followed by the fused
+  `training_ops.resource_apply_adam` update in the form its Eigen kernel uses:
+      m += (g - m) * (1 - beta1);  v += (g*g - v) * (1 - beta2)
+      var -= (m * lr_t) / (sqrt(v) + eps)
+  Note `1 - beta2` is an fp32 subtraction (1 - fp32(0.999) = 0.00100004673)."""
   f = np.float32
-  t = iterations + 1
-  lr_t = f(lr * np.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t))
+  t = f(iterations + 1)
+  b1, b2 = f(beta1), f(beta2)
+  b1p, b2p = np.power(b1, t, dtype=f), np.power(b2, t, dtype=f)
+  lr_t = f(lr) * (np.sqrt(f(1) - b2p, dtype=f) / (f(1) - b1p))
   p, g, m, v = (np.asarray(x, f) for x in (p, g, m, v))
-  m2 = f(beta1) * m + f(1.0 - beta1) * g
-  v2 = f(beta2) * v + f(1.0 - beta2) * g * g
-  p2 = p - lr_t * m2 / (np.sqrt(v2) + f(eps))
+  m2 = m + (g - m) * (f(1) - b1)
+  v2 = v + (g * g - v) * (f(1) - b2)
+  p2 = p - (m2 * lr_t) / (np.sqrt(v2) + f(eps))
   return p2.astype(f), m2.astype(f), v2.astype(f)
+
+
+def keras_adam_lr_t(iterations, lr, beta1, beta2):
+  """fp32 lr_t exactly as keras_adam_step computes it (shared with nobody: the product
+  recomputes it in seed_rl_b200/common/optimizers.py)."""
+  f = np.float32
+  t = f(iterations + 1)
+  return f(lr) * (np.sqrt(f(1) - np.power(f(beta2), t, dtype=f), dtype=f) /
+                  (f(1) - np.power(f(beta1), t, dtype=f)))

@@ -4,6 +4,7 @@ agents/vtrace/learner.py:272-273 -- here ONE fused kernel over the flat arena
 (seedrl_adam_apply).  `iterations` is the resumable step counter (learner.py:243)."""
 import math
 
+import numpy as np
 import torch
 
 from seed_rl_b200 import _lib
@@ -47,8 +48,11 @@ class Adam(object):
                       clamp_lo=0.0, clamp_hi=0.0):
     """params/grads: flat fp32 CUDA arenas (updated in place)."""
     self._create_slots(params)
-    t = self.iterations + 1
-    lr_t = self._lr() * math.sqrt(1.0 - self.beta_2 ** t) / (1.0 - self.beta_1 ** t)
+    # Keras `_prepare_local` computes these in fp32 tensors
+    f = np.float32
+    t = f(self.iterations + 1)
+    lr_t = float(f(self._lr()) * (np.sqrt(f(1) - np.power(f(self.beta_2), t, dtype=f), dtype=f) /
+                                  (f(1) - np.power(f(self.beta_1), t, dtype=f))))
     _lib.check(_lib.lib().seedrl_adam_apply(
         params.numel(), _lib.ptr(params), _lib.ptr(grads), _lib.ptr(self.m), _lib.ptr(self.v),
         lr_t, self.beta_1, self.beta_2, self.epsilon, grad_scale, clamp_index, clamp_lo,

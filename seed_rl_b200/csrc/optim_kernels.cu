@@ -1,4 +1,6 @@
-// (a4) Fused multi-tensor Adam over the flat parameter arena, tf.keras semantics
+// (a4) Fused multi-tensor Adam over the flat parameter arena, tf.keras semantics in the
+// form TF's fused ApplyAdam kernel uses: m += (g-m)(1-b1); v += (g*g-v)(1-b2);
+// var -= (m*lr_t)/(sqrt(v)+eps), all fp32 (incl. the 1-b subtraction)
 // (TF 2.4.1 Adam._resource_apply_dense; built at dmlab/vtrace_main.py:46-51,
 // applied at agents/vtrace/learner.py:272-273).  Pure HBM stream:
 // 4 reads + 3 writes of fp32 per parameter = 28 B/param; float4 vectorised,
@@ -24,9 +26,9 @@ adam_kernel(size_t n, float* __restrict__ p, const float* __restrict__ g, float*
 #define SEEDRL_ADAM1(c)                                   \
     {                                                     \
       const float gs = gg.c * gscale;                     \
-      mm.c = b1 * mm.c + ob1 * gs;                        \
-      vv.c = b2 * vv.c + ob2 * gs * gs;                   \
-      pp.c -= lr_t * mm.c / (sqrtf(vv.c) + eps);          \
+      mm.c += (gs - mm.c) * ob1;                          \
+      vv.c += (gs * gs - vv.c) * ob2;                     \
+      pp.c -= (mm.c * lr_t) / (sqrtf(vv.c) + eps);        \
     }
     SEEDRL_ADAM1(x) SEEDRL_ADAM1(y) SEEDRL_ADAM1(z) SEEDRL_ADAM1(w)
 #undef SEEDRL_ADAM1
@@ -35,10 +37,10 @@ adam_kernel(size_t n, float* __restrict__ p, const float* __restrict__ g, float*
   // tail (n % 4) + optional clamp handled by the first threads
   for (size_t i = (n4 << 2) + tid; i < n; i += stride) {
     const float gs = g[i] * gscale;
-    const float mm = b1 * m[i] + ob1 * gs;
-    const float vv = b2 * v[i] + ob2 * gs * gs;
+    const float mm = m[i] + (gs - m[i]) * ob1;
+    const float vv = v[i] + (gs * gs - v[i]) * ob2;
     m[i] = mm; v[i] = vv;
-    p[i] -= lr_t * mm / (sqrtf(vv) + eps);
+    p[i] -= (mm * lr_t) / (sqrtf(vv) + eps);
   }
   (void)clamp_index; (void)clamp_lo; (void)clamp_hi;
 }
