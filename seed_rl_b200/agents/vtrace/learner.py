@@ -167,6 +167,27 @@ Unroll = collections.namedtuple(
     'Unroll', 'agent_state prev_actions env_outputs agent_outputs')
 
 
+def reduce_gradients(flat_grads, world, process_group=None, grad_reduce='sum'):
+  """The ONE exchange step of a data-parallel iteration: all-reduce(SUM) of the flat
+  gradient arena in place (NCCL over NVLink on GPUs, gloo in the CPU tests).  Returns the
+  scale Adam must apply to the reduced gradient: 1 for the reference's semantics --
+  every replica's *mean*-loss gradient is SUMMED across replicas
+  (reference tests/utils_test.py:609-650: `expected_a = 1 - N*0.2`) -- or 1/world for
+  `grad_reduce='mean'`."""
+  if grad_reduce not in ('sum', 'mean'):
+    raise ValueError('grad_reduce must be "sum" or "mean"')
+  if world <= 1:
+    return 1.0
+  import torch.distributed as td
+  td.all_reduce(flat_grads, op=td.ReduceOp.SUM, group=process_group)
+  return 1.0 / world if grad_reduce == 'mean' else 1.0
+
+
+def env_shard(rank, world, num_envs):
+  """Environments owned by replica `rank`: {i : i mod world == rank}."""
+  return list(range(rank, num_envs, world))
+
+
 class LearnerStep(object):
   """`minimize` of reference learner.py:255-280 for one replica (= one GPU/process)."""
 
@@ -199,13 +220,7 @@ class LearnerStep(object):
 
   def apply_gradients(self):
     grads = self.agent.grads
-    scale = 1.0
-    if self.world > 1:
-      import torch.distributed as td
-      # ONE collective per step: SUM over replicas (reference tests/utils_test.py:640-650)
-      td.all_reduce(grads, op=td.ReduceOp.SUM, group=self.pg)
-      if self.grad_reduce == 'mean':
-        scale = 1.0 / self.world
+    scale = reduce_gradients(grads, self.world, self.pg, self.grad_reduce)
     mul = self.settings.entropy_cost_adjustment_speed
     self.optimizer.apply_gradients(
         self.agent.params, grads, grad_scale=scale,

@@ -11,6 +11,8 @@
 // coalesced traffic in both directions.
 #include <math.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace seedrl {
@@ -156,7 +158,7 @@ __global__ void categorical_sample_kernel(int N, int A, const float* __restrict_
 //   phase B  learner   logits tile -> smem (same buffer), thread-per-row:
 //            lse, target logp, entropy
 //   phase C  thread-per-column reverse scan (vs, pg_adv) + loss partial sums
-//   phase D  thread-per-element gradient, written back coalesced
+//   phase D  thread-per-row gradient in place, written back with float4 stores
 // Per-CTA partial sums go to scratch[cta][8]; the last CTA to finish (ticket)
 // reduces them in index order (deterministic) and writes loss_terms.
 constexpr int kLossThreads = 256;
@@ -209,15 +211,43 @@ __device__ __forceinline__ float block_reduce_max(float v, float* red) {
   return r;
 }
 
+// Moves the CTA's logits tile between global memory ([T, B, A], columns b0..b0+nb) and
+// shared memory ([T][BB][A], dense).  For each t the slice is nb*A contiguous floats; warp w
+// takes rows t = w, w+8, ... and its lanes stride the row with float4 (all of a thread's
+// loads are independent => several 16-byte requests in flight per thread).
+template <bool LOAD>
+__device__ __forceinline__ void tile_copy(float* s_tile, typename std::conditional<LOAD, const float*, float*>::type g,
+                                          int T, int B, int A, int BB, int nb, int tid) {
+  const int warp = tid >> 5, lane = tid & 31, nwarps = kLossThreads >> 5;
+  const int n = nb * A;
+  const bool vec = ((n & 3) == 0) && (((BB * A) & 3) == 0) && ((((size_t)B * A) & 3) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(g) & 15) == 0);
+  for (int t = warp; t < T; t += nwarps) {
+    float* sr = s_tile + (size_t)t * BB * A;
+    auto gr = g + (size_t)t * B * A;
+    if (vec) {
+      for (int v = lane; v < (n >> 2); v += 32) {
+        if (LOAD) reinterpret_cast<float4*>(sr)[v] = __ldg(reinterpret_cast<const float4*>(gr) + v);
+        else reinterpret_cast<float4*>(const_cast<float*>(gr))[v] = reinterpret_cast<const float4*>(sr)[v];
+      }
+    } else {
+      for (int e = lane; e < n; e += 32) {
+        if (LOAD) sr[e] = __ldg(gr + e);
+        else const_cast<float*>(gr)[e] = sr[e];
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kLossThreads)
 vtrace_loss_kernel(const LossParams p) {
   extern __shared__ float smem[];
-  const int T = p.T, B = p.B, A = p.A, BB = p.BB, AP = p.AP;
+  const int T = p.T, B = p.B, A = p.A, BB = p.BB;
   const int b0 = blockIdx.x * BB;
   const int nb = min(BB, B - b0);
   const int rows = T * BB;
-  float* s_logits = smem;                      // [T*BB][AP]
-  float* s_tlp = s_logits + (size_t)rows * AP; // [rows] target logp   -> later pg_adv
+  float* s_logits = smem;                      // [T][BB][A] dense, 16B-aligned rows of BB*A
+  float* s_tlp = s_logits + (((size_t)rows * A + 3) & ~(size_t)3); // [rows] target logp -> later pg_adv
   float* s_blp = s_tlp + rows;                 // [rows] behaviour logp -> later v_err
   float* s_lse = s_blp + rows;                 // [rows]
   float* s_ent = s_lse + rows;                 // [rows]
@@ -252,22 +282,17 @@ vtrace_loss_kernel(const LossParams p) {
   }
 
   // ---- phase A: behaviour logits ------------------------------------------
-  for (int t = 0; t < T; ++t) {
-    const float* src = p.bl + ((size_t)t * B + b0) * A;
-    for (int e = tid; e < nb * A; e += kLossThreads) {
-      const int c = e / A, j = e - c * A;
-      s_logits[(size_t)(t * BB + c) * AP + j] = __ldg(src + e);
-    }
-  }
+  tile_copy<true>(s_logits, p.bl + (size_t)b0 * A, T, B, A, BB, nb, tid);
   __syncthreads();
+  const int rot = (tid >> 4) & 1;   // half-warps start one column apart: conflict-free for even A
   for (int i = tid; i < rows; i += kLossThreads) {
     const int c = i % BB;
     if (c < nb) {
-      const float* l = s_logits + (size_t)i * AP;
+      const float* l = s_logits + (size_t)i * A;
       float m = -INFINITY;
-      for (int j = 0; j < A; ++j) m = fmaxf(m, l[j]);
+      for (int jj = 0, j = rot < A ? rot : 0; jj < A; ++jj, j = (j + 1 == A ? 0 : j + 1)) m = fmaxf(m, l[j]);
       float se = 0.f;
-      for (int j = 0; j < A; ++j) se += expf(l[j] - m);
+      for (int jj = 0, j = rot < A ? rot : 0; jj < A; ++jj, j = (j + 1 == A ? 0 : j + 1)) se += expf(l[j] - m);
       int a = s_act[i];
       a = a < 0 ? 0 : (a >= A ? A - 1 : a);
       s_blp[i] = l[a] - (m + logf(se));                    // :97-98
@@ -275,25 +300,20 @@ vtrace_loss_kernel(const LossParams p) {
   }
   __syncthreads();
   // ---- phase B: learner logits --------------------------------------------
-  for (int t = 0; t < T; ++t) {
-    const float* src = p.ll + ((size_t)t * B + b0) * A;
-    for (int e = tid; e < nb * A; e += kLossThreads) {
-      const int c = e / A, j = e - c * A;
-      s_logits[(size_t)(t * BB + c) * AP + j] = __ldg(src + e);
-    }
-  }
+  tile_copy<true>(s_logits, p.ll + (size_t)b0 * A, T, B, A, BB, nb, tid);
   __syncthreads();
   for (int i = tid; i < rows; i += kLossThreads) {
     const int c = i % BB;
     if (c < nb) {
-      const float* l = s_logits + (size_t)i * AP;
+      const float* l = s_logits + (size_t)i * A;
       float m = -INFINITY;
-      for (int j = 0; j < A; ++j) m = fmaxf(m, l[j]);
+      for (int jj = 0, j = rot < A ? rot : 0; jj < A; ++jj, j = (j + 1 == A ? 0 : j + 1)) m = fmaxf(m, l[j]);
       float se = 0.f, sel = 0.f;
-      for (int j = 0; j < A; ++j) {
-        const float e = expf(l[j] - m);
+      for (int jj = 0, j = rot < A ? rot : 0; jj < A; ++jj, j = (j + 1 == A ? 0 : j + 1)) {
+        const float d = l[j] - m;
+        const float e = expf(d);
         se += e;
-        sel += e * (l[j] - m);
+        sel = fmaf(e, d, sel);
       }
       const float lg = logf(se);
       int a = s_act[i];
@@ -343,26 +363,28 @@ vtrace_loss_kernel(const LossParams p) {
   }
   __syncthreads();
 
-  // ---- phase D: gradients --------------------------------------------------
+  // ---- phase D: gradients, thread-per-row in place, then a vectorised write-back -----
   const float invN = 1.0f / ((float)T * (float)B);
   const float kc = p.cfg.kl_cost;
-  for (int t = 0; t < T; ++t) {
-    float* dst = p.dlogits + ((size_t)t * B + b0) * A;
-    for (int e = tid; e < nb * A; e += kLossThreads) {
-      const int c = e / A, j = e - c * A;
-      const int i = t * BB + c;
-      const float l = s_logits[(size_t)i * AP + j];
-      const float logp = l - s_lse[i];
-      const float pj = expf(logp);
+  for (int i = tid; i < rows; i += kLossThreads) {
+    const int c = i % BB;
+    if (c < nb) {
+      float* l = s_logits + (size_t)i * A;
+      const float lse = s_lse[i], ent = s_ent[i];
+      const float wpg = -(s_tlp[i] + kc) * invN, wec = ec * invN;
       int a = s_act[i];
       a = a < 0 ? 0 : (a >= A ? A - 1 : a);
-      const float onehot = (j == a) ? 1.f : 0.f;
-      // d(-mean(tlp*pg))/dl_j = -pg/N (1[j=a]-p_j); d(kc*mean(blp-tlp)) = -kc/N (1[j=a]-p_j)
-      // d(-ec*mean(H))/dl_j  = ec/N * p_j (log p_j + H)
-      const float g = -(s_tlp[i] + kc) * invN * (onehot - pj) + ec * invN * pj * (logp + s_ent[i]);
-      dst[e] = g;
+      for (int jj = 0, j = rot < A ? rot : 0; jj < A; ++jj, j = (j + 1 == A ? 0 : j + 1)) {
+        const float logp = l[j] - lse;
+        const float pj = expf(logp);
+        // d(-mean(tlp*pg))/dl_j = -pg/N (1[j=a]-p_j); d(kc*mean(blp-tlp)) = -kc/N (1[j=a]-p_j)
+        // d(-ec*mean(H))/dl_j  = ec/N * p_j (log p_j + H)
+        l[j] = wpg * ((j == a ? 1.f : 0.f) - pj) + wec * pj * (logp + ent);
+      }
     }
   }
+  __syncthreads();
+  tile_copy<false>(s_logits, p.dlogits + (size_t)b0 * A, T, B, A, BB, nb, tid);
   {  // last row (bootstrap step): zero gradient
     float* dst = p.dlogits + ((size_t)T * B + b0) * A;
     for (int e = tid; e < nb * A; e += kLossThreads) dst[e] = 0.f;
@@ -438,10 +460,9 @@ vtrace_loss_kernel(const LossParams p) {
 }
 
 static int pick_bb(int T, int A, size_t* smem_bytes) {
-  const int AP = A | 1;
   for (int BB = 16; BB >= 1; BB >>= 1) {
     const size_t rows = (size_t)T * BB;
-    const size_t bytes = (rows * AP + rows * 6 + (size_t)(T + 1) * BB + rows + 32) * 4;
+    const size_t bytes = (((rows * A + 3) & ~(size_t)3) + rows * 6 + (size_t)(T + 1) * BB + rows + 32) * 4;
     if (bytes <= 200 * 1024) {
       *smem_bytes = bytes;
       return BB;

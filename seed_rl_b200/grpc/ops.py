@@ -123,8 +123,13 @@ def _parse_shape(buf):
   return dims
 
 
+def _contig(a):
+  a = np.asarray(a)          # (np.ascontiguousarray would turn 0-d into 1-d)
+  return a if a.flags.c_contiguous else a.copy()
+
+
 def encode_tensor(a):
-  a = np.ascontiguousarray(a)
+  a = _contig(a)
   return _key(1, 0) + _varint(_DT[a.dtype]) + _ld(2, _shape_proto(a.shape)) + _ld(4, a.tobytes())
 
 
@@ -362,7 +367,7 @@ class Server(object):
     if name not in self._fns:
       raise RpcError(INTERNAL, 'Function %s not found' % name)        # grpc.cc:187-190
     b = self._fns[name]
-    args = [np.ascontiguousarray(a) for a in args]
+    args = [_contig(a) for a in args]
     k, batched = self._verify_args(b, args)
     slab, row = ctypes.c_int(), ctypes.c_int()
     rc = L.seedrl_batcher_claim(b.batcher, k, ctypes.byref(slab), ctypes.byref(row))
