@@ -42,6 +42,8 @@ def parse_args():
   p.add_argument('--batch', type=int, default=64, help='unrolls per GPU')
   p.add_argument('--unroll', type=int, default=20)
   p.add_argument('--cpu-batch', type=int, default=8, help='unrolls per CPU-baseline step')
+  p.add_argument('--conv', default='simt', choices=['simt', 'tc'],
+                 help="contraction path of the 16/32-channel convs: fp32 SIMT or tcgen05 bf16")
   p.add_argument('--no-extras', action='store_true',
                  help='skip the profiling pass, the loss-kernel sweep and the CPU baseline')
   return p.parse_args()
@@ -240,7 +242,7 @@ def main():
   upload()
   unroll = make_unroll()
   cls = networks.ImpalaDeep if args.net == 'deep' else networks.ImpalaShallow
-  agent = cls(A, OBS, seed=0)            # same seed on every rank: replicas start identical
+  agent = cls(A, OBS, seed=0, conv_mode=args.conv)   # same seed on every rank: replicas start identical
   opt = optimizers.Adam(optimizers.PolynomialDecay(4.8e-4, 10**6, 0.0), beta_1=0.0, epsilon=3.125e-7)
   step = learner.LearnerStep(agent, opt, settings=learner.default_loss_settings(), grad_reduce='sum')
 
@@ -287,8 +289,9 @@ def main():
   line = {
       'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
       'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True,
-      'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-      'config': workload_config(args, world), 'clocks': clocks,
+      'scaling': 'weak', 'vs_baseline': None,
+      'dtype': 'bf16' if args.conv == 'tc' else 'f32', 'data': 'synthetic',
+      'config': dict(workload_config(args, world), conv_path=args.conv), 'clocks': clocks,
       'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e,
               'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes,
               'api': 'seed_rl_b200.agents.vtrace.learner.LearnerStep.minimize(Unroll)'},

@@ -64,6 +64,7 @@ SIGNATURES = {
     'seedrl_net_num_param_tensors': (c_int, [P]),
     'seedrl_net_num_params': (c_size_t, [P]),
     'seedrl_net_arena_floats': (c_size_t, [P]),
+    'seedrl_net_set_conv_mode': (c_int, [P, c_int]),
     'seedrl_net_param_info':
         (c_int, [P, c_int, ctypes.c_char_p, c_size_t, ctypes.POINTER(c_i64),
                  ctypes.POINTER(c_size_t)]),
@@ -96,6 +97,8 @@ SIGNATURES = {
     'seedrl_profile_end': (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_u64)]),
     'seedrl_debug_conv3x3': (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),
     'seedrl_debug_conv3x3_flip': (c_int, [c_int, c_int, P, P, P]),
+    'seedrl_debug_conv3x3_tc':
+        (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, c_int, c_int, P, P, P]),
     'seedrl_debug_wgrad_partial_bytes': (c_size_t, []),
     'seedrl_debug_conv3x3_wgrad':
         (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, c_size_t, P]),

@@ -19,40 +19,6 @@
 
 namespace seedrl {
 
-struct ConvGeom {
-  int N, H, W;       // images, spatial size (stride 1, 'same': out == in size)
-  int PW;            // W + 2
-  int RH;            // H + 1 (rows per image in the tall layout)
-  long long Q;       // N * RH * PW flattened output positions
-};
-
-__host__ __device__ inline ConvGeom make_geom(int N, int H, int W) {
-  ConvGeom g;
-  g.N = N; g.H = H; g.W = W; g.PW = W + 2; g.RH = H + 1;
-  g.Q = (long long)N * g.RH * g.PW;
-  return g;
-}
-
-// padded-input position -> element offset of pixel (n,h,w) in NHWC/C, or -1.
-// (positions fit in 31 bits: checked on the host)
-__device__ __forceinline__ int in_pixel(const ConvGeom& g, int gp) {
-  const int Rp = gp / g.PW;
-  const int c = gp - Rp * g.PW;
-  const int n = Rp / g.RH;
-  const int rr = Rp - n * g.RH;
-  if (rr == 0 || c == 0 || c > g.W || n >= g.N) return -1;
-  return (n * g.H + (rr - 1)) * g.W + (c - 1);
-}
-// output position -> pixel index or -1.
-__device__ __forceinline__ int out_pixel(const ConvGeom& g, int p) {
-  const int Ro = p / g.PW;
-  const int c = p - Ro * g.PW;
-  const int n = Ro / g.RH;
-  const int h = Ro - n * g.RH;
-  if (h >= g.H || c >= g.W || n >= g.N) return -1;
-  return (n * g.H + h) * g.W + c;
-}
-
 // ---------------------------------------------------------------------------
 // conv3x3 (forward, and data-gradient with flipped/transposed weights).
 //   out[pix, co] = epi( sum_{tap,ci} tin(in)[pix+tap, ci] * w[tap][ci][co] )

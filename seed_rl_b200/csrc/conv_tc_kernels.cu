@@ -1,0 +1,299 @@
+// conv3x3 'same' on the 5th-gen tensor cores (tcgen05 + TMEM), bf16 operands, fp32
+// accumulation -- forward and data-gradient of dmlab/networks.py:26-60 for the 16/32
+// channel layers (the uint8 4->16 first layer stays on the SIMT kernel).
+//
+// Implicit GEMM on the "tall image" (see conv_kernels.cu): a CTA owns M = 128
+// consecutive flattened output positions.  Activations are staged in shared memory as
+// channel-group planes [CIN/8][positions][8 ch] bf16 (16 B per position per plane), which
+// IS the canonical no-swizzle K-major UMMA layout:
+//     8 consecutive positions x 8 channels  = one 128-byte core matrix
+//     SBO (next 8 rows)            = 128 B
+//     LBO (next 8 K-elements)      = plane stride
+// and filter tap (kh,kw) is nothing but the descriptor START ADDRESS moved by
+// (kh*PW + kw) * 16 bytes.  So the 3x3 conv is 9 * CIN/16 back-to-back
+// tcgen05.mma.kind::f16 (128 x COUT x 16) issued by one thread into one TMEM
+// accumulator -- no im2col, no per-tap data movement.
+// Weights are pre-packed (prep kernel) to the K-major core-matrix layout
+// [tap][slab][kchunk][COUT/8][8 co][8 ci] bf16; the data-gradient uses the same kernel
+// with flipped/transposed packing.
+// Epilogue: tcgen05.ld 32x32b (thread = one output position, COUT fp32 columns) ->
+// bias / ReLU-mask / residual -> fp32 NHWC.
+#include <cuda_bf16.h>
+
+#include "kernels.h"
+
+namespace seedrl {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// cute::UMMA::SmemDescriptor (mma_sm100_desc.hpp): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type SWIZZLE_NONE=0 [61,64).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+
+// cute::UMMA::InstrDescriptor: c_format F32 (1<<4), a/b BF16 (1<<7, 1<<10), K-major both,
+// n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t a, uint64_t b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p; \n\t"
+      "}\n" ::"r"(tmem_d), "l"(a), "l"(b), "r"(idesc), "r"(accumulate));
+}
+
+template <int N>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float* v);
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <>
+__device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, float* v) {
+  tmem_ld<16>(taddr, v);
+  tmem_ld<16>(taddr + 16, v + 16);
+}
+
+// w fp32 [tap][ci_src][co_src]  ->  packed bf16 for an implicit GEMM with CIN x COUT:
+//   forward: element (tap, ci, co)   = w[tap][ci][co]
+//   flipped: element (tap, ci, co)   = w[8-tap][co][ci]     (data-gradient; src is [tap][COUT][CIN])
+__global__ void pack_w_tc_kernel(int CIN, int COUT, int flip, const float* __restrict__ w,
+                                 __nv_bfloat16* __restrict__ wq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 9 * CIN * COUT) return;
+  const int e = i & 7;                       // ci % 8
+  const int r = (i >> 3) & 7;                // co % 8
+  int rest = i >> 6;
+  const int cog = rest % (COUT / 8); rest /= (COUT / 8);
+  const int kc = rest & 1; rest >>= 1;
+  const int NS = CIN / 16;
+  const int slab = rest % NS;
+  const int tap = rest / NS;
+  const int ci = slab * 16 + kc * 8 + e, co = cog * 8 + r;
+  const float v = flip ? w[((size_t)(8 - tap) * COUT + co) * CIN + ci] : w[((size_t)tap * CIN + ci) * COUT + co];
+  wq[i] = __float2bfloat16_rn(v);
+}
+
+constexpr int kTcThreads = 128;
+constexpr int kTcM = 128;
+
+template <int CIN, int COUT, int IN_MODE>
+__global__ void __launch_bounds__(kTcThreads)
+conv3x3_tc_kernel(ConvGeom g, const float* __restrict__ in, const uint4* __restrict__ wq,
+                  const float* __restrict__ bias, const float* __restrict__ mask,
+                  const float* __restrict__ res, float* __restrict__ out, int variant,
+                  int* __restrict__ error_flag) {
+  constexpr int G = CIN / 8;          // channel-group planes
+  constexpr int NS = CIN / 16;        // K slabs per tap
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int PW = g.PW;
+  const int L = kTcM + 2 * PW + 2;    // staged input positions
+  const int LPl = L | 1;              // plane stride in 16-byte units (odd: conflict-free stores)
+  uint4* s_a = reinterpret_cast<uint4*>(smem_raw);                       // [G][LPl] x 16 B
+  uint4* s_b = s_a + (size_t)G * LPl;                                    // 9*CIN*COUT bf16
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_b + 9 * CIN * COUT / 8);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- one-time setup: weights -> smem, mbarrier, TMEM allocation --------------------
+  for (int i = tid; i < 9 * CIN * COUT / 8; i += kTcThreads) s_b[i] = __ldg(wq + i);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(smem_u32(s_tmem)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(s_tmem);
+  constexpr uint32_t idesc = umma_idesc(kTcM, COUT);
+  const uint32_t a_base = smem_u32(s_a), b_base = smem_u32(s_b);
+  const uint32_t a_lbo = (variant & 1) ? 128u : (uint32_t)LPl * 16u;
+  const uint32_t a_sbo = (variant & 1) ? (uint32_t)LPl * 16u : 128u;
+  const uint32_t b_lbo = (variant & 2) ? 128u : (uint32_t)(COUT / 8) * 128u;
+  const uint32_t b_sbo = (variant & 2) ? (uint32_t)(COUT / 8) * 128u : 128u;
+
+  float bv[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) bv[c] = bias ? __ldg(bias + c) : 0.f;
+
+  uint32_t phase = 0;
+  const int nchunks = (int)((g.Q + kTcM - 1) / kTcM);
+  for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
+    const int q0 = ch * kTcM;
+    // ---- stage the input tile: fp32 NHWC -> bf16 channel-group planes -------------------
+    for (int i = tid; i < L * G; i += kTcThreads) {
+      const int s = i / G, gch = i - s * G;
+      const int pix = in_pixel(g, q0 + s);
+      uint4 packed = make_uint4(0u, 0u, 0u, 0u);
+      if (pix >= 0) {
+        const float4* src = reinterpret_cast<const float4*>(in + (size_t)pix * CIN + gch * 8);
+        float4 a = __ldg(src), b = __ldg(src + 1);
+        if (IN_MODE == IN_RELU) {
+          a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+          b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f); b.z = fmaxf(b.z, 0.f); b.w = fmaxf(b.w, 0.f);
+        }
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+        packed.x = *reinterpret_cast<uint32_t*>(&p0); packed.y = *reinterpret_cast<uint32_t*>(&p1);
+        packed.z = *reinterpret_cast<uint32_t*>(&p2); packed.w = *reinterpret_cast<uint32_t*>(&p3);
+      }
+      s_a[(size_t)gch * LPl + s] = packed;
+    }
+    // generic-proxy smem writes -> visible to the tensor core's async proxy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    // ---- one thread issues the 9 * NS MMAs, then commits to the mbarrier ------------------
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint32_t acc = 0;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int off = (tap / 3) * PW + (tap % 3);
+#pragma unroll
+        for (int sl = 0; sl < NS; ++sl) {
+          const uint64_t da = umma_desc(a_base + ((uint32_t)(sl * 2) * LPl + off) * 16u, a_lbo, a_sbo);
+          const uint64_t db = umma_desc(b_base + (uint32_t)(tap * NS + sl) * (COUT * 32u), b_lbo, b_sbo);
+          umma_f16(tmem_base, da, db, idesc, acc);
+          acc = 1;
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                       smem_u32(s_bar))
+                   : "memory");
+    }
+    // ---- everyone waits for the accumulator (bounded spin: never hang the GPU) -----------
+    {
+      uint32_t done = 0;
+      int spins = 0;
+      while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(done)
+            : "r"(smem_u32(s_bar)), "r"(phase)
+            : "memory");
+        if (!done && ++spins > (1 << 22)) {
+          if (error_flag) atomicExch(error_flag, 1);
+          break;
+        }
+      }
+      phase ^= 1;
+    }
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // ---- epilogue: TMEM lane (= position) -> registers -> fp32 NHWC -----------------------
+    float acc[COUT];
+    tmem_ld<COUT>(tmem_base + ((uint32_t)(warp * 32) << 16), acc);
+    const int pix = out_pixel(g, q0 + warp * 32 + lane);
+    if (pix >= 0) {
+      const size_t o = (size_t)pix * COUT;
+#pragma unroll
+      for (int c4 = 0; c4 < COUT / 4; ++c4) {
+        float4 v = make_float4(acc[c4 * 4 + 0] + bv[c4 * 4 + 0], acc[c4 * 4 + 1] + bv[c4 * 4 + 1],
+                               acc[c4 * 4 + 2] + bv[c4 * 4 + 2], acc[c4 * 4 + 3] + bv[c4 * 4 + 3]);
+        if (mask) {
+          const float4 m = __ldg(reinterpret_cast<const float4*>(mask + o) + c4);
+          v.x = m.x > 0.f ? v.x : 0.f; v.y = m.y > 0.f ? v.y : 0.f;
+          v.z = m.z > 0.f ? v.z : 0.f; v.w = m.w > 0.f ? v.w : 0.f;
+        }
+        if (res) {
+          const float4 r = __ldg(reinterpret_cast<const float4*>(res + o) + c4);
+          v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        }
+        reinterpret_cast<float4*>(out + o)[c4] = v;
+      }
+    }
+    // TMEM reads and smem reads of this chunk are done before the next chunk overwrites them
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+  }
+
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem_base));
+  }
+}
+
+template <int CIN, int COUT, int IN_MODE>
+static int launch_tc(int N, int H, int W, const float* in, const uint4* wq, const float* bias,
+                     const float* mask, const float* res, float* out, int variant, int* err,
+                     cudaStream_t st) {
+  const ConvGeom g = make_geom(N, H, W);
+  const int L = kTcM + 2 * g.PW + 2;
+  const size_t smem = (size_t)(CIN / 8) * (L | 1) * 16 + (size_t)9 * CIN * COUT * 2 + 64;
+  static bool attr = false;
+  if (!attr) {
+    SEEDRL_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<CIN, COUT, IN_MODE>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  if (smem > 200 * 1024) return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "conv3x3_tc: image too wide");
+  if (g.Q + kTcM + 4 * g.PW >= (1LL << 31))
+    return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "conv3x3_tc: batch too large for 32-bit positions");
+  const long long nchunks = (g.Q + kTcM - 1) / kTcM;
+  long long grid = kNumSMs * 6;
+  if (grid > nchunks) grid = nchunks;
+  conv3x3_tc_kernel<CIN, COUT, IN_MODE><<<(unsigned)grid, kTcThreads, smem, st>>>(
+      g, in, wq, bias, mask, res, out, variant, err);
+  count_launch(g_conv_cat, st);
+  SEEDRL_CHECK_LAUNCH();
+  return SEEDRL_OK;
+}
+
+bool conv3x3_tc_supported(int cin, int cout, int in_mode) {
+  return (cin == 16 || cin == 32) && (cout == 16 || cout == 32) && (in_mode == IN_F32 || in_mode == IN_RELU);
+}
+
+int conv3x3_tc_pack_weights(int cin, int cout, int flip, const float* w, void* wq, cudaStream_t st) {
+  const int n = 9 * cin * cout;
+  pack_w_tc_kernel<<<ceil_div(n, 256), 256, 0, st>>>(cin, cout, flip, w, reinterpret_cast<__nv_bfloat16*>(wq));
+  count_launch(PC_MISC, st);
+  SEEDRL_CHECK_LAUNCH();
+  return SEEDRL_OK;
+}
+
+int conv3x3_tc_forward(int cin, int cout, int in_mode, int N, int H, int W, const float* in,
+                       const void* wq, const float* bias, const float* mask, const float* res,
+                       float* out, int variant, int* err, cudaStream_t st) {
+#define SEEDRL_TC_CASE(CI, CO_, MODE)                                                     \
+  if (cin == CI && cout == CO_ && in_mode == MODE)                                        \
+    return launch_tc<CI, CO_, MODE>(N, H, W, in, reinterpret_cast<const uint4*>(wq), bias, mask, res, \
+                                    out, variant, err, st);
+  SEEDRL_TC_CASE(16, 16, IN_F32)
+  SEEDRL_TC_CASE(16, 16, IN_RELU)
+  SEEDRL_TC_CASE(16, 32, IN_F32)
+  SEEDRL_TC_CASE(32, 16, IN_F32)
+  SEEDRL_TC_CASE(32, 32, IN_F32)
+  SEEDRL_TC_CASE(32, 32, IN_RELU)
+#undef SEEDRL_TC_CASE
+  return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "conv3x3_tc: unsupported (cin,cout,mode)");
+}
+
+}  // namespace seedrl

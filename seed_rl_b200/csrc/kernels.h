@@ -6,6 +6,51 @@ namespace seedrl {
 
 enum { IN_F32 = 0, IN_RELU = 1, IN_U8 = 2 };
 
+// "Tall image" geometry shared by the SIMT and tensor-core 3x3 convolutions (see
+// conv_kernels.cu): N images stacked into one zero-padded tall image, positions flattened.
+struct ConvGeom {
+  int N, H, W;       // images, spatial size (stride 1, 'same': out == in size)
+  int PW;            // W + 2
+  int RH;            // H + 1 (rows per image in the tall layout)
+  long long Q;       // N * RH * PW flattened output positions
+};
+
+__host__ __device__ inline ConvGeom make_geom(int N, int H, int W) {
+  ConvGeom g;
+  g.N = N; g.H = H; g.W = W; g.PW = W + 2; g.RH = H + 1;
+  g.Q = (long long)N * g.RH * g.PW;
+  return g;
+}
+
+#ifdef __CUDACC__
+// padded-input position -> pixel index (n*H + h)*W + w, or -1 for padding.
+// (positions fit in 31 bits: checked on the host)
+__device__ __forceinline__ int in_pixel(const ConvGeom& g, int gp) {
+  const int Rp = gp / g.PW;
+  const int c = gp - Rp * g.PW;
+  const int n = Rp / g.RH;
+  const int rr = Rp - n * g.RH;
+  if (rr == 0 || c == 0 || c > g.W || n >= g.N) return -1;
+  return (n * g.H + (rr - 1)) * g.W + (c - 1);
+}
+// output position -> pixel index or -1.
+__device__ __forceinline__ int out_pixel(const ConvGeom& g, int p) {
+  const int Ro = p / g.PW;
+  const int c = p - Ro * g.PW;
+  const int n = Ro / g.RH;
+  const int h = Ro - n * g.RH;
+  if (h >= g.H || c >= g.W || n >= g.N) return -1;
+  return (n * g.H + h) * g.W + c;
+}
+#endif
+
+// conv_tc_kernels.cu (tcgen05 tensor-core path)
+bool conv3x3_tc_supported(int cin, int cout, int in_mode);
+int conv3x3_tc_pack_weights(int cin, int cout, int flip, const float* w, void* wq, cudaStream_t st);
+int conv3x3_tc_forward(int cin, int cout, int in_mode, int N, int H, int W, const float* in,
+                       const void* wq, const float* bias, const float* mask, const float* res,
+                       float* out, int variant, int* err, cudaStream_t st);
+
 // conv_kernels.cu
 int conv3x3_forward(int cin, int cout, int in_mode, int N, int H, int W, const void* in,
                     const float* w, const float* bias, const float* mask, const float* res,

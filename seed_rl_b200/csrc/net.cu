@@ -48,6 +48,7 @@ struct seedrl_net {
   int sh_c0w, sh_c0b, sh_c1w, sh_c1b;      // shallow
   int sh_h1, sh_w1, sh_h2, sh_w2;
   int flat;                                // conv features fed to Dense(256)
+  int conv_mode = 0;                       // 0 = fp32 SIMT, 1 = tcgen05 bf16 for the 16/32-channel convs
   int core_in;                             // 256 + 1 + A
 };
 
@@ -94,7 +95,7 @@ struct Plan {
   size_t sh_a1, sh_a2;         // shallow conv outputs (post-relu)
   size_t xc, z, hp, cs, hs, c0buf;
   // backward scratch
-  size_t dhs, dz, dhrec, dc0, dc1, dd, gA, gB, gC, gFull, wt, partial;
+  size_t dhs, dz, dhrec, dc0, dc1, dd, gA, gB, gC, gFull, wt, partial, wq, tcerr;
   size_t total;
 };
 
@@ -144,6 +145,8 @@ static Plan make_plan(const seedrl_net* n, int T1, int B) {
   p.gC = b.take(pooled_max * 4);
   p.gFull = b.take(full_max * 4);
   p.wt = b.take(64 * 1024 * 4);
+  p.wq = b.take(64 * 1024 * 2);
+  p.tcerr = b.take(256);
   p.partial = b.take(conv3x3_wgrad_partial_bytes());
   p.total = b.off;
   return p;
@@ -164,6 +167,26 @@ static inline float* G(const seedrl_net* n, float* arena, int idx) {
 template <typename T>
 static inline T* W(void* ws, size_t off) {
   return reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + off);
+}
+
+// One 3x3 'same' convolution of the schedule.  flip != 0: data-gradient (weights flipped and
+// transposed; cin/cout are those of the *gradient* convolution).  Dispatches to the tcgen05
+// kernel when the net runs in tensor-core mode and the shape is supported, else fp32 SIMT.
+static int run_conv(const seedrl_net* n, void* ws, const Plan& pl, int cin, int cout, int in_mode,
+                    int N, int H, int Wd, const void* in, const float* w, const float* bias,
+                    const float* mask, const float* res, float* out, int flip, cudaStream_t st) {
+  if (n->conv_mode == 1 && conv3x3_tc_supported(cin, cout, in_mode)) {
+    void* wq = W<void>(ws, pl.wq);
+    SEEDRL_TRY(conv3x3_tc_pack_weights(cin, cout, flip, w, wq, st));
+    return conv3x3_tc_forward(cin, cout, in_mode, N, H, Wd, reinterpret_cast<const float*>(in), wq,
+                              bias, mask, res, out, 0, W<int>(ws, pl.tcerr), st);
+  }
+  if (flip) {
+    float* wt = W<float>(ws, pl.wt);
+    SEEDRL_TRY(conv3x3_flip_weights(cout, cin, w, wt, st));   // source layout is [tap][cout][cin]
+    return conv3x3_forward(cin, cout, in_mode, N, H, Wd, in, wt, bias, mask, res, out, st);
+  }
+  return conv3x3_forward(cin, cout, in_mode, N, H, Wd, in, w, bias, mask, res, out, st);
 }
 
 }  // namespace seedrl
@@ -241,6 +264,11 @@ extern "C" int seedrl_net_num_param_tensors(const seedrl_net* net) {
 }
 extern "C" size_t seedrl_net_num_params(const seedrl_net* net) { return net ? net->logical_params : 0; }
 extern "C" size_t seedrl_net_arena_floats(const seedrl_net* net) { return net ? net->arena_floats : 0; }
+extern "C" int seedrl_net_set_conv_mode(seedrl_net* net, int mode) {
+  SEEDRL_CHECK_ARG(net && (mode == 0 || mode == 1), "mode must be 0 (fp32 SIMT) or 1 (tcgen05 bf16)");
+  net->conv_mode = mode;
+  return SEEDRL_OK;
+}
 
 extern "C" int seedrl_net_param_info(const seedrl_net* net, int index, char* name_buf,
                                      size_t name_buf_len, int64_t* dims, size_t* offset) {
@@ -273,17 +301,17 @@ static int torso_forward_deep(const seedrl_net* n, const float* prm, const Plan&
     float* c0 = W<float>(ws, b.c0); float* o0 = W<float>(ws, b.o0);
     float* c1 = W<float>(ws, b.c1); float* o1 = W<float>(ws, b.o1);
     // _Stack.__call__, dmlab/networks.py:46-60
-    SEEDRL_TRY(conv3x3_forward(k.cin, k.c, in_mode, N, k.hin, k.win, in, P(n, prm, k.conv.w),
-                               P(n, prm, k.conv.b), nullptr, nullptr, a0, st));
+    SEEDRL_TRY(run_conv(n, ws, pl, k.cin, k.c, in_mode, N, k.hin, k.win, in, P(n, prm, k.conv.w),
+                        P(n, prm, k.conv.b), nullptr, nullptr, a0, 0, st));
     SEEDRL_TRY(maxpool3s2_forward(N, k.hin, k.win, k.c, a0, p, W<uint8_t>(ws, b.idx), st));
-    SEEDRL_TRY(conv3x3_forward(k.c, k.c, IN_RELU, N, k.hout, k.wout, p, P(n, prm, k.r00.w),
-                               P(n, prm, k.r00.b), nullptr, nullptr, c0, st));
-    SEEDRL_TRY(conv3x3_forward(k.c, k.c, IN_RELU, N, k.hout, k.wout, c0, P(n, prm, k.r01.w),
-                               P(n, prm, k.r01.b), nullptr, p, o0, st));
-    SEEDRL_TRY(conv3x3_forward(k.c, k.c, IN_RELU, N, k.hout, k.wout, o0, P(n, prm, k.r10.w),
-                               P(n, prm, k.r10.b), nullptr, nullptr, c1, st));
-    SEEDRL_TRY(conv3x3_forward(k.c, k.c, IN_RELU, N, k.hout, k.wout, c1, P(n, prm, k.r11.w),
-                               P(n, prm, k.r11.b), nullptr, o0, o1, st));
+    SEEDRL_TRY(run_conv(n, ws, pl, k.c, k.c, IN_RELU, N, k.hout, k.wout, p, P(n, prm, k.r00.w),
+                        P(n, prm, k.r00.b), nullptr, nullptr, c0, 0, st));
+    SEEDRL_TRY(run_conv(n, ws, pl, k.c, k.c, IN_RELU, N, k.hout, k.wout, c0, P(n, prm, k.r01.w),
+                        P(n, prm, k.r01.b), nullptr, p, o0, 0, st));
+    SEEDRL_TRY(run_conv(n, ws, pl, k.c, k.c, IN_RELU, N, k.hout, k.wout, o0, P(n, prm, k.r10.w),
+                        P(n, prm, k.r10.b), nullptr, nullptr, c1, 0, st));
+    SEEDRL_TRY(run_conv(n, ws, pl, k.c, k.c, IN_RELU, N, k.hout, k.wout, c1, P(n, prm, k.r11.w),
+                        P(n, prm, k.r11.b), nullptr, o0, o1, 0, st));
     in = o1;
     in_mode = IN_F32;
   }
@@ -382,10 +410,9 @@ static int conv_bwd(const seedrl_net* n, const float* prm, float* grd, const Con
   SEEDRL_TRY(conv3x3_wgrad(l.cin, l.cout, x_mode, N, H, Wd, x, dy, G(n, grd, l.w), G(n, grd, l.b),
                            W<float>(ws, pl.partial), conv3x3_wgrad_partial_bytes(), st));
   if (dx) {  // data gradient = conv with flipped, transposed weights
-    float* wt = W<float>(ws, pl.wt);
-    SEEDRL_TRY(conv3x3_flip_weights(l.cin, l.cout, P(n, prm, l.w), wt, st));
     g_conv_cat = PC_CONV_DGRAD;
-    const int rc = conv3x3_forward(l.cout, l.cin, IN_F32, N, H, Wd, dy, wt, nullptr, dmask, dres, dx, st);
+    const int rc = run_conv(n, ws, pl, l.cout, l.cin, IN_F32, N, H, Wd, dy, P(n, prm, l.w), nullptr,
+                            dmask, dres, dx, 1, st);
     g_conv_cat = PC_CONV_FWD;
     SEEDRL_TRY(rc);
   }
@@ -538,4 +565,19 @@ extern "C" int seedrl_debug_sgemm(int ta, int tb, int M, int N, int K, const flo
                                   seedrl_stream_t stream) {
   GemmEpi e{bias, mask, ldm, relu, accumulate, a_relu};
   return sgemm(ta != 0, tb != 0, M, N, K, A, lda, B, ldb, C, ldc, e, (cudaStream_t)stream);
+}
+
+// tcgen05 conv test hook: packs fp32 HWIO weights (optionally flipped/transposed for the
+// data-gradient) into `wq_scratch` (>= 9*cin*cout*2 bytes) and runs the tensor-core conv.
+// `variant` bit0/bit1 swap LBO/SBO of the A/B descriptors (bring-up aid); *error_flag is
+// set to 1 by the kernel if its bounded mbarrier wait expires.
+extern "C" int seedrl_debug_conv3x3_tc(int cin, int cout, int in_mode, int N, int H, int W,
+                                       const float* in, const float* w, const float* bias,
+                                       const float* mask, const float* res, float* out, int flip,
+                                       int variant, void* wq_scratch, int* error_flag,
+                                       seedrl_stream_t stream) {
+  SEEDRL_CHECK_ARG(conv3x3_tc_supported(cin, cout, in_mode), "unsupported (cin,cout,mode)");
+  SEEDRL_TRY(conv3x3_tc_pack_weights(cin, cout, flip, w, wq_scratch, (cudaStream_t)stream));
+  return conv3x3_tc_forward(cin, cout, in_mode, N, H, W, in, wq_scratch, bias, mask, res, out,
+                            variant, error_flag, (cudaStream_t)stream);
 }

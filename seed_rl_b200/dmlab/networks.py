@@ -30,7 +30,10 @@ LSTM_UNITS = 256
 class _CudaAgent(object):
   _NET = None
 
-  def __init__(self, num_actions, obs_shape=(84, 84, 4), seed=0, device=None):
+  def __init__(self, num_actions, obs_shape=(84, 84, 4), seed=0, device=None, conv_mode='simt'):
+    """conv_mode: 'simt' = fp32 CUDA-core contractions (bit-reproducible fp32 path),
+    'tc' = tcgen05 tensor cores (bf16 operands, fp32 accumulation) for the 16/32-channel
+    3x3 convolutions."""
     L = _lib.lib()
     self._num_actions = int(num_actions)
     self._obs_shape = tuple(int(x) for x in obs_shape)
@@ -38,6 +41,10 @@ class _CudaAgent(object):
     h = ctypes.c_void_p()
     _lib.check(L.seedrl_net_create(ctypes.byref(cfg), ctypes.byref(h)))
     self._h = h
+    if conv_mode not in ('simt', 'tc'):
+      raise ValueError("conv_mode must be 'simt' or 'tc'")
+    self.conv_mode = conv_mode
+    _lib.check(L.seedrl_net_set_conv_mode(h, 1 if conv_mode == 'tc' else 0))
     self._n_tensors = L.seedrl_net_num_param_tensors(h)
     self.arena_floats = int(L.seedrl_net_arena_floats(h))
     self.num_params = int(L.seedrl_net_num_params(h))
