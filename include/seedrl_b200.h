@@ -303,6 +303,11 @@ int seedrl_debug_conv3x3_tc(int cin, int cout, int in_mode, int N, int H, int W,
                             const float* mask, const float* res, float* out, int flip,
                             int variant, void* wq_scratch, int* error_flag,
                             seedrl_stream_t stream);
+/* tcgen05 weight gradient (MN-major operands, one TMEM accumulator per tap). */
+int seedrl_debug_conv3x3_wgrad_tc(int cin, int cout, int in_mode, int N, int H, int W,
+                                  const float* x, const float* dy, float* dw, float* db,
+                                  float* partial, size_t partial_bytes, int* error_flag,
+                                  seedrl_stream_t stream);
 int seedrl_debug_maxpool(int backward, int N, int H, int W, int C, const float* x_or_dy,
                          float* y_or_dx, uint8_t* idx, seedrl_stream_t stream);
 int seedrl_debug_sgemm(int ta, int tb, int M, int N, int K, const float* A, int lda,

@@ -100,6 +100,8 @@ SIGNATURES = {
     'seedrl_debug_conv3x3_tc':
         (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, c_int, c_int, P, P, P]),
     'seedrl_debug_wgrad_partial_bytes': (c_size_t, []),
+    'seedrl_debug_conv3x3_wgrad_tc':
+        (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, c_size_t, P, P]),
     'seedrl_debug_conv3x3_wgrad':
         (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, c_size_t, P]),
     'seedrl_debug_maxpool': (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P]),

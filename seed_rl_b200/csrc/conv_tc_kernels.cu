@@ -267,6 +267,242 @@ static int launch_tc(int N, int H, int W, const float* in, const uint4* wq, cons
   return SEEDRL_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// Weight gradient on the tensor cores.
+//   dW[tap][ci][co] = sum_p x~[p + tap][ci] * dy[p][co]      (x~ = relu(x) for the res convs)
+// as a GEMM with M = ci, N = co, K = positions.  Both operands are MN-major: for a fixed
+// position (K index) the 8 channels of a group are contiguous -- which is again exactly the
+// channel-group plane layout used by the forward kernel:
+//     core matrix = 8 positions (K) x 8 channels (MN), 128 B;  K-group stride (LBO) = 128 B;
+//     MN-group stride (SBO) = plane stride;  tap = descriptor start address + off*16 B.
+// UMMA M is 128, so rows >= CIN of every accumulator are junk (they read whatever follows
+// the x planes in shared memory) and are simply never read back; the MMA cost is the same
+// as M = 64.  One accumulator per tap (9 * COUT TMEM columns) lives across ALL chunks a
+// persistent CTA processes; shared-memory staging is double-buffered so that staging chunk
+// i+1 overlaps the 72 (= 9 taps x 8 K-steps) MMAs of chunk i.  Per-CTA partial dW/db are
+// reduced in fixed order by wgrad_reduce (deterministic).
+__host__ __device__ constexpr uint32_t umma_idesc_mn(int M, int N) {
+  return umma_idesc(M, N) | (1u << 15) | (1u << 16);
+}
+
+constexpr int kWgThreads = 256;
+
+template <int CIN, int COUT, int IN_MODE>
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv3x3_wgrad_tc_kernel(ConvGeom g, const float* __restrict__ x, const float* __restrict__ dy,
+                        float* __restrict__ partial, int* __restrict__ error_flag) {
+  constexpr int G = CIN / 8, GO = COUT / 8;
+  constexpr int TCOLS = (9 * COUT <= 256) ? 256 : 512;
+  constexpr int NW = 9 * CIN * COUT + COUT;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int PW = g.PW;
+  const int L = kTcM + 2 * PW + 2;
+  const int LPl = L | 1;                                  // x plane stride (16-byte units)
+  const uint32_t buf_units = (uint32_t)G * LPl + (uint32_t)GO * kTcM;   // one staging buffer
+  uint4* s_buf = reinterpret_cast<uint4*>(smem_raw);      // [2][x planes | dy planes]
+  // (the region after the buffers is only ever READ by the junk rows of A)
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)2 * buf_units * 16);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(s_tmem + 2);   // [kWgThreads][8] bias partials
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_bar + 1)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                 "r"(TCOLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(s_tmem);
+  constexpr uint32_t idesc = umma_idesc_mn(kTcM, COUT);
+
+  float bsum[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) bsum[c] = 0.f;
+  uint32_t phase[2] = {0u, 0u};
+  bool pending[2] = {false, false};
+  bool timed_out = false;
+  auto wait_bar = [&](int b) {
+    uint32_t done = 0;
+    int spins = 0;
+    while (!done) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}\n"
+          : "=r"(done)
+          : "r"(smem_u32(s_bar + b)), "r"(phase[b])
+          : "memory");
+      if (!done && ++spins > (1 << 22)) { timed_out = true; break; }
+    }
+    phase[b] ^= 1u;
+  };
+
+  const int nchunks = (int)((g.Q + kTcM - 1) / kTcM);
+  int it = 0;
+  for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x, ++it) {
+    const int b = it & 1;
+    const int q0 = ch * kTcM;
+    uint4* s_x = s_buf + (size_t)b * buf_units;
+    uint4* s_d = s_x + (size_t)G * LPl;
+    // buffer b was last read by the MMAs issued two iterations ago
+    if (pending[b]) { wait_bar(b); pending[b] = false; }
+    // ---- stage x~ (with halo) and dy (zero at invalid positions) as bf16 planes ------------
+    for (int i = tid; i < L * G; i += kWgThreads) {
+      const int s = i / G, gch = i - s * G;
+      const int pix = in_pixel(g, q0 + s);
+      uint4 packed = make_uint4(0u, 0u, 0u, 0u);
+      if (pix >= 0) {
+        const float4* src = reinterpret_cast<const float4*>(x + (size_t)pix * CIN + gch * 8);
+        float4 a = __ldg(src), c = __ldg(src + 1);
+        if (IN_MODE == IN_RELU) {
+          a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+          c.x = fmaxf(c.x, 0.f); c.y = fmaxf(c.y, 0.f); c.z = fmaxf(c.z, 0.f); c.w = fmaxf(c.w, 0.f);
+        }
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(c.x, c.y), p3 = __floats2bfloat162_rn(c.z, c.w);
+        packed.x = *reinterpret_cast<uint32_t*>(&p0); packed.y = *reinterpret_cast<uint32_t*>(&p1);
+        packed.z = *reinterpret_cast<uint32_t*>(&p2); packed.w = *reinterpret_cast<uint32_t*>(&p3);
+      }
+      s_x[(size_t)gch * LPl + s] = packed;
+    }
+    // every thread always stages the same co-group (kWgThreads % GO == 0) => bsum[] is per
+    // (thread, channel-in-group) and the final reduction order is fixed.
+    for (int i = tid; i < kTcM * GO; i += kWgThreads) {
+      const int s = i / GO, go = i - s * GO;
+      const int pix = out_pixel(g, q0 + s);
+      uint4 packed = make_uint4(0u, 0u, 0u, 0u);
+      if (pix >= 0) {
+        const float4* src = reinterpret_cast<const float4*>(dy + (size_t)pix * COUT + go * 8);
+        const float4 a = __ldg(src), c = __ldg(src + 1);
+        bsum[0] += a.x; bsum[1] += a.y; bsum[2] += a.z; bsum[3] += a.w;
+        bsum[4] += c.x; bsum[5] += c.y; bsum[6] += c.z; bsum[7] += c.w;
+        __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+        __nv_bfloat162 p2 = __floats2bfloat162_rn(c.x, c.y), p3 = __floats2bfloat162_rn(c.z, c.w);
+        packed.x = *reinterpret_cast<uint32_t*>(&p0); packed.y = *reinterpret_cast<uint32_t*>(&p1);
+        packed.z = *reinterpret_cast<uint32_t*>(&p2); packed.w = *reinterpret_cast<uint32_t*>(&p3);
+      }
+      s_d[(size_t)go * kTcM + s] = packed;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    // ---- 9 taps x 8 K-steps of 16 positions: D[tap] (+)= X_tap^T . dY ----------------------
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t xa = smem_u32(s_x), da = smem_u32(s_d);
+      const uint32_t acc0 = it > 0 ? 1u : 0u;
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int off = (tap / 3) * PW + (tap % 3);
+#pragma unroll
+        for (int ks = 0; ks < kTcM / 16; ++ks) {
+          const uint64_t adesc = umma_desc(xa + (uint32_t)(ks * 16 + off) * 16u, 128u, (uint32_t)LPl * 16u);
+          const uint64_t bdesc = umma_desc(da + (uint32_t)(ks * 16) * 16u, 128u, (uint32_t)kTcM * 16u);
+          umma_f16(tmem_base + (uint32_t)(tap * COUT), adesc, bdesc, idesc, (ks > 0) ? 1u : acc0);
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                       smem_u32(s_bar + b))
+                   : "memory");
+    }
+    pending[b] = true;
+  }
+  // drain
+  if (pending[0]) wait_bar(0);
+  if (pending[1]) wait_bar(1);
+  if (timed_out && error_flag) atomicExch(error_flag, 1);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+  // ---- epilogue: rows 0..CIN-1 of each tap's accumulator -> this CTA's partial --------------
+  float* dst = partial + (size_t)blockIdx.x * NW;
+  if (warp == 0) {
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+      float v[COUT];
+      tmem_ld<COUT>(tmem_base + (uint32_t)(tap * COUT), v);       // lanes 0..31 of the accumulator
+      if (lane < CIN && it > 0) {
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) dst[((size_t)tap * CIN + lane) * COUT + c] = v[c];
+      } else if (lane < CIN) {
+#pragma unroll
+        for (int c = 0; c < COUT; ++c) dst[((size_t)tap * CIN + lane) * COUT + c] = 0.f;
+      }
+    }
+  }
+  // bias partial: fixed-order reduction over the threads that staged each co-group
+#pragma unroll
+  for (int c = 0; c < 8; ++c) s_bias[tid * 8 + c] = bsum[c];
+  __syncthreads();
+  if (tid < COUT) {
+    const int go = tid >> 3, c = tid & 7;
+    float s = 0.f;
+    for (int t = go; t < kWgThreads; t += GO) s += s_bias[t * 8 + c];   // thread t staged group t % GO
+    dst[9 * CIN * COUT + tid] = s;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TCOLS));
+  }
+}
+
+template <int CIN, int COUT, int IN_MODE>
+static int launch_wgrad_tc(int N, int H, int W, const float* x, const float* dy, float* dw, float* db,
+                           float* partial, size_t partial_bytes, int* err, cudaStream_t st) {
+  const ConvGeom g = make_geom(N, H, W);
+  const int L = kTcM + 2 * g.PW + 2;
+  const size_t plane = (size_t)(L | 1) * 16;
+  const size_t buf = (size_t)(CIN / 8) * plane + (size_t)(COUT / 8) * kTcM * 16;
+  // A's junk rows reach 16 plane strides past the start of the second buffer's x planes
+  size_t smem = buf + 16 * plane + 256;
+  const size_t need = 2 * buf + 64 + (size_t)kWgThreads * 8 * 4;
+  if (smem < need) smem = need;
+  static bool attr = false;
+  if (!attr) {
+    SEEDRL_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel<CIN, COUT, IN_MODE>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    attr = true;
+  }
+  if (smem > 220 * 1024) return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "wgrad_tc: image too wide");
+  if (g.Q + kTcM + 4 * g.PW >= (1LL << 31))
+    return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "wgrad_tc: batch too large for 32-bit positions");
+  constexpr int NW = 9 * CIN * COUT + COUT;
+  const long long nchunks = (g.Q + kTcM - 1) / kTcM;
+  int grid = kNumSMs;                       // 1 CTA per SM (TMEM: 9*COUT accumulator columns)
+  if (grid > nchunks) grid = (int)nchunks;
+  if ((size_t)grid * NW * sizeof(float) > partial_bytes)
+    return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "wgrad_tc: partial buffer too small");
+  conv3x3_wgrad_tc_kernel<CIN, COUT, IN_MODE><<<grid, kWgThreads, smem, st>>>(g, x, dy, partial, err);
+  count_launch(PC_CONV_WGRAD, st);
+  SEEDRL_CHECK_LAUNCH();
+  return wgrad_reduce(grid, 9 * CIN * COUT, COUT, partial, dw, db, st);
+}
+
+int conv3x3_wgrad_tc(int cin, int cout, int in_mode, int N, int H, int W, const float* x,
+                     const float* dy, float* dw, float* db, float* partial, size_t partial_bytes,
+                     int* err, cudaStream_t st) {
+#define SEEDRL_WGTC_CASE(CI, CO_, MODE)                                                   \
+  if (cin == CI && cout == CO_ && in_mode == MODE)                                        \
+    return launch_wgrad_tc<CI, CO_, MODE>(N, H, W, x, dy, dw, db, partial, partial_bytes, err, st);
+  SEEDRL_WGTC_CASE(16, 16, IN_RELU)
+  SEEDRL_WGTC_CASE(16, 32, IN_F32)
+  SEEDRL_WGTC_CASE(32, 32, IN_F32)
+  SEEDRL_WGTC_CASE(32, 32, IN_RELU)
+#undef SEEDRL_WGTC_CASE
+  return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "wgrad_tc: unsupported (cin,cout,mode)");
+}
+
+bool conv3x3_wgrad_tc_supported(int cin, int cout, int in_mode) {
+  return (cin == 16 && cout == 16 && in_mode == IN_RELU) || (cin == 16 && cout == 32 && in_mode == IN_F32) ||
+         (cin == 32 && cout == 32 && (in_mode == IN_F32 || in_mode == IN_RELU));
+}
+
 bool conv3x3_tc_supported(int cin, int cout, int in_mode) {
   return (cin == 16 || cin == 32) && (cout == 16 || cout == 32) && (in_mode == IN_F32 || in_mode == IN_RELU);
 }

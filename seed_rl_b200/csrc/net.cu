@@ -407,8 +407,14 @@ static int conv_bwd(const seedrl_net* n, const float* prm, float* grd, const Con
                     int H, int Wd, const void* x, int x_mode, const float* dy, const float* dmask,
                     const float* dres, float* dx, void* ws, const Plan& pl, cudaStream_t st) {
   // weight + bias gradient
-  SEEDRL_TRY(conv3x3_wgrad(l.cin, l.cout, x_mode, N, H, Wd, x, dy, G(n, grd, l.w), G(n, grd, l.b),
-                           W<float>(ws, pl.partial), conv3x3_wgrad_partial_bytes(), st));
+  if (n->conv_mode == 1 && conv3x3_wgrad_tc_supported(l.cin, l.cout, x_mode)) {
+    SEEDRL_TRY(conv3x3_wgrad_tc(l.cin, l.cout, x_mode, N, H, Wd, reinterpret_cast<const float*>(x), dy,
+                                G(n, grd, l.w), G(n, grd, l.b), W<float>(ws, pl.partial),
+                                conv3x3_wgrad_partial_bytes(), W<int>(ws, pl.tcerr), st));
+  } else {
+    SEEDRL_TRY(conv3x3_wgrad(l.cin, l.cout, x_mode, N, H, Wd, x, dy, G(n, grd, l.w), G(n, grd, l.b),
+                             W<float>(ws, pl.partial), conv3x3_wgrad_partial_bytes(), st));
+  }
   if (dx) {  // data gradient = conv with flipped, transposed weights
     g_conv_cat = PC_CONV_DGRAD;
     const int rc = run_conv(n, ws, pl, l.cout, l.cin, IN_F32, N, H, Wd, dy, P(n, prm, l.w), nullptr,
@@ -571,6 +577,14 @@ extern "C" int seedrl_debug_sgemm(int ta, int tb, int M, int N, int K, const flo
 // data-gradient) into `wq_scratch` (>= 9*cin*cout*2 bytes) and runs the tensor-core conv.
 // `variant` bit0/bit1 swap LBO/SBO of the A/B descriptors (bring-up aid); *error_flag is
 // set to 1 by the kernel if its bounded mbarrier wait expires.
+extern "C" int seedrl_debug_conv3x3_wgrad_tc(int cin, int cout, int in_mode, int N, int H, int W,
+                                             const float* x, const float* dy, float* dw, float* db,
+                                             float* partial, size_t partial_bytes, int* error_flag,
+                                             seedrl_stream_t stream) {
+  SEEDRL_CHECK_ARG(conv3x3_wgrad_tc_supported(cin, cout, in_mode), "unsupported (cin,cout,mode)");
+  return conv3x3_wgrad_tc(cin, cout, in_mode, N, H, W, x, dy, dw, db, partial, partial_bytes,
+                          error_flag, (cudaStream_t)stream);
+}
 extern "C" int seedrl_debug_conv3x3_tc(int cin, int cout, int in_mode, int N, int H, int W,
                                        const float* in, const float* w, const float* bias,
                                        const float* mask, const float* res, float* out, int flip,
