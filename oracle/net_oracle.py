@@ -79,8 +79,41 @@ def param_specs(net, num_actions, obs_shape):
   return specs + conv
 
 
+# When set to torch.bfloat16, the 3x3 convolutions with >= 16 input channels round their
+# OPERANDS (activations, weights, and -- in the backward -- the incoming gradient) to bf16
+# and accumulate in fp32: the arithmetic contract of the tcgen05 tensor-core path
+# (seed_rl_b200 conv_mode='tc').  The fp32 reference semantics are CONV_OPERAND_DTYPE=None.
+CONV_OPERAND_DTYPE = None
+
+
+class _RoundedOperandConv(torch.autograd.Function):
+
+  @staticmethod
+  def forward(ctx, x, w, b, pads, dt):
+    q = lambda t: t.to(dt).to(torch.float32)
+    xq, wq = q(x), q(w)
+    ctx.save_for_backward(xq, wq)
+    ctx.pads, ctx.dt = pads, dt
+    y = F.conv2d(F.pad(xq.permute(0, 3, 1, 2), pads), wq.permute(3, 2, 0, 1), b)
+    return y.permute(0, 2, 3, 1)
+
+  @staticmethod
+  def backward(ctx, gy):
+    xq, wq = ctx.saved_tensors
+    gq = gy.to(ctx.dt).to(torch.float32)
+    with torch.enable_grad():
+      x2 = xq.detach().requires_grad_(True)
+      w2 = wq.detach().requires_grad_(True)
+      y = F.conv2d(F.pad(x2.permute(0, 3, 1, 2), ctx.pads), w2.permute(3, 2, 0, 1)).permute(0, 2, 3, 1)
+      gx, gw = torch.autograd.grad(y, (x2, w2), gq)
+    return gx, gw, gy.sum((0, 1, 2)), None, None     # bias gradient stays fp32
+
+
 def _conv_nhwc(x, w_hwio, b, stride, same):
   """x [N,H,W,C] -> [N,H',W',O].  Keras Conv2D(padding='same'|'valid')."""
+  if (CONV_OPERAND_DTYPE is not None and same and stride == 1 and tuple(w_hwio.shape[:2]) == (3, 3)
+      and w_hwio.shape[2] >= 16):
+    return _RoundedOperandConv.apply(x, w_hwio, b, (1, 1, 1, 1), CONV_OPERAND_DTYPE)
   N, H, W, C = x.shape
   kh, kw = w_hwio.shape[:2]
   xc = x.permute(0, 3, 1, 2)

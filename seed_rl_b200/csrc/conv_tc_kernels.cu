@@ -147,23 +147,42 @@ conv3x3_tc_kernel(ConvGeom g, const float* __restrict__ in, const uint4* __restr
   for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
     const int q0 = ch * kTcM;
     // ---- stage the input tile: fp32 NHWC -> bf16 channel-group planes -------------------
-    for (int i = tid; i < L * G; i += kTcThreads) {
-      const int s = i / G, gch = i - s * G;
-      const int pix = in_pixel(g, q0 + s);
-      uint4 packed = make_uint4(0u, 0u, 0u, 0u);
-      if (pix >= 0) {
-        const float4* src = reinterpret_cast<const float4*>(in + (size_t)pix * CIN + gch * 8);
-        float4 a = __ldg(src), b = __ldg(src + 1);
-        if (IN_MODE == IN_RELU) {
-          a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
-          b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f); b.z = fmaxf(b.z, 0.f); b.w = fmaxf(b.w, 0.f);
+    // 4 items per thread per round: all 8 x 16-byte loads are issued before any is consumed
+    for (int i0 = tid; i0 < L * G; i0 += 4 * kTcThreads) {
+      float4 va[4], vb[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k * kTcThreads;
+        va[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        vb[k] = va[k];
+        if (i < L * G) {
+          const int s = i / G, gch = i - s * G;
+          const int pix = in_pixel(g, q0 + s);
+          if (pix >= 0) {
+            const float4* src = reinterpret_cast<const float4*>(in + (size_t)pix * CIN + gch * 8);
+            va[k] = __ldg(src);
+            vb[k] = __ldg(src + 1);
+          }
         }
-        __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
-        __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
-        packed.x = *reinterpret_cast<uint32_t*>(&p0); packed.y = *reinterpret_cast<uint32_t*>(&p1);
-        packed.z = *reinterpret_cast<uint32_t*>(&p2); packed.w = *reinterpret_cast<uint32_t*>(&p3);
       }
-      s_a[(size_t)gch * LPl + s] = packed;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k * kTcThreads;
+        if (i < L * G) {
+          const int s = i / G, gch = i - s * G;
+          float4 a = va[k], b = vb[k];
+          if (IN_MODE == IN_RELU) {
+            a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+            b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f); b.z = fmaxf(b.z, 0.f); b.w = fmaxf(b.w, 0.f);
+          }
+          __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+          __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+          uint4 packed;
+          packed.x = *reinterpret_cast<uint32_t*>(&p0); packed.y = *reinterpret_cast<uint32_t*>(&p1);
+          packed.z = *reinterpret_cast<uint32_t*>(&p2); packed.w = *reinterpret_cast<uint32_t*>(&p3);
+          s_a[(size_t)gch * LPl + s] = packed;
+        }
+      }
     }
     // generic-proxy smem writes -> visible to the tensor core's async proxy
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -285,7 +304,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_mn(int M, int N) {
   return umma_idesc(M, N) | (1u << 15) | (1u << 16);
 }
 
-constexpr int kWgThreads = 256;
+constexpr int kWgThreads = 512;
 
 template <int CIN, int COUT, int IN_MODE>
 __global__ void __launch_bounds__(kWgThreads, 1)
@@ -344,52 +363,92 @@ conv3x3_wgrad_tc_kernel(ConvGeom g, const float* __restrict__ x, const float* __
     phase[b] ^= 1u;
   };
 
-  const int nchunks = (int)((g.Q + kTcM - 1) / kTcM);
-  int it = 0;
-  for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x, ++it) {
-    const int b = it & 1;
-    const int q0 = ch * kTcM;
-    uint4* s_x = s_buf + (size_t)b * buf_units;
-    uint4* s_d = s_x + (size_t)G * LPl;
-    // buffer b was last read by the MMAs issued two iterations ago
-    if (pending[b]) { wait_bar(b); pending[b] = false; }
-    // ---- stage x~ (with halo) and dy (zero at invalid positions) as bf16 planes ------------
-    for (int i = tid; i < L * G; i += kWgThreads) {
-      const int s = i / G, gch = i - s * G;
-      const int pix = in_pixel(g, q0 + s);
-      uint4 packed = make_uint4(0u, 0u, 0u, 0u);
-      if (pix >= 0) {
-        const float4* src = reinterpret_cast<const float4*>(x + (size_t)pix * CIN + gch * 8);
-        float4 a = __ldg(src), c = __ldg(src + 1);
+  // Register-prefetch pipeline: the global loads of chunk i+1 are issued right after chunk i
+  // has been converted into shared memory, so they are in flight during the barrier, the MMA
+  // issue and the next buffer wait (1 CTA/SM: latency must be hidden inside the CTA).
+  constexpr int IX = 3;                                             // host checks L*G <= IX*threads
+  constexpr int ID = (kTcM * GO + kWgThreads - 1) / kWgThreads;
+  float4 xa[IX], xb[IX], dya[ID], dyb[ID];
+  auto issue_loads = [&](int q0) {
+#pragma unroll
+    for (int k = 0; k < IX; ++k) {
+      const int i = tid + k * kWgThreads;
+      xa[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      xb[k] = xa[k];
+      if (i < L * G) {
+        const int s = i / G, gch = i - s * G;
+        const int pix = in_pixel(g, q0 + s);
+        if (pix >= 0) {
+          const float4* src = reinterpret_cast<const float4*>(x + (size_t)pix * CIN + gch * 8);
+          xa[k] = __ldg(src);
+          xb[k] = __ldg(src + 1);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < ID; ++k) {
+      const int i = tid + k * kWgThreads;
+      dya[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      dyb[k] = dya[k];
+      if (i < kTcM * GO) {
+        const int s = i / GO, go = i - s * GO;
+        const int pix = out_pixel(g, q0 + s);
+        if (pix >= 0) {
+          const float4* src = reinterpret_cast<const float4*>(dy + (size_t)pix * COUT + go * 8);
+          dya[k] = __ldg(src);
+          dyb[k] = __ldg(src + 1);
+        }
+      }
+    }
+  };
+  auto pack8 = [](float4 a, float4 c) {
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(c.x, c.y), p3 = __floats2bfloat162_rn(c.z, c.w);
+    uint4 r;
+    r.x = *reinterpret_cast<uint32_t*>(&p0); r.y = *reinterpret_cast<uint32_t*>(&p1);
+    r.z = *reinterpret_cast<uint32_t*>(&p2); r.w = *reinterpret_cast<uint32_t*>(&p3);
+    return r;
+  };
+  auto store_tile = [&](uint4* s_x, uint4* s_d) {
+#pragma unroll
+    for (int k = 0; k < IX; ++k) {
+      const int i = tid + k * kWgThreads;
+      if (i < L * G) {
+        const int s = i / G, gch = i - s * G;
+        float4 a = xa[k], c = xb[k];
         if (IN_MODE == IN_RELU) {
           a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
           c.x = fmaxf(c.x, 0.f); c.y = fmaxf(c.y, 0.f); c.z = fmaxf(c.z, 0.f); c.w = fmaxf(c.w, 0.f);
         }
-        __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
-        __nv_bfloat162 p2 = __floats2bfloat162_rn(c.x, c.y), p3 = __floats2bfloat162_rn(c.z, c.w);
-        packed.x = *reinterpret_cast<uint32_t*>(&p0); packed.y = *reinterpret_cast<uint32_t*>(&p1);
-        packed.z = *reinterpret_cast<uint32_t*>(&p2); packed.w = *reinterpret_cast<uint32_t*>(&p3);
+        s_x[(size_t)gch * LPl + s] = pack8(a, c);
       }
-      s_x[(size_t)gch * LPl + s] = packed;
     }
-    // every thread always stages the same co-group (kWgThreads % GO == 0) => bsum[] is per
-    // (thread, channel-in-group) and the final reduction order is fixed.
-    for (int i = tid; i < kTcM * GO; i += kWgThreads) {
-      const int s = i / GO, go = i - s * GO;
-      const int pix = out_pixel(g, q0 + s);
-      uint4 packed = make_uint4(0u, 0u, 0u, 0u);
-      if (pix >= 0) {
-        const float4* src = reinterpret_cast<const float4*>(dy + (size_t)pix * COUT + go * 8);
-        const float4 a = __ldg(src), c = __ldg(src + 1);
+    // a thread always stages the same co-group (kWgThreads % GO == 0) => bsum[] is per
+    // (thread, channel-in-group) and the final reduction order is fixed (deterministic).
+#pragma unroll
+    for (int k = 0; k < ID; ++k) {
+      const int i = tid + k * kWgThreads;
+      if (i < kTcM * GO) {
+        const int s = i / GO, go = i - s * GO;
+        const float4 a = dya[k], c = dyb[k];
         bsum[0] += a.x; bsum[1] += a.y; bsum[2] += a.z; bsum[3] += a.w;
         bsum[4] += c.x; bsum[5] += c.y; bsum[6] += c.z; bsum[7] += c.w;
-        __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
-        __nv_bfloat162 p2 = __floats2bfloat162_rn(c.x, c.y), p3 = __floats2bfloat162_rn(c.z, c.w);
-        packed.x = *reinterpret_cast<uint32_t*>(&p0); packed.y = *reinterpret_cast<uint32_t*>(&p1);
-        packed.z = *reinterpret_cast<uint32_t*>(&p2); packed.w = *reinterpret_cast<uint32_t*>(&p3);
+        s_d[(size_t)go * kTcM + s] = pack8(a, c);
       }
-      s_d[(size_t)go * kTcM + s] = packed;
     }
+  };
+
+  const int nchunks = (int)((g.Q + kTcM - 1) / kTcM);
+  int it = 0;
+  if ((int)blockIdx.x < nchunks) issue_loads(blockIdx.x * kTcM);
+  for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x, ++it) {
+    const int b = it & 1;
+    uint4* s_x = s_buf + (size_t)b * buf_units;
+    uint4* s_d = s_x + (size_t)G * LPl;
+    // buffer b was last read by the MMAs issued two iterations ago
+    if (pending[b]) { wait_bar(b); pending[b] = false; }
+    store_tile(s_x, s_d);                                  // x~ (with halo) and dy as bf16 planes
+    if (ch + (int)gridDim.x < nchunks) issue_loads((ch + (int)gridDim.x) * kTcM);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     // ---- 9 taps x 8 K-steps of 16 positions: D[tap] (+)= X_tap^T . dY ----------------------
@@ -469,7 +528,8 @@ static int launch_wgrad_tc(int N, int H, int W, const float* x, const float* dy,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr = true;
   }
-  if (smem > 220 * 1024) return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "wgrad_tc: image too wide");
+  if (smem > 220 * 1024 || (size_t)L * (CIN / 8) > (size_t)3 * kWgThreads)
+    return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "wgrad_tc: image too wide");
   if (g.Q + kTcM + 4 * g.PW >= (1LL << 31))
     return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "wgrad_tc: batch too large for 32-bit positions");
   constexpr int NW = 9 * CIN * COUT + COUT;
