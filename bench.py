@@ -42,8 +42,9 @@ def parse_args():
   p.add_argument('--batch', type=int, default=64, help='unrolls per GPU')
   p.add_argument('--unroll', type=int, default=20)
   p.add_argument('--cpu-batch', type=int, default=8, help='unrolls per CPU-baseline step')
-  p.add_argument('--conv', default='simt', choices=['simt', 'tc'],
-                 help="contraction path of the 16/32-channel convs: fp32 SIMT or tcgen05 bf16")
+  p.add_argument('--conv', default='tc3', choices=['simt', 'tc', 'tc3'],
+                 help="contraction path of the 16/32-channel convs: fp32 SIMT, tcgen05 bf16, or "
+                      "tcgen05 bf16x3 (fp32-faithful split operands; the parity mode)")
   p.add_argument('--no-extras', action='store_true',
                  help='skip the profiling pass, the loss-kernel sweep and the CPU baseline')
   return p.parse_args()
@@ -290,7 +291,8 @@ def main():
       'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
       'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True,
       'scaling': 'weak', 'vs_baseline': None,
-      'dtype': 'bf16' if args.conv == 'tc' else 'f32', 'data': 'synthetic',
+      'dtype': {'tc': 'bf16', 'tc3': 'bf16x3 (fp32-faithful tensor-core contraction), f32 elsewhere',
+                'simt': 'f32'}[args.conv], 'data': 'synthetic',
       'config': dict(workload_config(args, world), conv_path=args.conv), 'clocks': clocks,
       'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e,
               'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes,

@@ -168,7 +168,8 @@ size_t seedrl_net_num_params(const seedrl_net* net);          /* excl. entropy p
 size_t seedrl_net_arena_floats(const seedrl_net* net);
 /* Contraction path of the 16/32-channel 3x3 convolutions (forward + data gradient):
  * 0 = fp32 SIMT (bit-reproducible fp32 reference path), 1 = tcgen05 tensor cores, bf16
- * operands with fp32 accumulation. */
+ * operands with fp32 accumulation, 2 = tcgen05 with bf16x3 split operands (hi*hi + lo*hi +
+ * hi*lo: fp32-faithful to ~2^-16 relative). */
 int seedrl_net_set_conv_mode(seedrl_net* net, int mode);
 /* name is written into buf (NUL-terminated); shape into dims[0..3], rank returned. */
 int seedrl_net_param_info(const seedrl_net* net, int index, char* name_buf,
@@ -294,17 +295,17 @@ int seedrl_debug_conv3x3_wgrad(int cin, int cout, int in_mode, int N, int H, int
                                float* partial, size_t partial_bytes,
                                seedrl_stream_t stream);
 /* tcgen05 (tensor-core, bf16 x bf16 -> fp32) 3x3 convolution: packs fp32 HWIO weights
- * (flip != 0: flipped + transposed, i.e. the data-gradient) into wq_scratch
- * (>= 9*cin*cout*2 bytes) and runs the implicit-GEMM kernel.  variant bit0/bit1 swap the
+ * (flip != 0: flipped + transposed, i.e. the data-gradient; split != 0: bf16x3 hi/lo
+ * operands, fp32-faithful) into wq_scratch (>= 2*9*cin*cout*2 bytes) and runs the implicit-GEMM kernel.  variant bit0/bit1 swap the
  * LBO/SBO fields of the A/B shared-memory descriptors (bring-up aid); *error_flag becomes 1
  * if the kernel's bounded mbarrier wait expires. */
-int seedrl_debug_conv3x3_tc(int cin, int cout, int in_mode, int N, int H, int W,
+int seedrl_debug_conv3x3_tc(int cin, int cout, int in_mode, int split, int N, int H, int W,
                             const float* in, const float* w, const float* bias,
                             const float* mask, const float* res, float* out, int flip,
                             int variant, void* wq_scratch, int* error_flag,
                             seedrl_stream_t stream);
 /* tcgen05 weight gradient (MN-major operands, one TMEM accumulator per tap). */
-int seedrl_debug_conv3x3_wgrad_tc(int cin, int cout, int in_mode, int N, int H, int W,
+int seedrl_debug_conv3x3_wgrad_tc(int cin, int cout, int in_mode, int split, int N, int H, int W,
                                   const float* x, const float* dy, float* dw, float* db,
                                   float* partial, size_t partial_bytes, int* error_flag,
                                   seedrl_stream_t stream);

@@ -98,10 +98,10 @@ SIGNATURES = {
     'seedrl_debug_conv3x3': (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),
     'seedrl_debug_conv3x3_flip': (c_int, [c_int, c_int, P, P, P]),
     'seedrl_debug_conv3x3_tc':
-        (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, c_int, c_int, P, P, P]),
+        (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, c_int, c_int, P, P, P]),
     'seedrl_debug_wgrad_partial_bytes': (c_size_t, []),
     'seedrl_debug_conv3x3_wgrad_tc':
-        (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, c_size_t, P, P]),
+        (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, c_size_t, P, P]),
     'seedrl_debug_conv3x3_wgrad':
         (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, c_size_t, P]),
     'seedrl_debug_maxpool': (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P]),

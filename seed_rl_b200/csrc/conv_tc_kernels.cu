@@ -76,10 +76,25 @@ __device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, float* v) {
   tmem_ld<16>(taddr + 16, v + 16);
 }
 
+__device__ __forceinline__ uint4 pack8_bf16(float4 a, float4 c) {
+  __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+  __nv_bfloat162 p2 = __floats2bfloat162_rn(c.x, c.y), p3 = __floats2bfloat162_rn(c.z, c.w);
+  uint4 r;
+  r.x = *reinterpret_cast<uint32_t*>(&p0); r.y = *reinterpret_cast<uint32_t*>(&p1);
+  r.z = *reinterpret_cast<uint32_t*>(&p2); r.w = *reinterpret_cast<uint32_t*>(&p3);
+  return r;
+}
+// residual of the bf16 rounding: v - float(bf16(v)), componentwise (exact in fp32)
+__device__ __forceinline__ float bf16_resid(float v) { return v - __bfloat162float(__float2bfloat16_rn(v)); }
+__device__ __forceinline__ float4 bf16_resid4(float4 v) {
+  return make_float4(bf16_resid(v.x), bf16_resid(v.y), bf16_resid(v.z), bf16_resid(v.w));
+}
+
 // w fp32 [tap][ci_src][co_src]  ->  packed bf16 for an implicit GEMM with CIN x COUT:
 //   forward: element (tap, ci, co)   = w[tap][ci][co]
 //   flipped: element (tap, ci, co)   = w[8-tap][co][ci]     (data-gradient; src is [tap][COUT][CIN])
-__global__ void pack_w_tc_kernel(int CIN, int COUT, int flip, const float* __restrict__ w,
+// split != 0 (bf16x3): the lo parts (w - bf16(w), rounded to bf16) follow at wq[9*CIN*COUT + i].
+__global__ void pack_w_tc_kernel(int CIN, int COUT, int flip, int split, const float* __restrict__ w,
                                  __nv_bfloat16* __restrict__ wq) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 9 * CIN * COUT) return;
@@ -93,13 +108,18 @@ __global__ void pack_w_tc_kernel(int CIN, int COUT, int flip, const float* __res
   const int tap = rest / NS;
   const int ci = slab * 16 + kc * 8 + e, co = cog * 8 + r;
   const float v = flip ? w[((size_t)(8 - tap) * COUT + co) * CIN + ci] : w[((size_t)tap * CIN + ci) * COUT + co];
-  wq[i] = __float2bfloat16_rn(v);
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  wq[i] = hi;
+  if (split) wq[9 * CIN * COUT + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
 constexpr int kTcThreads = 128;
 constexpr int kTcM = 128;
 
-template <int CIN, int COUT, int IN_MODE>
+// SPLIT = bf16x3: activations and weights are split v = hi + lo (two bf16 planes / two packed
+// weight sets) and each K-step issues hi*hi + lo*hi + hi*lo -- an fp32-faithful (~2^-16
+// relative) contraction on the tensor cores; SPLIT = false is plain bf16 operands.
+template <int CIN, int COUT, int IN_MODE, bool SPLIT>
 __global__ void __launch_bounds__(kTcThreads)
 conv3x3_tc_kernel(ConvGeom g, const float* __restrict__ in, const uint4* __restrict__ wq,
                   const float* __restrict__ bias, const float* __restrict__ mask,
@@ -107,18 +127,19 @@ conv3x3_tc_kernel(ConvGeom g, const float* __restrict__ in, const uint4* __restr
                   int* __restrict__ error_flag) {
   constexpr int G = CIN / 8;          // channel-group planes
   constexpr int NS = CIN / 16;        // K slabs per tap
+  constexpr int S = SPLIT ? 2 : 1;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int PW = g.PW;
   const int L = kTcM + 2 * PW + 2;    // staged input positions
   const int LPl = L | 1;              // plane stride in 16-byte units (odd: conflict-free stores)
-  uint4* s_a = reinterpret_cast<uint4*>(smem_raw);                       // [G][LPl] x 16 B
-  uint4* s_b = s_a + (size_t)G * LPl;                                    // 9*CIN*COUT bf16
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_b + 9 * CIN * COUT / 8);
+  uint4* s_a = reinterpret_cast<uint4*>(smem_raw);                       // [S][G][LPl] x 16 B
+  uint4* s_b = s_a + (size_t)S * G * LPl;                                // [S] 9*CIN*COUT bf16
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_b + S * 9 * CIN * COUT / 8);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   // ---- one-time setup: weights -> smem, mbarrier, TMEM allocation --------------------
-  for (int i = tid; i < 9 * CIN * COUT / 8; i += kTcThreads) s_b[i] = __ldg(wq + i);
+  for (int i = tid; i < S * 9 * CIN * COUT / 8; i += kTcThreads) s_b[i] = __ldg(wq + i);
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_bar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -175,12 +196,8 @@ conv3x3_tc_kernel(ConvGeom g, const float* __restrict__ in, const uint4* __restr
             a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
             b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f); b.z = fmaxf(b.z, 0.f); b.w = fmaxf(b.w, 0.f);
           }
-          __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
-          __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
-          uint4 packed;
-          packed.x = *reinterpret_cast<uint32_t*>(&p0); packed.y = *reinterpret_cast<uint32_t*>(&p1);
-          packed.z = *reinterpret_cast<uint32_t*>(&p2); packed.w = *reinterpret_cast<uint32_t*>(&p3);
-          s_a[(size_t)gch * LPl + s] = packed;
+          s_a[(size_t)gch * LPl + s] = pack8_bf16(a, b);
+          if (SPLIT) s_a[(size_t)(G + gch) * LPl + s] = pack8_bf16(bf16_resid4(a), bf16_resid4(b));
         }
       }
     }
@@ -201,6 +218,10 @@ conv3x3_tc_kernel(ConvGeom g, const float* __restrict__ in, const uint4* __restr
           const uint64_t db = umma_desc(b_base + (uint32_t)(tap * NS + sl) * (COUT * 32u), b_lbo, b_sbo);
           umma_f16(tmem_base, da, db, idesc, acc);
           acc = 1;
+          if (SPLIT) {   // + lo(a)*hi(b) + hi(a)*lo(b); the address field counts 16-byte units
+            umma_f16(tmem_base, da + (uint64_t)(G * LPl), db, idesc, 1u);
+            umma_f16(tmem_base, da, db + (uint64_t)(9 * CIN * COUT / 8), idesc, 1u);
+          }
         }
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
@@ -260,16 +281,17 @@ conv3x3_tc_kernel(ConvGeom g, const float* __restrict__ in, const uint4* __restr
   }
 }
 
-template <int CIN, int COUT, int IN_MODE>
+template <int CIN, int COUT, int IN_MODE, bool SPLIT>
 static int launch_tc(int N, int H, int W, const float* in, const uint4* wq, const float* bias,
                      const float* mask, const float* res, float* out, int variant, int* err,
                      cudaStream_t st) {
   const ConvGeom g = make_geom(N, H, W);
   const int L = kTcM + 2 * g.PW + 2;
-  const size_t smem = (size_t)(CIN / 8) * (L | 1) * 16 + (size_t)9 * CIN * COUT * 2 + 64;
+  constexpr int S = SPLIT ? 2 : 1;
+  const size_t smem = S * ((size_t)(CIN / 8) * (L | 1) * 16 + (size_t)9 * CIN * COUT * 2) + 64;
   static bool attr = false;
   if (!attr) {
-    SEEDRL_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<CIN, COUT, IN_MODE>,
+    SEEDRL_CUDA(cudaFuncSetAttribute(conv3x3_tc_kernel<CIN, COUT, IN_MODE, SPLIT>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr = true;
   }
@@ -279,7 +301,7 @@ static int launch_tc(int N, int H, int W, const float* in, const uint4* wq, cons
   const long long nchunks = (g.Q + kTcM - 1) / kTcM;
   long long grid = kNumSMs * 6;
   if (grid > nchunks) grid = nchunks;
-  conv3x3_tc_kernel<CIN, COUT, IN_MODE><<<(unsigned)grid, kTcThreads, smem, st>>>(
+  conv3x3_tc_kernel<CIN, COUT, IN_MODE, SPLIT><<<(unsigned)grid, kTcThreads, smem, st>>>(
       g, in, wq, bias, mask, res, out, variant, err);
   count_launch(g_conv_cat, st);
   SEEDRL_CHECK_LAUNCH();
@@ -295,39 +317,68 @@ static int launch_tc(int N, int H, int W, const float* in, const uint4* wq, cons
 //     core matrix = 8 positions (K) x 8 channels (MN), 128 B;  K-group stride (LBO) = 128 B;
 //     MN-group stride (SBO) = plane stride;  tap = descriptor start address + off*16 B.
 // UMMA M is 128, so rows >= CIN of every accumulator are junk (they read whatever follows
-// the x planes in shared memory) and are simply never read back; the MMA cost is the same
-// as M = 64.  One accumulator per tap (9 * COUT TMEM columns) lives across ALL chunks a
-// persistent CTA processes; shared-memory staging is double-buffered so that staging chunk
-// i+1 overlaps the 72 (= 9 taps x 8 K-steps) MMAs of chunk i.  Per-CTA partial dW/db are
-// reduced in fixed order by wgrad_reduce (deterministic).
+// the x planes in shared memory) and are never read back; the MMA cost equals M = 64.
+// One accumulator per tap (9 * COUT TMEM columns) lives across ALL chunks of a persistent
+// CTA (1 CTA / SM).  Warp-specialised pipeline over kWgBufs shared-memory stages:
+//     warps 1..15  producers: fp32 global -> registers (prefetched one chunk ahead) ->
+//                  bf16 planes in smem -> fence.proxy.async -> arrive on full[stage]
+//     warp 0       one lane waits full[stage], issues the 72 (x3 when SPLIT) MMAs by
+//                  bumping the descriptor start-address field, commits to empty[stage]
+// SPLIT = bf16x3: operands are split x = hi + lo (two bf16 planes) and the product is
+// hi*hi + lo*hi + hi*lo, i.e. fp32-faithful (~2^-16 relative) contraction on tensor cores.
+// Per-CTA partial dW/db are reduced in fixed order by wgrad_reduce (deterministic).
 __host__ __device__ constexpr uint32_t umma_idesc_mn(int M, int N) {
   return umma_idesc(M, N) | (1u << 15) | (1u << 16);
 }
 
 constexpr int kWgThreads = 512;
+constexpr int kWgProducers = kWgThreads - 32;
+constexpr int kWgBufs = 3;
 
-template <int CIN, int COUT, int IN_MODE>
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, bool* timed_out) {
+  uint32_t done = 0;
+  int spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1 << 22)) { *timed_out = true; return; }
+  }
+}
+
+template <int CIN, int COUT, int IN_MODE, bool SPLIT>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv3x3_wgrad_tc_kernel(ConvGeom g, const float* __restrict__ x, const float* __restrict__ dy,
                         float* __restrict__ partial, int* __restrict__ error_flag) {
-  constexpr int G = CIN / 8, GO = COUT / 8;
+  constexpr int G = CIN / 8, GO = COUT / 8, S = SPLIT ? 2 : 1;
   constexpr int TCOLS = (9 * COUT <= 256) ? 256 : 512;
   constexpr int NW = 9 * CIN * COUT + COUT;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int PW = g.PW;
   const int L = kTcM + 2 * PW + 2;
   const int LPl = L | 1;                                  // x plane stride (16-byte units)
-  const uint32_t buf_units = (uint32_t)G * LPl + (uint32_t)GO * kTcM;   // one staging buffer
-  uint4* s_buf = reinterpret_cast<uint4*>(smem_raw);      // [2][x planes | dy planes]
-  // (the region after the buffers is only ever READ by the junk rows of A)
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)2 * buf_units * 16);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 2);
-  float* s_bias = reinterpret_cast<float*>(s_tmem + 2);   // [kWgThreads][8] bias partials
+  // one stage: [x hi planes | x lo planes | dy hi planes | dy lo planes]
+  const uint32_t xs_units = (uint32_t)G * LPl, ds_units = (uint32_t)GO * kTcM;
+  const uint32_t buf_units = S * (xs_units + ds_units);
+  uint4* s_buf = reinterpret_cast<uint4*>(smem_raw);
+  // (whatever follows the last stage is only ever READ, by the junk rows of A)
+  uint64_t* s_full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kWgBufs * buf_units * 16);
+  uint64_t* s_empty = s_full + kWgBufs;
+  uint64_t* s_done = s_empty + kWgBufs;
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_done + 1);
+  float* s_bias = reinterpret_cast<float*>(smem_raw);     // reused after the pipeline drains
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_bar)));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_bar + 1)));
+    for (int i = 0; i < kWgBufs; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(s_full + i)), "r"(kWgProducers / 32));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_empty + i)));
+    }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_done)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -341,142 +392,136 @@ conv3x3_wgrad_tc_kernel(ConvGeom g, const float* __restrict__ x, const float* __
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(s_tmem);
   constexpr uint32_t idesc = umma_idesc_mn(kTcM, COUT);
 
+  const int nchunks = (int)((g.Q + kTcM - 1) / kTcM);
+  const int my_chunks = ((int)blockIdx.x < nchunks) ? (nchunks - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  bool timed_out = false;
   float bsum[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) bsum[c] = 0.f;
-  uint32_t phase[2] = {0u, 0u};
-  bool pending[2] = {false, false};
-  bool timed_out = false;
-  auto wait_bar = [&](int b) {
-    uint32_t done = 0;
-    int spins = 0;
-    while (!done) {
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-          "selp.u32 %0, 1, 0, p;\n\t}\n"
-          : "=r"(done)
-          : "r"(smem_u32(s_bar + b)), "r"(phase[b])
-          : "memory");
-      if (!done && ++spins > (1 << 22)) { timed_out = true; break; }
-    }
-    phase[b] ^= 1u;
-  };
 
-  // Register-prefetch pipeline: the global loads of chunk i+1 are issued right after chunk i
-  // has been converted into shared memory, so they are in flight during the barrier, the MMA
-  // issue and the next buffer wait (1 CTA/SM: latency must be hidden inside the CTA).
-  constexpr int IX = 3;                                             // host checks L*G <= IX*threads
-  constexpr int ID = (kTcM * GO + kWgThreads - 1) / kWgThreads;
-  float4 xa[IX], xb[IX], dya[ID], dyb[ID];
-  auto issue_loads = [&](int q0) {
+  if (warp == 0) {
+    // ================================ MMA issuer ===========================================
+    if (lane == 0) {
+      for (int it = 0; it < my_chunks; ++it) {
+        const int b = it % kWgBufs;
+        mbar_wait(s_full + b, (uint32_t)((it / kWgBufs) & 1), &timed_out);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t xbase = smem_u32(s_buf + (size_t)b * buf_units);
+        const uint32_t dbase = xbase + S * xs_units * 16u;
+        // descriptors with start address 0; the address field counts 16-byte units
+        const uint64_t ax = umma_desc(0u, 128u, (uint32_t)LPl * 16u);
+        const uint64_t bd = umma_desc(0u, 128u, (uint32_t)kTcM * 16u);
+        const uint64_t xh = ax + (xbase >> 4), xl = xh + xs_units;
+        const uint64_t dh = bd + (dbase >> 4), dl = dh + ds_units;
+        const uint32_t acc0 = it > 0 ? 1u : 0u;
 #pragma unroll
-    for (int k = 0; k < IX; ++k) {
-      const int i = tid + k * kWgThreads;
-      xa[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      xb[k] = xa[k];
-      if (i < L * G) {
-        const int s = i / G, gch = i - s * G;
-        const int pix = in_pixel(g, q0 + s);
-        if (pix >= 0) {
-          const float4* src = reinterpret_cast<const float4*>(x + (size_t)pix * CIN + gch * 8);
-          xa[k] = __ldg(src);
-          xb[k] = __ldg(src + 1);
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t off = (uint32_t)((tap / 3) * PW + (tap % 3));
+          const uint32_t d_tmem = tmem_base + (uint32_t)(tap * COUT);
+#pragma unroll
+          for (int ks = 0; ks < kTcM / 16; ++ks) {
+            const uint32_t ko = (uint32_t)(ks * 16);
+            umma_f16(d_tmem, xh + ko + off, dh + ko, idesc, (ks > 0) ? 1u : acc0);
+            if (SPLIT) {
+              umma_f16(d_tmem, xl + ko + off, dh + ko, idesc, 1u);
+              umma_f16(d_tmem, xh + ko + off, dl + ko, idesc, 1u);
+            }
+          }
         }
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < ID; ++k) {
-      const int i = tid + k * kWgThreads;
-      dya[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-      dyb[k] = dya[k];
-      if (i < kTcM * GO) {
-        const int s = i / GO, go = i - s * GO;
-        const int pix = out_pixel(g, q0 + s);
-        if (pix >= 0) {
-          const float4* src = reinterpret_cast<const float4*>(dy + (size_t)pix * COUT + go * 8);
-          dya[k] = __ldg(src);
-          dyb[k] = __ldg(src + 1);
-        }
-      }
-    }
-  };
-  auto pack8 = [](float4 a, float4 c) {
-    __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
-    __nv_bfloat162 p2 = __floats2bfloat162_rn(c.x, c.y), p3 = __floats2bfloat162_rn(c.z, c.w);
-    uint4 r;
-    r.x = *reinterpret_cast<uint32_t*>(&p0); r.y = *reinterpret_cast<uint32_t*>(&p1);
-    r.z = *reinterpret_cast<uint32_t*>(&p2); r.w = *reinterpret_cast<uint32_t*>(&p3);
-    return r;
-  };
-  auto store_tile = [&](uint4* s_x, uint4* s_d) {
-#pragma unroll
-    for (int k = 0; k < IX; ++k) {
-      const int i = tid + k * kWgThreads;
-      if (i < L * G) {
-        const int s = i / G, gch = i - s * G;
-        float4 a = xa[k], c = xb[k];
-        if (IN_MODE == IN_RELU) {
-          a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
-          c.x = fmaxf(c.x, 0.f); c.y = fmaxf(c.y, 0.f); c.z = fmaxf(c.z, 0.f); c.w = fmaxf(c.w, 0.f);
-        }
-        s_x[(size_t)gch * LPl + s] = pack8(a, c);
-      }
-    }
-    // a thread always stages the same co-group (kWgThreads % GO == 0) => bsum[] is per
-    // (thread, channel-in-group) and the final reduction order is fixed (deterministic).
-#pragma unroll
-    for (int k = 0; k < ID; ++k) {
-      const int i = tid + k * kWgThreads;
-      if (i < kTcM * GO) {
-        const int s = i / GO, go = i - s * GO;
-        const float4 a = dya[k], c = dyb[k];
-        bsum[0] += a.x; bsum[1] += a.y; bsum[2] += a.z; bsum[3] += a.w;
-        bsum[4] += c.x; bsum[5] += c.y; bsum[6] += c.z; bsum[7] += c.w;
-        s_d[(size_t)go * kTcM + s] = pack8(a, c);
-      }
-    }
-  };
-
-  const int nchunks = (int)((g.Q + kTcM - 1) / kTcM);
-  int it = 0;
-  if ((int)blockIdx.x < nchunks) issue_loads(blockIdx.x * kTcM);
-  for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x, ++it) {
-    const int b = it & 1;
-    uint4* s_x = s_buf + (size_t)b * buf_units;
-    uint4* s_d = s_x + (size_t)G * LPl;
-    // buffer b was last read by the MMAs issued two iterations ago
-    if (pending[b]) { wait_bar(b); pending[b] = false; }
-    store_tile(s_x, s_d);                                  // x~ (with halo) and dy as bf16 planes
-    if (ch + (int)gridDim.x < nchunks) issue_loads((ch + (int)gridDim.x) * kTcM);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncthreads();
-    // ---- 9 taps x 8 K-steps of 16 positions: D[tap] (+)= X_tap^T . dY ----------------------
-    if (tid == 0) {
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t xa = smem_u32(s_x), da = smem_u32(s_d);
-      const uint32_t acc0 = it > 0 ? 1u : 0u;
-#pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        const int off = (tap / 3) * PW + (tap % 3);
-#pragma unroll
-        for (int ks = 0; ks < kTcM / 16; ++ks) {
-          const uint64_t adesc = umma_desc(xa + (uint32_t)(ks * 16 + off) * 16u, 128u, (uint32_t)LPl * 16u);
-          const uint64_t bdesc = umma_desc(da + (uint32_t)(ks * 16) * 16u, 128u, (uint32_t)kTcM * 16u);
-          umma_f16(tmem_base + (uint32_t)(tap * COUT), adesc, bdesc, idesc, (ks > 0) ? 1u : acc0);
-        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                         smem_u32(s_empty + b))
+                     : "memory");
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                       smem_u32(s_bar + b))
+                       smem_u32(s_done))
                    : "memory");
     }
-    pending[b] = true;
+  } else {
+    // ================================ producers ============================================
+    const int pt = tid - 32;
+    constexpr int IX = 3;                                             // host checks L*G <= IX*producers
+    constexpr int ID = (kTcM * GO + kWgProducers - 1) / kWgProducers;
+    float4 xa[IX], xb[IX], dya[ID], dyb[ID];
+    auto issue_loads = [&](int q0) {
+#pragma unroll
+      for (int k = 0; k < IX; ++k) {
+        const int i = pt + k * kWgProducers;
+        xa[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        xb[k] = xa[k];
+        if (i < L * G) {
+          const int s = i / G, gch = i - s * G;
+          const int pix = in_pixel(g, q0 + s);
+          if (pix >= 0) {
+            const float4* src = reinterpret_cast<const float4*>(x + (size_t)pix * CIN + gch * 8);
+            xa[k] = __ldg(src);
+            xb[k] = __ldg(src + 1);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < ID; ++k) {
+        const int i = pt + k * kWgProducers;
+        dya[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        dyb[k] = dya[k];
+        if (i < kTcM * GO) {
+          const int s = i / GO, go = i - s * GO;
+          const int pix = out_pixel(g, q0 + s);
+          if (pix >= 0) {
+            const float4* src = reinterpret_cast<const float4*>(dy + (size_t)pix * COUT + go * 8);
+            dya[k] = __ldg(src);
+            dyb[k] = __ldg(src + 1);
+          }
+        }
+      }
+    };
+    if (my_chunks > 0) issue_loads((int)blockIdx.x * kTcM);
+    for (int it = 0; it < my_chunks; ++it) {
+      const int b = it % kWgBufs;
+      uint4* s_x = s_buf + (size_t)b * buf_units;
+      uint4* s_d = s_x + (size_t)S * xs_units;
+      if (it >= kWgBufs) mbar_wait(s_empty + b, (uint32_t)(((it / kWgBufs) - 1) & 1), &timed_out);
+#pragma unroll
+      for (int k = 0; k < IX; ++k) {
+        const int i = pt + k * kWgProducers;
+        if (i < L * G) {
+          const int s = i / G, gch = i - s * G;
+          float4 a = xa[k], c = xb[k];
+          if (IN_MODE == IN_RELU) {
+            a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+            c.x = fmaxf(c.x, 0.f); c.y = fmaxf(c.y, 0.f); c.z = fmaxf(c.z, 0.f); c.w = fmaxf(c.w, 0.f);
+          }
+          s_x[(size_t)gch * LPl + s] = pack8_bf16(a, c);
+          if (SPLIT) s_x[xs_units + (size_t)gch * LPl + s] = pack8_bf16(bf16_resid4(a), bf16_resid4(c));
+        }
+      }
+      // a thread always stages the same co-group (kWgProducers % GO == 0) => bsum[] is per
+      // (thread, channel-in-group) and the final reduction order is fixed (deterministic).
+#pragma unroll
+      for (int k = 0; k < ID; ++k) {
+        const int i = pt + k * kWgProducers;
+        if (i < kTcM * GO) {
+          const int s = i / GO, go = i - s * GO;
+          const float4 a = dya[k], c = dyb[k];
+          bsum[0] += a.x; bsum[1] += a.y; bsum[2] += a.z; bsum[3] += a.w;
+          bsum[4] += c.x; bsum[5] += c.y; bsum[6] += c.z; bsum[7] += c.w;
+          s_d[(size_t)go * kTcM + s] = pack8_bf16(a, c);
+          if (SPLIT) s_d[ds_units + (size_t)go * kTcM + s] = pack8_bf16(bf16_resid4(a), bf16_resid4(c));
+        }
+      }
+      if (it + 1 < my_chunks) issue_loads(((int)blockIdx.x + (it + 1) * (int)gridDim.x) * kTcM);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0)
+        asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(
+                         smem_u32(s_full + b))
+                     : "memory");
+    }
   }
-  // drain
-  if (pending[0]) wait_bar(0);
-  if (pending[1]) wait_bar(1);
+  // ---- drain: every MMA of this CTA has completed when s_done flips --------------------------
+  mbar_wait(s_done, 0u, &timed_out);
   if (timed_out && error_flag) atomicExch(error_flag, 1);
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  __syncthreads();
 
   // ---- epilogue: rows 0..CIN-1 of each tap's accumulator -> this CTA's partial --------------
   float* dst = partial + (size_t)blockIdx.x * NW;
@@ -485,24 +530,24 @@ conv3x3_wgrad_tc_kernel(ConvGeom g, const float* __restrict__ x, const float* __
     for (int tap = 0; tap < 9; ++tap) {
       float v[COUT];
       tmem_ld<COUT>(tmem_base + (uint32_t)(tap * COUT), v);       // lanes 0..31 of the accumulator
-      if (lane < CIN && it > 0) {
+      if (lane < CIN) {
 #pragma unroll
-        for (int c = 0; c < COUT; ++c) dst[((size_t)tap * CIN + lane) * COUT + c] = v[c];
-      } else if (lane < CIN) {
-#pragma unroll
-        for (int c = 0; c < COUT; ++c) dst[((size_t)tap * CIN + lane) * COUT + c] = 0.f;
+        for (int c = 0; c < COUT; ++c)
+          dst[((size_t)tap * CIN + lane) * COUT + c] = my_chunks > 0 ? v[c] : 0.f;
       }
     }
   }
-  // bias partial: fixed-order reduction over the threads that staged each co-group
+  // bias partial: fixed-order reduction over the producers that staged each co-group
+  if (warp > 0) {
 #pragma unroll
-  for (int c = 0; c < 8; ++c) s_bias[tid * 8 + c] = bsum[c];
+    for (int c = 0; c < 8; ++c) s_bias[(tid - 32) * 8 + c] = bsum[c];
+  }
   __syncthreads();
   if (tid < COUT) {
     const int go = tid >> 3, c = tid & 7;
-    float s = 0.f;
-    for (int t = go; t < kWgThreads; t += GO) s += s_bias[t * 8 + c];   // thread t staged group t % GO
-    dst[9 * CIN * COUT + tid] = s;
+    float sum = 0.f;
+    for (int t = go; t < kWgProducers; t += GO) sum += s_bias[t * 8 + c];   // producer t staged group t % GO
+    dst[9 * CIN * COUT + tid] = sum;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -511,24 +556,26 @@ conv3x3_wgrad_tc_kernel(ConvGeom g, const float* __restrict__ x, const float* __
   }
 }
 
-template <int CIN, int COUT, int IN_MODE>
+template <int CIN, int COUT, int IN_MODE, bool SPLIT>
 static int launch_wgrad_tc(int N, int H, int W, const float* x, const float* dy, float* dw, float* db,
                            float* partial, size_t partial_bytes, int* err, cudaStream_t st) {
   const ConvGeom g = make_geom(N, H, W);
   const int L = kTcM + 2 * g.PW + 2;
+  constexpr int S = SPLIT ? 2 : 1;
   const size_t plane = (size_t)(L | 1) * 16;
-  const size_t buf = (size_t)(CIN / 8) * plane + (size_t)(COUT / 8) * kTcM * 16;
-  // A's junk rows reach 16 plane strides past the start of the second buffer's x planes
-  size_t smem = buf + 16 * plane + 256;
-  const size_t need = 2 * buf + 64 + (size_t)kWgThreads * 8 * 4;
+  const size_t buf = S * ((size_t)(CIN / 8) * plane + (size_t)(COUT / 8) * kTcM * 16);
+  // A's junk rows reach 16 plane strides past the start of the last stage's (lo) x planes
+  size_t smem = (kWgBufs - 1) * buf + (S - 1) * (size_t)(CIN / 8) * plane + 16 * plane + 256;
+  const size_t need = kWgBufs * buf + 256;
   if (smem < need) smem = need;
+  if (smem < (size_t)kWgProducers * 8 * 4) smem = (size_t)kWgProducers * 8 * 4;
   static bool attr = false;
   if (!attr) {
-    SEEDRL_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel<CIN, COUT, IN_MODE>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    SEEDRL_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel<CIN, COUT, IN_MODE, SPLIT>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     attr = true;
   }
-  if (smem > 220 * 1024 || (size_t)L * (CIN / 8) > (size_t)3 * kWgThreads)
+  if (smem > 224 * 1024 || (size_t)L * (CIN / 8) > (size_t)3 * kWgProducers)
     return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "wgrad_tc: image too wide");
   if (g.Q + kTcM + 4 * g.PW >= (1LL << 31))
     return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "wgrad_tc: batch too large for 32-bit positions");
@@ -538,18 +585,20 @@ static int launch_wgrad_tc(int N, int H, int W, const float* x, const float* dy,
   if (grid > nchunks) grid = (int)nchunks;
   if ((size_t)grid * NW * sizeof(float) > partial_bytes)
     return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "wgrad_tc: partial buffer too small");
-  conv3x3_wgrad_tc_kernel<CIN, COUT, IN_MODE><<<grid, kWgThreads, smem, st>>>(g, x, dy, partial, err);
+  conv3x3_wgrad_tc_kernel<CIN, COUT, IN_MODE, SPLIT><<<grid, kWgThreads, smem, st>>>(g, x, dy, partial, err);
   count_launch(PC_CONV_WGRAD, st);
   SEEDRL_CHECK_LAUNCH();
   return wgrad_reduce(grid, 9 * CIN * COUT, COUT, partial, dw, db, st);
 }
 
-int conv3x3_wgrad_tc(int cin, int cout, int in_mode, int N, int H, int W, const float* x,
+int conv3x3_wgrad_tc(int cin, int cout, int in_mode, int split, int N, int H, int W, const float* x,
                      const float* dy, float* dw, float* db, float* partial, size_t partial_bytes,
                      int* err, cudaStream_t st) {
-#define SEEDRL_WGTC_CASE(CI, CO_, MODE)                                                   \
-  if (cin == CI && cout == CO_ && in_mode == MODE)                                        \
-    return launch_wgrad_tc<CI, CO_, MODE>(N, H, W, x, dy, dw, db, partial, partial_bytes, err, st);
+#define SEEDRL_WGTC_CASE(CI, CO_, MODE)                                                          \
+  if (cin == CI && cout == CO_ && in_mode == MODE) {                                             \
+    if (split) return launch_wgrad_tc<CI, CO_, MODE, true>(N, H, W, x, dy, dw, db, partial, partial_bytes, err, st); \
+    return launch_wgrad_tc<CI, CO_, MODE, false>(N, H, W, x, dy, dw, db, partial, partial_bytes, err, st);           \
+  }
   SEEDRL_WGTC_CASE(16, 16, IN_RELU)
   SEEDRL_WGTC_CASE(16, 32, IN_F32)
   SEEDRL_WGTC_CASE(32, 32, IN_F32)
@@ -567,21 +616,25 @@ bool conv3x3_tc_supported(int cin, int cout, int in_mode) {
   return (cin == 16 || cin == 32) && (cout == 16 || cout == 32) && (in_mode == IN_F32 || in_mode == IN_RELU);
 }
 
-int conv3x3_tc_pack_weights(int cin, int cout, int flip, const float* w, void* wq, cudaStream_t st) {
+int conv3x3_tc_pack_weights(int cin, int cout, int flip, int split, const float* w, void* wq,
+                            cudaStream_t st) {
   const int n = 9 * cin * cout;
-  pack_w_tc_kernel<<<ceil_div(n, 256), 256, 0, st>>>(cin, cout, flip, w, reinterpret_cast<__nv_bfloat16*>(wq));
+  pack_w_tc_kernel<<<ceil_div(n, 256), 256, 0, st>>>(cin, cout, flip, split, w,
+                                                     reinterpret_cast<__nv_bfloat16*>(wq));
   count_launch(PC_MISC, st);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
 }
 
-int conv3x3_tc_forward(int cin, int cout, int in_mode, int N, int H, int W, const float* in,
+int conv3x3_tc_forward(int cin, int cout, int in_mode, int split, int N, int H, int W, const float* in,
                        const void* wq, const float* bias, const float* mask, const float* res,
                        float* out, int variant, int* err, cudaStream_t st) {
-#define SEEDRL_TC_CASE(CI, CO_, MODE)                                                     \
-  if (cin == CI && cout == CO_ && in_mode == MODE)                                        \
-    return launch_tc<CI, CO_, MODE>(N, H, W, in, reinterpret_cast<const uint4*>(wq), bias, mask, res, \
-                                    out, variant, err, st);
+  const uint4* q = reinterpret_cast<const uint4*>(wq);
+#define SEEDRL_TC_CASE(CI, CO_, MODE)                                                               \
+  if (cin == CI && cout == CO_ && in_mode == MODE) {                                                \
+    if (split) return launch_tc<CI, CO_, MODE, true>(N, H, W, in, q, bias, mask, res, out, variant, err, st); \
+    return launch_tc<CI, CO_, MODE, false>(N, H, W, in, q, bias, mask, res, out, variant, err, st); \
+  }
   SEEDRL_TC_CASE(16, 16, IN_F32)
   SEEDRL_TC_CASE(16, 16, IN_RELU)
   SEEDRL_TC_CASE(16, 32, IN_F32)

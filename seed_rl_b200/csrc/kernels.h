@@ -46,12 +46,13 @@ __device__ __forceinline__ int out_pixel(const ConvGeom& g, int p) {
 
 // conv_tc_kernels.cu (tcgen05 tensor-core path)
 bool conv3x3_tc_supported(int cin, int cout, int in_mode);
-int conv3x3_tc_pack_weights(int cin, int cout, int flip, const float* w, void* wq, cudaStream_t st);
+int conv3x3_tc_pack_weights(int cin, int cout, int flip, int split, const float* w, void* wq,
+                            cudaStream_t st);
 bool conv3x3_wgrad_tc_supported(int cin, int cout, int in_mode);
-int conv3x3_wgrad_tc(int cin, int cout, int in_mode, int N, int H, int W, const float* x,
+int conv3x3_wgrad_tc(int cin, int cout, int in_mode, int split, int N, int H, int W, const float* x,
                      const float* dy, float* dw, float* db, float* partial, size_t partial_bytes,
                      int* err, cudaStream_t st);
-int conv3x3_tc_forward(int cin, int cout, int in_mode, int N, int H, int W, const float* in,
+int conv3x3_tc_forward(int cin, int cout, int in_mode, int split, int N, int H, int W, const float* in,
                        const void* wq, const float* bias, const float* mask, const float* res,
                        float* out, int variant, int* err, cudaStream_t st);
 

@@ -48,7 +48,7 @@ struct seedrl_net {
   int sh_c0w, sh_c0b, sh_c1w, sh_c1b;      // shallow
   int sh_h1, sh_w1, sh_h2, sh_w2;
   int flat;                                // conv features fed to Dense(256)
-  int conv_mode = 0;                       // 0 = fp32 SIMT, 1 = tcgen05 bf16 for the 16/32-channel convs
+  int conv_mode = 0;                       // 0 = fp32 SIMT, 1 = tcgen05 bf16, 2 = tcgen05 bf16x3 (fp32-faithful)
   int core_in;                             // 256 + 1 + A
 };
 
@@ -145,7 +145,7 @@ static Plan make_plan(const seedrl_net* n, int T1, int B) {
   p.gC = b.take(pooled_max * 4);
   p.gFull = b.take(full_max * 4);
   p.wt = b.take(64 * 1024 * 4);
-  p.wq = b.take(64 * 1024 * 2);
+  p.wq = b.take(2 * 64 * 1024 * 2);
   p.tcerr = b.take(256);
   p.partial = b.take(conv3x3_wgrad_partial_bytes());
   p.total = b.off;
@@ -175,11 +175,12 @@ static inline T* W(void* ws, size_t off) {
 static int run_conv(const seedrl_net* n, void* ws, const Plan& pl, int cin, int cout, int in_mode,
                     int N, int H, int Wd, const void* in, const float* w, const float* bias,
                     const float* mask, const float* res, float* out, int flip, cudaStream_t st) {
-  if (n->conv_mode == 1 && conv3x3_tc_supported(cin, cout, in_mode)) {
+  if (n->conv_mode >= 1 && conv3x3_tc_supported(cin, cout, in_mode)) {
     void* wq = W<void>(ws, pl.wq);
-    SEEDRL_TRY(conv3x3_tc_pack_weights(cin, cout, flip, w, wq, st));
-    return conv3x3_tc_forward(cin, cout, in_mode, N, H, Wd, reinterpret_cast<const float*>(in), wq,
-                              bias, mask, res, out, 0, W<int>(ws, pl.tcerr), st);
+    const int split = n->conv_mode == 2;
+    SEEDRL_TRY(conv3x3_tc_pack_weights(cin, cout, flip, split, w, wq, st));
+    return conv3x3_tc_forward(cin, cout, in_mode, split, N, H, Wd, reinterpret_cast<const float*>(in),
+                              wq, bias, mask, res, out, 0, W<int>(ws, pl.tcerr), st);
   }
   if (flip) {
     float* wt = W<float>(ws, pl.wt);
@@ -265,7 +266,8 @@ extern "C" int seedrl_net_num_param_tensors(const seedrl_net* net) {
 extern "C" size_t seedrl_net_num_params(const seedrl_net* net) { return net ? net->logical_params : 0; }
 extern "C" size_t seedrl_net_arena_floats(const seedrl_net* net) { return net ? net->arena_floats : 0; }
 extern "C" int seedrl_net_set_conv_mode(seedrl_net* net, int mode) {
-  SEEDRL_CHECK_ARG(net && (mode == 0 || mode == 1), "mode must be 0 (fp32 SIMT) or 1 (tcgen05 bf16)");
+  SEEDRL_CHECK_ARG(net && mode >= 0 && mode <= 2,
+                   "mode must be 0 (fp32 SIMT), 1 (tcgen05 bf16) or 2 (tcgen05 bf16x3)");
   net->conv_mode = mode;
   return SEEDRL_OK;
 }
@@ -407,8 +409,9 @@ static int conv_bwd(const seedrl_net* n, const float* prm, float* grd, const Con
                     int H, int Wd, const void* x, int x_mode, const float* dy, const float* dmask,
                     const float* dres, float* dx, void* ws, const Plan& pl, cudaStream_t st) {
   // weight + bias gradient
-  if (n->conv_mode == 1 && conv3x3_wgrad_tc_supported(l.cin, l.cout, x_mode)) {
-    SEEDRL_TRY(conv3x3_wgrad_tc(l.cin, l.cout, x_mode, N, H, Wd, reinterpret_cast<const float*>(x), dy,
+  if (n->conv_mode >= 1 && conv3x3_wgrad_tc_supported(l.cin, l.cout, x_mode)) {
+    SEEDRL_TRY(conv3x3_wgrad_tc(l.cin, l.cout, x_mode, n->conv_mode == 2, N, H, Wd,
+                                reinterpret_cast<const float*>(x), dy,
                                 G(n, grd, l.w), G(n, grd, l.b), W<float>(ws, pl.partial),
                                 conv3x3_wgrad_partial_bytes(), W<int>(ws, pl.tcerr), st));
   } else {
@@ -577,21 +580,21 @@ extern "C" int seedrl_debug_sgemm(int ta, int tb, int M, int N, int K, const flo
 // data-gradient) into `wq_scratch` (>= 9*cin*cout*2 bytes) and runs the tensor-core conv.
 // `variant` bit0/bit1 swap LBO/SBO of the A/B descriptors (bring-up aid); *error_flag is
 // set to 1 by the kernel if its bounded mbarrier wait expires.
-extern "C" int seedrl_debug_conv3x3_wgrad_tc(int cin, int cout, int in_mode, int N, int H, int W,
+extern "C" int seedrl_debug_conv3x3_wgrad_tc(int cin, int cout, int in_mode, int split, int N, int H, int W,
                                              const float* x, const float* dy, float* dw, float* db,
                                              float* partial, size_t partial_bytes, int* error_flag,
                                              seedrl_stream_t stream) {
   SEEDRL_CHECK_ARG(conv3x3_wgrad_tc_supported(cin, cout, in_mode), "unsupported (cin,cout,mode)");
-  return conv3x3_wgrad_tc(cin, cout, in_mode, N, H, W, x, dy, dw, db, partial, partial_bytes,
+  return conv3x3_wgrad_tc(cin, cout, in_mode, split, N, H, W, x, dy, dw, db, partial, partial_bytes,
                           error_flag, (cudaStream_t)stream);
 }
-extern "C" int seedrl_debug_conv3x3_tc(int cin, int cout, int in_mode, int N, int H, int W,
+extern "C" int seedrl_debug_conv3x3_tc(int cin, int cout, int in_mode, int split, int N, int H, int W,
                                        const float* in, const float* w, const float* bias,
                                        const float* mask, const float* res, float* out, int flip,
                                        int variant, void* wq_scratch, int* error_flag,
                                        seedrl_stream_t stream) {
   SEEDRL_CHECK_ARG(conv3x3_tc_supported(cin, cout, in_mode), "unsupported (cin,cout,mode)");
-  SEEDRL_TRY(conv3x3_tc_pack_weights(cin, cout, flip, w, wq_scratch, (cudaStream_t)stream));
-  return conv3x3_tc_forward(cin, cout, in_mode, N, H, W, in, wq_scratch, bias, mask, res, out,
+  SEEDRL_TRY(conv3x3_tc_pack_weights(cin, cout, flip, split, w, wq_scratch, (cudaStream_t)stream));
+  return conv3x3_tc_forward(cin, cout, in_mode, split, N, H, W, in, wq_scratch, bias, mask, res, out,
                             variant, error_flag, (cudaStream_t)stream);
 }

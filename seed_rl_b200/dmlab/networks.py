@@ -41,10 +41,11 @@ class _CudaAgent(object):
     h = ctypes.c_void_p()
     _lib.check(L.seedrl_net_create(ctypes.byref(cfg), ctypes.byref(h)))
     self._h = h
-    if conv_mode not in ('simt', 'tc'):
-      raise ValueError("conv_mode must be 'simt' or 'tc'")
+    modes = {'simt': 0, 'tc': 1, 'tc3': 2}
+    if conv_mode not in modes:
+      raise ValueError("conv_mode must be 'simt', 'tc' (bf16) or 'tc3' (bf16x3, fp32-faithful)")
     self.conv_mode = conv_mode
-    _lib.check(L.seedrl_net_set_conv_mode(h, 1 if conv_mode == 'tc' else 0))
+    _lib.check(L.seedrl_net_set_conv_mode(h, modes[conv_mode]))
     self._n_tensors = L.seedrl_net_num_param_tensors(h)
     self.arena_floats = int(L.seedrl_net_arena_floats(h))
     self.num_params = int(L.seedrl_net_num_params(h))
