@@ -42,7 +42,7 @@ def parse_args():
   p.add_argument('--batch', type=int, default=64, help='unrolls per GPU')
   p.add_argument('--unroll', type=int, default=20)
   p.add_argument('--cpu-batch', type=int, default=8, help='unrolls per CPU-baseline step')
-  p.add_argument('--conv', default='tc3', choices=['simt', 'tc', 'tc3'],
+  p.add_argument('--conv', default='tc', choices=['simt', 'tc', 'tc3'],
                  help="contraction path of the 16/32-channel convs: fp32 SIMT, tcgen05 bf16, or "
                       "tcgen05 bf16x3 (fp32-faithful split operands; the parity mode)")
   p.add_argument('--no-extras', action='store_true',
@@ -372,6 +372,20 @@ def main():
                                       'peak_source': peak_src, 'l2': 'flushed between launches',
                                       'timing': 'median of 10 single launches incl. torch wrapper '
                                                 'allocations on the stream', 'sweep': sweep}
+      # ---- the other contraction paths, same workload (5 steps each) ----------------------
+      others = {}
+      for mode in ('simt', 'tc', 'tc3'):
+        if mode == args.conv:
+          continue
+        ag = cls(A, OBS, seed=0, conv_mode=mode)
+        stp = learner.LearnerStep(ag, optimizers.Adam(4.8e-4, beta_1=0.0, epsilon=3.125e-7),
+                                  settings=learner.default_loss_settings())
+        for _ in range(3):
+          stp.minimize(unroll)
+        ms = timed(lambda: stp.minimize(unroll), 5)
+        others[mode] = {'ms_per_step': ms, 'value': B * T / (ms * 1e-3)}
+        del ag, stp
+      line['other_conv_paths'] = others
       # ---- CPU baseline beside it (bounded sample) ----------------------------------------
       r = cpu_learner_throughput(args.net, T, args.cpu_batch, 3, 1)
       line['cpu_baseline'] = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',

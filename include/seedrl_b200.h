@@ -171,6 +171,9 @@ size_t seedrl_net_arena_floats(const seedrl_net* net);
  * operands with fp32 accumulation, 2 = tcgen05 with bf16x3 split operands (hi*hi + lo*hi +
  * hi*lo: fp32-faithful to ~2^-16 relative). */
 int seedrl_net_set_conv_mode(seedrl_net* net, int mode);
+/* LSTM recurrence: 1 (default) = one persistent cooperative kernel for all T steps each way,
+ * 0 = a GEMM + a pointwise kernel per time step. */
+int seedrl_net_set_lstm_mode(seedrl_net* net, int mode);
 /* name is written into buf (NUL-terminated); shape into dims[0..3], rank returned. */
 int seedrl_net_param_info(const seedrl_net* net, int index, char* name_buf,
                           size_t name_buf_len, int64_t* dims, size_t* offset);

@@ -48,6 +48,7 @@ struct seedrl_net {
   int sh_c0w, sh_c0b, sh_c1w, sh_c1b;      // shallow
   int sh_h1, sh_w1, sh_h2, sh_w2;
   int flat;                                // conv features fed to Dense(256)
+  int lstm_mode = 1;                       // 1 = persistent cooperative LSTM kernels, 0 = per-step launches
   int conv_mode = 0;                       // 0 = fp32 SIMT, 1 = tcgen05 bf16, 2 = tcgen05 bf16x3 (fp32-faithful)
   int core_in;                             // 256 + 1 + A
 };
@@ -95,7 +96,7 @@ struct Plan {
   size_t sh_a1, sh_a2;         // shallow conv outputs (post-relu)
   size_t xc, z, hp, cs, hs, c0buf;
   // backward scratch
-  size_t dhs, dz, dhrec, dc0, dc1, dd, gA, gB, gC, gFull, wt, partial, wq, tcerr;
+  size_t dhs, dz, dhrec, dc0, dc1, dd, gA, gB, gC, gFull, wt, partial, wq, tcerr, counter;
   size_t total;
 };
 
@@ -147,6 +148,7 @@ static Plan make_plan(const seedrl_net* n, int T1, int B) {
   p.wt = b.take(64 * 1024 * 4);
   p.wq = b.take(2 * 64 * 1024 * 2);
   p.tcerr = b.take(256);
+  p.counter = b.take(256);
   p.partial = b.take(conv3x3_wgrad_partial_bytes());
   p.total = b.off;
   return p;
@@ -265,6 +267,11 @@ extern "C" int seedrl_net_num_param_tensors(const seedrl_net* net) {
 }
 extern "C" size_t seedrl_net_num_params(const seedrl_net* net) { return net ? net->logical_params : 0; }
 extern "C" size_t seedrl_net_arena_floats(const seedrl_net* net) { return net ? net->arena_floats : 0; }
+extern "C" int seedrl_net_set_lstm_mode(seedrl_net* net, int mode) {
+  SEEDRL_CHECK_ARG(net && (mode == 0 || mode == 1), "mode must be 0 (per-step launches) or 1 (persistent)");
+  net->lstm_mode = mode;
+  return SEEDRL_OK;
+}
 extern "C" int seedrl_net_set_conv_mode(seedrl_net* net, int mode) {
   SEEDRL_CHECK_ARG(net && mode >= 0 && mode <= 2,
                    "mode must be 0 (fp32 SIMT), 1 (tcgen05 bf16) or 2 (tcgen05 bf16x3)");
@@ -374,10 +381,16 @@ extern "C" int seedrl_net_forward(const seedrl_net* n, const float* prm, int T1,
   SEEDRL_TRY(sgemm(false, false, N, 4 * kHidden, CI, xc, CI, P(n, prm, n->p_core_w), 4 * kHidden, z,
                    4 * kHidden, e, st));
   SEEDRL_CUDA(cudaMemcpyAsync(c0buf, c0, (size_t)B * kHidden * 4, cudaMemcpyDeviceToDevice, st));
-  SEEDRL_TRY(lstm_mask_state(B, kHidden, done, h0, hp, st));
   GemmEpi eacc = epi_none();
   eacc.accumulate = 1;
-  for (int t = 0; t < T1; ++t) {
+  if (n->lstm_mode == 1) {
+    // one cooperative kernel for the whole recurrence (lstm_persistent.cu)
+    SEEDRL_TRY(lstm_forward_persistent(T1, B, P(n, prm, n->p_core_u), done, z, h0, c0buf, hs, cs, hp,
+                                       W<unsigned int>(ws, pl.counter), W<int>(ws, pl.tcerr), st));
+  } else {
+    SEEDRL_TRY(lstm_mask_state(B, kHidden, done, h0, hp, st));
+  }
+  for (int t = 0; t < T1 && n->lstm_mode == 0; ++t) {
     float* zt = z + (size_t)t * B * 4 * kHidden;
     SEEDRL_TRY(sgemm(false, false, B, 4 * kHidden, kHidden, hp + (size_t)t * B * kHidden, kHidden,
                      P(n, prm, n->p_core_u), 4 * kHidden, zt, 4 * kHidden, eacc, st));
@@ -504,7 +517,10 @@ extern "C" int seedrl_net_backward(const seedrl_net* n, const float* prm, int T1
   SEEDRL_TRY(sgemm(false, true, N, kHidden, 1, dbaseline, 1, P(n, prm, n->p_base_w), 1, dhs, kHidden,
                    eacc, st));
   // BPTT
-  for (int t = T1 - 1; t >= 0; --t) {
+  if (n->lstm_mode == 1)
+    SEEDRL_TRY(lstm_backward_persistent(T1, B, P(n, prm, n->p_core_u), done, z, cs, c0buf, dhs, dz,
+                                        W<unsigned int>(ws, pl.counter), W<int>(ws, pl.tcerr), st));
+  for (int t = T1 - 1; t >= 0 && n->lstm_mode == 0; --t) {
     const bool last = (t + 1 == T1);
     const size_t o = (size_t)t * B * kHidden;
     SEEDRL_TRY(lstm_pointwise_bwd(B, kHidden, z + (size_t)t * B * 4 * kHidden, cs + o,

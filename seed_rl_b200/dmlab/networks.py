@@ -30,7 +30,8 @@ LSTM_UNITS = 256
 class _CudaAgent(object):
   _NET = None
 
-  def __init__(self, num_actions, obs_shape=(84, 84, 4), seed=0, device=None, conv_mode='simt'):
+  def __init__(self, num_actions, obs_shape=(84, 84, 4), seed=0, device=None, conv_mode='simt',
+               lstm_mode='persistent'):
     """conv_mode: 'simt' = fp32 CUDA-core contractions (bit-reproducible fp32 path),
     'tc' = tcgen05 tensor cores (bf16 operands, fp32 accumulation) for the 16/32-channel
     3x3 convolutions."""
@@ -46,6 +47,10 @@ class _CudaAgent(object):
       raise ValueError("conv_mode must be 'simt', 'tc' (bf16) or 'tc3' (bf16x3, fp32-faithful)")
     self.conv_mode = conv_mode
     _lib.check(L.seedrl_net_set_conv_mode(h, modes[conv_mode]))
+    if lstm_mode not in ('persistent', 'stepwise'):
+      raise ValueError("lstm_mode must be 'persistent' or 'stepwise'")
+    self.lstm_mode = lstm_mode
+    _lib.check(L.seedrl_net_set_lstm_mode(h, 1 if lstm_mode == 'persistent' else 0))
     self._n_tensors = L.seedrl_net_num_param_tensors(h)
     self.arena_floats = int(L.seedrl_net_arena_floats(h))
     self.num_params = int(L.seedrl_net_num_params(h))
