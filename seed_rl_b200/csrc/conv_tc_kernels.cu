@@ -390,7 +390,7 @@ conv3x3_wgrad_tc_kernel(ConvGeom g, const float* __restrict__ x, const float* __
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(s_tmem);
-  constexpr uint32_t idesc = umma_idesc_mn(kTcM, COUT);
+  constexpr uint32_t idesc = umma_idesc_mn(64, COUT);   // M = 64: only 8 channel-group rows of A are read
 
   const int nchunks = (int)((g.Q + kTcM - 1) / kTcM);
   const int my_chunks = ((int)blockIdx.x < nchunks) ? (nchunks - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -525,15 +525,18 @@ conv3x3_wgrad_tc_kernel(ConvGeom g, const float* __restrict__ x, const float* __
 
   // ---- epilogue: rows 0..CIN-1 of each tap's accumulator -> this CTA's partial --------------
   float* dst = partial + (size_t)blockIdx.x * NW;
-  if (warp == 0) {
+  // UMMA M = 64 accumulator layout (cute tmem_frg_1sm, M_MMA == 64): row m lives in TMEM
+  // lane (m % 16) + 32 * (m / 16), i.e. 16 rows per 32-lane sub-partition.
+  if (warp < (CIN + 15) / 16) {
 #pragma unroll 1
     for (int tap = 0; tap < 9; ++tap) {
       float v[COUT];
-      tmem_ld<COUT>(tmem_base + (uint32_t)(tap * COUT), v);       // lanes 0..31 of the accumulator
-      if (lane < CIN) {
+      tmem_ld<COUT>(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tap * COUT), v);
+      const int row = warp * 16 + lane;
+      if (lane < 16 && row < CIN) {
 #pragma unroll
         for (int c = 0; c < COUT; ++c)
-          dst[((size_t)tap * CIN + lane) * COUT + c] = my_chunks > 0 ? v[c] : 0.f;
+          dst[((size_t)tap * CIN + row) * COUT + c] = my_chunks > 0 ? v[c] : 0.f;
       }
     }
   }
@@ -565,7 +568,7 @@ static int launch_wgrad_tc(int N, int H, int W, const float* x, const float* dy,
   const size_t plane = (size_t)(L | 1) * 16;
   const size_t buf = S * ((size_t)(CIN / 8) * plane + (size_t)(COUT / 8) * kTcM * 16);
   // A's junk rows reach 16 plane strides past the start of the last stage's (lo) x planes
-  size_t smem = (kWgBufs - 1) * buf + (S - 1) * (size_t)(CIN / 8) * plane + 16 * plane + 256;
+  size_t smem = (kWgBufs - 1) * buf + (S - 1) * (size_t)(CIN / 8) * plane + 8 * plane + 256;
   const size_t need = kWgBufs * buf + 256;
   if (smem < need) smem = need;
   if (smem < (size_t)kWgProducers * 8 * 4) smem = (size_t)kWgProducers * 8 * 4;
