@@ -102,7 +102,7 @@ def run_reference(args):
       'gpu_launches': 0,
       'note': 'TensorFlow 2.4.1 is not installable here (no network): this arm times the CPU '
               'oracle, a line-by-line torch-CPU restatement of the reference learner step.'}
-  print(json.dumps(line))
+  emit(line)
 
 
 def workload_config(args, n, cpu=False):
@@ -189,8 +189,25 @@ def conv_bytes_per_step(N, cat):
   return tot, launches
 
 
+_JSON_FD = None
+
+
+def emit(line):
+  """The ONE JSON line goes to the real stdout; everything libraries print (e.g. NCCL's
+  version banner) was redirected to stderr by main()."""
+  data = (json.dumps(line) + '\n').encode()
+  if _JSON_FD is None:
+    sys.stdout.write(data.decode()); sys.stdout.flush()
+  else:
+    os.write(_JSON_FD, data)
+
+
 def main():
+  global _JSON_FD
   args = parse_args()
+  sys.stdout.flush()
+  _JSON_FD = os.dup(1)
+  os.dup2(2, 1)
   if args.impl == 'reference':
     return run_reference(args)
 
@@ -392,7 +409,7 @@ def main():
                               'sample': r['sample'], 'ms_per_step': r['ms_per_step']}
 
   if rank == 0:
-    print(json.dumps(line))
+    emit(line)
   if world > 1:
     dist.destroy_process_group()
 

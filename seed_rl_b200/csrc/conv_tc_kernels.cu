@@ -438,44 +438,46 @@ conv3x3_wgrad_tc_kernel(ConvGeom g, const float* __restrict__ x, const float* __
     }
   } else {
     // ================================ producers ============================================
+    // Two register sets: while chunk i is converted into shared memory, the global loads of
+    // chunks i+1 and i+2 are already in flight (the producers are pure latency hiding).
     const int pt = tid - 32;
-    constexpr int IX = 3;                                             // host checks L*G <= IX*producers
+    constexpr int IX = 2;                                             // host checks L*G <= IX*producers
     constexpr int ID = (kTcM * GO + kWgProducers - 1) / kWgProducers;
-    float4 xa[IX], xb[IX], dya[ID], dyb[ID];
-    auto issue_loads = [&](int q0) {
+    struct Regs { float4 xa[IX], xb[IX], dya[ID], dyb[ID]; };
+    auto issue_loads = [&](Regs& r, int q0) {
 #pragma unroll
       for (int k = 0; k < IX; ++k) {
         const int i = pt + k * kWgProducers;
-        xa[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        xb[k] = xa[k];
+        r.xa[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        r.xb[k] = r.xa[k];
         if (i < L * G) {
           const int s = i / G, gch = i - s * G;
           const int pix = in_pixel(g, q0 + s);
           if (pix >= 0) {
             const float4* src = reinterpret_cast<const float4*>(x + (size_t)pix * CIN + gch * 8);
-            xa[k] = __ldg(src);
-            xb[k] = __ldg(src + 1);
+            r.xa[k] = __ldg(src);
+            r.xb[k] = __ldg(src + 1);
           }
         }
       }
 #pragma unroll
       for (int k = 0; k < ID; ++k) {
         const int i = pt + k * kWgProducers;
-        dya[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        dyb[k] = dya[k];
+        r.dya[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        r.dyb[k] = r.dya[k];
         if (i < kTcM * GO) {
           const int s = i / GO, go = i - s * GO;
           const int pix = out_pixel(g, q0 + s);
           if (pix >= 0) {
             const float4* src = reinterpret_cast<const float4*>(dy + (size_t)pix * COUT + go * 8);
-            dya[k] = __ldg(src);
-            dyb[k] = __ldg(src + 1);
+            r.dya[k] = __ldg(src);
+            r.dyb[k] = __ldg(src + 1);
           }
         }
       }
     };
-    if (my_chunks > 0) issue_loads((int)blockIdx.x * kTcM);
-    for (int it = 0; it < my_chunks; ++it) {
+    auto chunk_q0 = [&](int it) { return ((int)blockIdx.x + it * (int)gridDim.x) * kTcM; };
+    auto stage = [&](Regs& r, int it) {
       const int b = it % kWgBufs;
       uint4* s_x = s_buf + (size_t)b * buf_units;
       uint4* s_d = s_x + (size_t)S * xs_units;
@@ -485,7 +487,7 @@ conv3x3_wgrad_tc_kernel(ConvGeom g, const float* __restrict__ x, const float* __
         const int i = pt + k * kWgProducers;
         if (i < L * G) {
           const int s = i / G, gch = i - s * G;
-          float4 a = xa[k], c = xb[k];
+          float4 a = r.xa[k], c = r.xb[k];
           if (IN_MODE == IN_RELU) {
             a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
             c.x = fmaxf(c.x, 0.f); c.y = fmaxf(c.y, 0.f); c.z = fmaxf(c.z, 0.f); c.w = fmaxf(c.w, 0.f);
@@ -501,20 +503,27 @@ conv3x3_wgrad_tc_kernel(ConvGeom g, const float* __restrict__ x, const float* __
         const int i = pt + k * kWgProducers;
         if (i < kTcM * GO) {
           const int s = i / GO, go = i - s * GO;
-          const float4 a = dya[k], c = dyb[k];
+          const float4 a = r.dya[k], c = r.dyb[k];
           bsum[0] += a.x; bsum[1] += a.y; bsum[2] += a.z; bsum[3] += a.w;
           bsum[4] += c.x; bsum[5] += c.y; bsum[6] += c.z; bsum[7] += c.w;
           s_d[(size_t)go * kTcM + s] = pack8_bf16(a, c);
           if (SPLIT) s_d[ds_units + (size_t)go * kTcM + s] = pack8_bf16(bf16_resid4(a), bf16_resid4(c));
         }
       }
-      if (it + 1 < my_chunks) issue_loads(((int)blockIdx.x + (it + 1) * (int)gridDim.x) * kTcM);
+      if (it + 2 < my_chunks) issue_loads(r, chunk_q0(it + 2));     // refill this register set
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0)
         asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(
                          smem_u32(s_full + b))
                      : "memory");
+    };
+    Regs r0, r1;
+    if (my_chunks > 0) issue_loads(r0, chunk_q0(0));
+    if (my_chunks > 1) issue_loads(r1, chunk_q0(1));
+    for (int it = 0; it < my_chunks; it += 2) {
+      stage(r0, it);
+      if (it + 1 < my_chunks) stage(r1, it + 1);
     }
   }
   // ---- drain: every MMA of this CTA has completed when s_done flips --------------------------
@@ -578,7 +587,7 @@ static int launch_wgrad_tc(int N, int H, int W, const float* x, const float* dy,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     attr = true;
   }
-  if (smem > 224 * 1024 || (size_t)L * (CIN / 8) > (size_t)3 * kWgProducers)
+  if (smem > 224 * 1024 || (size_t)L * (CIN / 8) > (size_t)2 * kWgProducers)
     return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "wgrad_tc: image too wide");
   if (g.Q + kTcM + 4 * g.PW >= (1LL << 31))
     return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "wgrad_tc: batch too large for 32-bit positions");
