@@ -28,6 +28,19 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a CONVERGED warp (elect.sync): inside `if (elect_one())` the compiler knows a
+// single thread is active, so uniform-datapath instructions (UTCHMMA, UTCBAR) are issued
+// directly instead of through a per-instruction election loop.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // cute::UMMA::SmemDescriptor (mma_sm100_desc.hpp): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout_type SWIZZLE_NONE=0 [61,64).
 __device__ __forceinline__ uint64_t umma_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -205,8 +218,8 @@ conv3x3_tc_kernel(ConvGeom g, const float* __restrict__ in, const uint4* __restr
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 
-    // ---- one thread issues the 9 * NS MMAs, then commits to the mbarrier ------------------
-    if (tid == 0) {
+    // ---- one elected lane of warp 0 issues the 9 * NS MMAs, then commits to the mbarrier ----
+    if (warp == 0 && elect_one()) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       uint32_t acc = 0;
 #pragma unroll
@@ -401,11 +414,12 @@ conv3x3_wgrad_tc_kernel(ConvGeom g, const float* __restrict__ x, const float* __
 
   if (warp == 0) {
     // ================================ MMA issuer ===========================================
-    if (lane == 0) {
-      for (int it = 0; it < my_chunks; ++it) {
-        const int b = it % kWgBufs;
-        mbar_wait(s_full + b, (uint32_t)((it / kWgBufs) & 1), &timed_out);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // (the whole warp walks the loop converged; one elected lane issues)
+    for (int it = 0; it < my_chunks; ++it) {
+      const int b = it % kWgBufs;
+      mbar_wait(s_full + b, (uint32_t)((it / kWgBufs) & 1), &timed_out);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (elect_one()) {
         const uint32_t xbase = smem_u32(s_buf + (size_t)b * buf_units);
         const uint32_t dbase = xbase + S * xs_units * 16u;
         // descriptors with start address 0; the address field counts 16-byte units
@@ -432,10 +446,13 @@ conv3x3_wgrad_tc_kernel(ConvGeom g, const float* __restrict__ x, const float* __
                          smem_u32(s_empty + b))
                      : "memory");
       }
+      __syncwarp();
+    }
+    if (elect_one())
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
                        smem_u32(s_done))
                    : "memory");
-    }
+    __syncwarp();
   } else {
     // ================================ producers ============================================
     // Two register sets: while chunk i is converted into shared memory, the global loads of

@@ -211,6 +211,66 @@ __device__ __forceinline__ float block_reduce_max(float v, float* red) {
   return r;
 }
 
+
+// Last CTA to arrive (ticket) reduces the per-CTA partials in index order and writes the
+// loss terms; deterministic for a given grid.
+__device__ __forceinline__ void loss_finalize(const LossParams& p, float* s_red, float ec, float invN) {
+  const int tid = threadIdx.x;
+  const float mul = p.cfg.entropy_cost_adjustment_speed;
+  const float kc = p.cfg.kl_cost;
+  __shared__ bool s_last;
+  if (tid == 0) {
+    __threadfence();
+    const unsigned int prev = atomicAdd(p.ticket, 1u);
+    s_last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float acc6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  // deterministic: thread k sums slices k, k+256, ... then a fixed-order tree.
+  for (unsigned int g = tid; g < gridDim.x; g += blockDim.x) {
+    const volatile float* q = p.partials + (size_t)g * kLossPartials;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) acc6[k] += q[k];
+    acc6[5] = fmaxf(acc6[5], q[5]);
+  }
+  float tot[6];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) tot[k] = block_reduce_sum(acc6[k], s_red);
+  tot[5] = block_reduce_max(acc6[5], s_red);
+  if (tid == 0) {
+    const float policy_loss = -tot[0] * invN;
+    const float mse = tot[1] * invN;
+    const float v_loss = p.cfg.baseline_cost * 0.5f * mse;
+    const float mean_h = tot[2] * invN;
+    const float entropy_loss = -ec * mean_h;
+    const float mean_kl = tot[3] * invN;
+    const float kl_loss = kc * mean_kl;
+    float adj = 0.f, dparam = 0.f;
+    if (p.cfg.has_target_entropy) {                        // :128-132
+      adj = ec * (mean_h - p.cfg.target_entropy);
+      dparam = mul * ec * (mean_h - p.cfg.target_entropy);
+    }
+    float* L = p.loss_terms;
+    L[SEEDRL_LT_TOTAL] = policy_loss + v_loss + entropy_loss + kl_loss + adj;  // :134-135
+    L[SEEDRL_LT_POLICY] = policy_loss;
+    L[SEEDRL_LT_V] = v_loss;
+    L[SEEDRL_LT_ENTROPY] = entropy_loss;
+    L[SEEDRL_LT_KL] = kl_loss;
+    L[SEEDRL_LT_ENTROPY_ADJ] = adj;
+    L[SEEDRL_LT_V_MEAN] = tot[4] * invN;
+    L[SEEDRL_LT_V_L2_ERROR] = sqrtf(mse);
+    L[SEEDRL_LT_MEAN_ENTROPY] = mean_h;
+    L[SEEDRL_LT_ENTROPY_COST] = ec;
+    L[SEEDRL_LT_MEAN_KL] = mean_kl;
+    L[SEEDRL_LT_MAX_ACTION_ABS] = tot[5];
+    for (int k = 12; k < SEEDRL_LOSS_TERMS; ++k) L[k] = 0.f;
+    *p.d_ecp = dparam;
+    *p.ticket = 0u;   // self-reset for the next launch
+  }
+}
+
 // Moves the CTA's logits tile between global memory ([T, B, A], columns b0..b0+nb) and
 // shared memory ([T][BB][A], dense).  For each t the slice is nb*A contiguous floats; warp w
 // takes rows t = w, w+8, ... and its lanes stride the row with float4 (all of a thread's
@@ -406,57 +466,301 @@ vtrace_loss_kernel(const LossParams p) {
   r = block_reduce_sum(sum_kl, s_red);  if (tid == 0) part[3] = r;
   r = block_reduce_sum(sum_v, s_red);   if (tid == 0) part[4] = r;
   r = block_reduce_max(max_a, s_red);   if (tid == 0) part[5] = r;
-  __shared__ bool s_last;
+  loss_finalize(p, s_red, ec, invN);
+}
+
+
+// ---------------------------------------------------------------------------
+// (a2, streaming form)  Same math, laid out for HBM throughput at large B.
+//
+// One persistent CTA per SM walks tiles of BB columns x T steps.  The two logits tiles of
+// a tile (behaviour, learner) are fetched by the TMA engine (cp.async.bulk, one 1-D bulk
+// copy of BB*A floats per time step) into a ring of three shared-memory buffers; the
+// gradient tile is written in place and leaves through cp.async.bulk stores.  Order of
+// bulk loads is bl_0, ll_0, bl_1, ll_1, ... (load k -> buffer k % 3), so while tile i is
+// being computed both tiles of tile i+1 are in flight and the dlogits store of tile i-1
+// drains: the memory system never idles behind the math.  The small per-row inputs
+// (reward, done, action, baseline) of tile i+1 are prefetched into registers during tile i.
+//   phase A   thread-per-row: behaviour log-prob                      (frees that buffer)
+//   phase B   thread-per-row: lse, target log-prob, entropy, rho -> (delta_t, d_t*c_t, clipped pg rho)
+//   scan      thread-per-column: acc_t = delta_t + (d_t c_t) acc_{t+1}   (one FMA per step)
+//   phase D   thread-per-row: pg advantage, loss sums, gradient in place, dbaseline
+// Loss sums are kept per thread over all tiles of the CTA (fixed tile->CTA map =>
+// deterministic), reduced once per CTA, finalised by the last CTA in index order.
+constexpr int kStreamThreadsMax = 512;
+constexpr int kStreamRounds = 4;    // register-prefetch rounds for the per-row inputs
+
+__device__ __forceinline__ uint32_t sm_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_wait_or_trap(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  int spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(sm_u32(bar)), "r"(parity)
+        : "memory");
+    if (!done && ++spins > (1 << 24)) __trap();   // never hang the GPU
+  }
+}
+
+struct SmallRegs {
+  float rew[kStreamRounds], val[kStreamRounds];
+  int act[kStreamRounds];
+  uint8_t done[kStreamRounds];
+};
+
+__global__ void __launch_bounds__(kStreamThreadsMax)
+vtrace_loss_stream_kernel(const LossParams p, const int ntiles) {
+  extern __shared__ __align__(128) float smem[];
+  const int T = p.T, B = p.B, A = p.A, BB = p.BB;
+  const int rows = T * BB;
+  const int tile_f = rows * A;                       // floats per logits tile (multiple of 4)
+  const uint32_t chunk_bytes = (uint32_t)(BB * A) * 4u;
+  const uint32_t tile_bytes = (uint32_t)tile_f * 4u;
+  float* s_tiles = smem;                             // [3][T][BB][A]
+  float* s_tlp = s_tiles + (size_t)3 * tile_f;       // [rows] target logp
+  float* s_acc = s_tlp + rows;                       // [rows] behaviour logp -> delta -> vs - V
+  float* s_lse = s_acc + rows;
+  float* s_ent = s_lse + rows;
+  float* s_rew = s_ent + rows;
+  float* s_dis = s_rew + rows;
+  float* s_dc = s_dis + rows;                        // [rows] discount_t * c_t
+  float* s_cpg = s_dc + rows;                        // [rows] clipped pg rho
+  float* s_val = s_cpg + rows;                       // [(T+1)*BB]
+  int* s_act = reinterpret_cast<int*>(s_val + (T + 1) * BB);
+  float* s_red = reinterpret_cast<float*>(s_act + rows);   // [32]
+  uint64_t* s_full = reinterpret_cast<uint64_t*>(s_red + 32);
+  const int tid = threadIdx.x, nthreads = blockDim.x, warp = tid >> 5, lane = tid & 31;
+  const float mul = p.cfg.entropy_cost_adjustment_speed;
+  const float ec = expf(mul * __ldg(p.ecp));
+  const bool hcr = !isnan(p.cfg.clip_rho_threshold);
+  const bool hcp = !isnan(p.cfg.clip_pg_rho_threshold);
+  const float invN = 1.0f / ((float)T * (float)B);
+  const float kc = p.cfg.kl_cost;
+  const int rot = (tid >> 4) & 1;
+
   if (tid == 0) {
-    __threadfence();
-    const unsigned int prev = atomicAdd(p.ticket, 1u);
-    s_last = (prev == gridDim.x - 1);
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sm_u32(s_full + k)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  float acc6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  // deterministic: thread k sums slices k, k+256, ... then a fixed-order tree.
-  for (unsigned int g = tid; g < gridDim.x; g += kLossThreads) {
-    const volatile float* q = p.partials + (size_t)g * kLossPartials;
+
+  // warp 0: one bulk copy per time step; lanes stride t.
+  auto issue_load = [&](int k, const float* gbase, int tile) {
+    uint64_t* bar = s_full + (k % 3);
+    if (lane == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sm_u32(bar)),
+                   "r"(tile_bytes)
+                   : "memory");
+    __syncwarp();
+    float* dst = s_tiles + (size_t)(k % 3) * tile_f;
+    const float* src = gbase + (size_t)tile * BB * A;
+    for (int t = lane; t < T; t += 32)
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+              sm_u32(dst + (size_t)t * BB * A)),
+          "l"(src + (size_t)t * B * A), "r"(chunk_bytes), "r"(sm_u32(bar))
+          : "memory");
+  };
+  auto load_small = [&](int tile, SmallRegs& r) {
 #pragma unroll
-    for (int k = 0; k < 5; ++k) acc6[k] += q[k];
-    acc6[5] = fmaxf(acc6[5], q[5]);
-  }
-  float tot[6];
-#pragma unroll
-  for (int k = 0; k < 5; ++k) tot[k] = block_reduce_sum(acc6[k], s_red);
-  tot[5] = block_reduce_max(acc6[5], s_red);
-  if (tid == 0) {
-    const float policy_loss = -tot[0] * invN;
-    const float mse = tot[1] * invN;
-    const float v_loss = p.cfg.baseline_cost * 0.5f * mse;
-    const float mean_h = tot[2] * invN;
-    const float entropy_loss = -ec * mean_h;
-    const float mean_kl = tot[3] * invN;
-    const float kl_loss = kc * mean_kl;
-    float adj = 0.f, dparam = 0.f;
-    if (p.cfg.has_target_entropy) {                        // :128-132
-      adj = ec * (mean_h - p.cfg.target_entropy);
-      dparam = mul * ec * (mean_h - p.cfg.target_entropy);
+    for (int k = 0; k < kStreamRounds; ++k) {
+      const int i = tid + k * nthreads;
+      if (i < (T + 1) * BB) {
+        const int t = i / BB, c = i - t * BB;
+        const size_t g = (size_t)t * B + (size_t)tile * BB + c;
+        r.val[k] = __ldg(p.lb + g);
+        if (t < T) {
+          r.rew[k] = __ldg(p.rew + g + B);                 // env_outputs[1:], learner.py:87
+          r.done[k] = p.done[g + B];
+          r.act[k] = (int)p.act[g];                        // agent_outputs[:-1], :86
+        }
+      }
     }
-    float* L = p.loss_terms;
-    L[SEEDRL_LT_TOTAL] = policy_loss + v_loss + entropy_loss + kl_loss + adj;  // :134-135
-    L[SEEDRL_LT_POLICY] = policy_loss;
-    L[SEEDRL_LT_V] = v_loss;
-    L[SEEDRL_LT_ENTROPY] = entropy_loss;
-    L[SEEDRL_LT_KL] = kl_loss;
-    L[SEEDRL_LT_ENTROPY_ADJ] = adj;
-    L[SEEDRL_LT_V_MEAN] = tot[4] * invN;
-    L[SEEDRL_LT_V_L2_ERROR] = sqrtf(mse);
-    L[SEEDRL_LT_MEAN_ENTROPY] = mean_h;
-    L[SEEDRL_LT_ENTROPY_COST] = ec;
-    L[SEEDRL_LT_MEAN_KL] = mean_kl;
-    L[SEEDRL_LT_MAX_ACTION_ABS] = tot[5];
-    for (int k = 12; k < SEEDRL_LOSS_TERMS; ++k) L[k] = 0.f;
-    *p.d_ecp = dparam;
-    *p.ticket = 0u;   // self-reset for the next launch
+  };
+  auto store_small = [&](const SmallRegs& r) {
+#pragma unroll
+    for (int k = 0; k < kStreamRounds; ++k) {
+      const int i = tid + k * nthreads;
+      if (i < (T + 1) * BB) {
+        s_val[i] = r.val[k];
+        if (i < rows) {
+          float rw = r.rew[k];
+          if (p.cfg.max_abs_reward != 0.f)                 // :90-92
+            rw = fminf(fmaxf(rw, -p.cfg.max_abs_reward), p.cfg.max_abs_reward);
+          s_rew[i] = rw;
+          s_dis[i] = r.done[k] ? 0.f : p.cfg.discounting;  // :93
+          s_act[i] = r.act[k];
+        }
+      }
+    }
+  };
+
+  const int n_my = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  SmallRegs sm;
+  if (n_my > 0) {
+    if (warp == 0) {
+      issue_load(0, p.bl, blockIdx.x);
+      issue_load(1, p.ll, blockIdx.x);
+    }
+    load_small(blockIdx.x, sm);
+    store_small(sm);
   }
+  __syncthreads();
+
+  float sum_tp = 0.f, sum_ve2 = 0.f, sum_h = 0.f, sum_kl = 0.f, sum_v = 0.f, max_a = 0.f;
+  for (int it = 0; it < n_my; ++it) {
+    const int tile = blockIdx.x + it * gridDim.x;
+    const int next = tile + gridDim.x;
+    const bool has_next = it + 1 < n_my;
+    const int k0 = 2 * it;
+    if (warp == 0) {
+      // the dlogits store of the previous tile has finished reading its buffer
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+      if (has_next) issue_load(k0 + 2, p.bl, next);
+    }
+    if (has_next) load_small(next, sm);
+
+    // ---- phase A: behaviour logits ----------------------------------------------------
+    mbar_wait_or_trap(s_full + (k0 % 3), (uint32_t)((k0 / 3) & 1));
+    {
+      const float* tileA = s_tiles + (size_t)(k0 % 3) * tile_f;
+      for (int i = tid; i < rows; i += nthreads) {
+        const float* l = tileA + (size_t)i * A;
+        float m = -INFINITY;
+        for (int jj = 0, j = rot < A ? rot : 0; jj < A; ++jj, j = (j + 1 == A ? 0 : j + 1)) m = fmaxf(m, l[j]);
+        float se = 0.f;
+        for (int jj = 0, j = rot < A ? rot : 0; jj < A; ++jj, j = (j + 1 == A ? 0 : j + 1)) se += expf(l[j] - m);
+        int a = s_act[i];
+        a = a < 0 ? 0 : (a >= A ? A - 1 : a);
+        s_acc[i] = l[a] - (m + logf(se));                  // :97-98
+      }
+    }
+    __syncthreads();
+    if (warp == 0 && has_next) issue_load(k0 + 3, p.ll, next);   // into the buffer just freed
+
+    // ---- phase B: learner logits, importance weights ----------------------------------
+    mbar_wait_or_trap(s_full + ((k0 + 1) % 3), (uint32_t)(((k0 + 1) / 3) & 1));
+    float* tileB = s_tiles + (size_t)((k0 + 1) % 3) * tile_f;
+    for (int i = tid; i < rows; i += nthreads) {
+      const float* l = tileB + (size_t)i * A;
+      float m = -INFINITY;
+      for (int jj = 0, j = rot < A ? rot : 0; jj < A; ++jj, j = (j + 1 == A ? 0 : j + 1)) m = fmaxf(m, l[j]);
+      float se = 0.f, sel = 0.f;
+      for (int jj = 0, j = rot < A ? rot : 0; jj < A; ++jj, j = (j + 1 == A ? 0 : j + 1)) {
+        const float d = l[j] - m;
+        const float e = expf(d);
+        se += e;
+        sel = fmaf(e, d, sel);
+      }
+      const float lg = logf(se);
+      int a = s_act[i];
+      a = a < 0 ? 0 : (a >= A ? A - 1 : a);
+      const float tl = l[a] - (m + lg);                    // :95-96
+      const float bp = s_acc[i];
+      const float ent = lg - sel / se;                     // :119-120
+      s_lse[i] = m + lg;
+      s_tlp[i] = tl;
+      s_ent[i] = ent;
+      sum_h += ent;
+      sum_kl += bp - tl;                                   // :124
+      const float rho = expf(tl - bp);                     // vtrace.py:84,110
+      const float crho = hcr ? fminf(p.cfg.clip_rho_threshold, rho) : rho;
+      const float cc = fminf(1.0f, rho) * p.cfg.lambda_;
+      const float v = s_val[i], v_next = s_val[i + BB], d = s_dis[i];
+      s_acc[i] = crho * (s_rew[i] + d * v_next - v);       // delta_t, vtrace.py:122
+      s_dc[i] = d * cc;
+      s_cpg[i] = hcp ? fminf(p.cfg.clip_pg_rho_threshold, rho) : rho;
+      sum_v += v;
+      max_a = fmaxf(max_a, fabsf((float)s_act[i]));
+    }
+    __syncthreads();
+
+    // ---- scan: acc_t = delta_t + d_t c_t acc_{t+1} (vtrace.py:128), in place -------------
+    if (tid < BB) {
+      float acc = 0.f;
+      int t = T - 1;
+      for (; t >= 3; t -= 4) {
+        const int i = t * BB + tid;
+        const float e0 = s_acc[i], e1 = s_acc[i - BB], e2 = s_acc[i - 2 * BB], e3 = s_acc[i - 3 * BB];
+        const float c0 = s_dc[i], c1 = s_dc[i - BB], c2 = s_dc[i - 2 * BB], c3 = s_dc[i - 3 * BB];
+        acc = e0 + c0 * acc; s_acc[i] = acc;
+        acc = e1 + c1 * acc; s_acc[i - BB] = acc;
+        acc = e2 + c2 * acc; s_acc[i - 2 * BB] = acc;
+        acc = e3 + c3 * acc; s_acc[i - 3 * BB] = acc;
+      }
+      for (; t >= 0; --t) {
+        const int i = t * BB + tid;
+        acc = s_acc[i] + s_dc[i] * acc;
+        s_acc[i] = acc;
+      }
+    }
+    __syncthreads();
+
+    // ---- phase D: advantages, loss sums, gradient in place -------------------------------
+    for (int i = tid; i < rows; i += nthreads) {
+      const int t = i / BB, c = i - t * BB;
+      const float v = s_val[i], verr = s_acc[i];           // vs_t - V_t, :115
+      const float vs_next = t + 1 < T ? s_acc[i + BB] + s_val[i + BB] : s_val[T * BB + c];
+      const float pg = s_cpg[i] * (s_rew[i] + s_dis[i] * vs_next - v);   // vtrace.py:143-144
+      const float tl = s_tlp[i];
+      sum_tp += tl * pg;                                   // :111-112
+      sum_ve2 += verr * verr;                              // :116
+      const size_t g = (size_t)t * B + (size_t)tile * BB + c;
+      if (p.vs_out) p.vs_out[g] = verr + v;
+      if (p.pg_out) p.pg_out[g] = pg;
+      p.dbaseline[g] = -p.cfg.baseline_cost * verr * invN;
+      float* l = tileB + (size_t)i * A;
+      const float lse = s_lse[i], ent = s_ent[i];
+      const float wpg = -(pg + kc) * invN, wec = ec * invN;
+      int a = s_act[i];
+      a = a < 0 ? 0 : (a >= A ? A - 1 : a);
+      for (int jj = 0, j = rot < A ? rot : 0; jj < A; ++jj, j = (j + 1 == A ? 0 : j + 1)) {
+        const float logp = l[j] - lse;
+        const float pj = expf(logp);
+        l[j] = wpg * ((j == a ? 1.f : 0.f) - pj) + wec * pj * (logp + ent);
+      }
+    }
+    // generic-proxy writes of the gradient tile -> visible to the bulk-copy (async) proxy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) {
+      float* dst = p.dlogits + (size_t)tile * BB * A;
+      for (int t = lane; t < T; t += 32)
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
+                         dst + (size_t)t * B * A),
+                     "r"(sm_u32(tileB + (size_t)t * BB * A)), "r"(chunk_bytes)
+                     : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    } else {
+      // bootstrap step: zero gradient
+      float* dz = p.dlogits + ((size_t)T * B + (size_t)tile * BB) * A;
+      for (int e = tid - 32; e < BB * A; e += nthreads - 32) dz[e] = 0.f;
+      for (int c = tid - 32; c < BB; c += nthreads - 32) p.dbaseline[(size_t)T * B + (size_t)tile * BB + c] = 0.f;
+    }
+    if (has_next) store_small(sm);   // every read of the per-row arrays is behind the barrier above
+    __syncthreads();
+  }
+  if (warp == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+
+  // ---- per-CTA partials, then last-CTA finalisation (same as vtrace_loss_kernel) ---------
+  float r;
+  float* part = p.partials + (size_t)blockIdx.x * kLossPartials;
+  r = block_reduce_sum(sum_tp, s_red);  if (tid == 0) part[0] = r;
+  r = block_reduce_sum(sum_ve2, s_red); if (tid == 0) part[1] = r;
+  r = block_reduce_sum(sum_h, s_red);   if (tid == 0) part[2] = r;
+  r = block_reduce_sum(sum_kl, s_red);  if (tid == 0) part[3] = r;
+  r = block_reduce_sum(sum_v, s_red);   if (tid == 0) part[4] = r;
+  r = block_reduce_max(max_a, s_red);   if (tid == 0) part[5] = r;
+  loss_finalize(p, s_red, ec, invN);
 }
 
 static int pick_bb(int T, int A, size_t* smem_bytes) {
