@@ -293,6 +293,9 @@ int seedrl_debug_conv3x3(int cin, int cout, int in_mode, int N, int H, int W,
 int seedrl_debug_conv3x3_flip(int cin, int cout, const float* w, float* wt,
                               seedrl_stream_t stream);
 size_t seedrl_debug_wgrad_partial_bytes(void);
+/* 0: every shape takes vtrace_loss_kernel; 1 (default): large aligned batches take the
+ * TMA-streamed vtrace_loss_stream_kernel.  Lets the tests run both on the same inputs. */
+int seedrl_debug_set_loss_stream(int enabled);
 int seedrl_debug_conv3x3_wgrad(int cin, int cout, int in_mode, int N, int H, int W,
                                const void* x, const float* dy, float* dw, float* db,
                                float* partial, size_t partial_bytes,

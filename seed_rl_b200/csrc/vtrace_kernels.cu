@@ -9,6 +9,7 @@
 // coalesced loads across B, the T-scan sequential in registers per column,
 // logits tiles staged through shared memory so that HBM sees only full-line
 // coalesced traffic in both directions.
+#include <cuda.h>
 #include <math.h>
 
 #include <type_traits>
@@ -212,6 +213,138 @@ __device__ __forceinline__ float block_reduce_max(float v, float* red) {
 }
 
 
+// ---- thread-per-row softmax pieces over a row of A logits in shared memory -----------------
+// Rows are dense (stride A floats).  Even A: rows are 8-byte aligned and read with 64-bit
+// loads, which a half-warp serves conflict-free for A/2 odd (A = 18: word index 9r + k);
+// odd A: the row stride is odd, 32-bit loads are conflict-free.  AS > 0 is a compile-time
+// number of actions (loops fully unrolled), AS == 0 takes it at run time.  Four independent
+// accumulators keep four loads / MUFU ops in flight per thread.  exp() is one FFMA/FMUL into
+// ex2.approx.ftz (<= 2 ulp plus 6e-8 |x| relative): the only terms it perturbs visibly are
+// the already-negligible ones; log() stays the accurate logf (two per row).
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float ex2_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int AS, typename F4, typename F1>
+__device__ __forceinline__ void row_foreach(const float* l, int A_rt, F4 f4, F1 f1) {
+  const int A = AS ? AS : A_rt;
+  int j = 0;
+  if ((A & 1) == 0) {
+    const float2* l2 = reinterpret_cast<const float2*>(l);
+    if (AS > 0) {
+#pragma unroll
+      for (int jj = 0; jj + 3 < AS; jj += 4) {
+        const float2 a = l2[jj >> 1], b = l2[(jj >> 1) + 1];
+        f4(jj, a.x, a.y, b.x, b.y);
+      }
+      j = AS & ~3;
+    } else {
+#pragma unroll 1
+      for (; j + 3 < A; j += 4) {
+        const float2 a = l2[j >> 1], b = l2[(j >> 1) + 1];
+        f4(j, a.x, a.y, b.x, b.y);
+      }
+    }
+    if (j < A) {
+      const float2 a = l2[j >> 1];
+      f1(j, a.x);
+      f1(j + 1, a.y);
+    }
+  } else {
+    if (AS > 0) {
+#pragma unroll
+      for (int jj = 0; jj + 3 < AS; jj += 4) f4(jj, l[jj], l[jj + 1], l[jj + 2], l[jj + 3]);
+      j = AS & ~3;
+    } else {
+#pragma unroll 1
+      for (; j + 3 < A; j += 4) f4(j, l[j], l[j + 1], l[j + 2], l[j + 3]);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      if (j + k < A) f1(j + k, l[j + k]);
+  }
+}
+
+template <int AS>
+__device__ __forceinline__ float row_max(const float* l, int A) {
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+  row_foreach<AS>(l, A,
+      [&](int, float x0, float x1, float x2, float x3) {
+        m0 = fmaxf(m0, x0); m1 = fmaxf(m1, x1); m2 = fmaxf(m2, x2); m3 = fmaxf(m3, x3);
+      },
+      [&](int, float x0) { m0 = fmaxf(m0, x0); });
+  return fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+}
+// sum_j exp(l_j - m)
+template <int AS>
+__device__ __forceinline__ float row_sumexp(const float* l, int A, float m) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  const float nm2 = -m * kLog2e;
+  row_foreach<AS>(l, A,
+      [&](int, float x0, float x1, float x2, float x3) {
+        s0 += ex2_ftz(fmaf(x0, kLog2e, nm2)); s1 += ex2_ftz(fmaf(x1, kLog2e, nm2));
+        s2 += ex2_ftz(fmaf(x2, kLog2e, nm2)); s3 += ex2_ftz(fmaf(x3, kLog2e, nm2));
+      },
+      [&](int, float x0) { s0 += ex2_ftz(fmaf(x0, kLog2e, nm2)); });
+  return (s0 + s1) + (s2 + s3);
+}
+// se = sum_j exp(d_j), sel = sum_j exp(d_j) d_j with d_j = l_j - m
+template <int AS>
+__device__ __forceinline__ void row_sumexp_ent(const float* l, int A, float m, float* se, float* sel) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+  auto one = [&](float x, float& s, float& q) {
+    const float d = x - m, e = ex2_ftz(d * kLog2e);
+    s += e;
+    q = fmaf(e, d, q);
+  };
+  row_foreach<AS>(l, A,
+      [&](int, float x0, float x1, float x2, float x3) { one(x0, s0, q0); one(x1, s1, q1); one(x2, s2, q2); one(x3, s3, q3); },
+      [&](int, float x0) { one(x0, s0, q0); });
+  *se = (s0 + s1) + (s2 + s3);
+  *sel = (q0 + q1) + (q2 + q3);
+}
+// in place: l_j <- wpg (1[j=a] - p_j) + wec p_j (log p_j + H),  p_j = exp(l_j - lse)
+//   d(-mean(tlp*pg))/dl_j = -pg/N (1[j=a]-p_j); d(kc*mean(blp-tlp)) = -kc/N (1[j=a]-p_j)
+//   d(-ec*mean(H))/dl_j  = ec/N * p_j (log p_j + H)
+// evaluated as p_j (wec (log p_j + H) - wpg), then + wpg on the taken action.
+template <int AS>
+__device__ __forceinline__ void row_grad(float* l, int A_rt, int a, float lse, float ent, float wpg, float wec) {
+  const int A = AS ? AS : A_rt;
+  auto g1 = [&](float x) {
+    const float logp = x - lse;
+    const float pj = ex2_ftz(logp * kLog2e);
+    return pj * fmaf(wec, logp + ent, -wpg);
+  };
+  int j = 0;
+  if ((A & 1) == 0) {
+    float2* l2 = reinterpret_cast<float2*>(l);
+    auto two = [&](int k) {
+      float2 u = l2[k];
+      u.x = g1(u.x); u.y = g1(u.y);
+      l2[k] = u;
+    };
+    if (AS > 0) {
+#pragma unroll
+      for (int k = 0; k < AS / 2; ++k) two(k);
+    } else {
+#pragma unroll 1
+      for (int k = 0; k < (A >> 1); ++k) two(k);
+    }
+  } else {
+    if (AS > 0) {
+#pragma unroll
+      for (int jj = 0; jj < AS; ++jj) l[jj] = g1(l[jj]);
+    } else {
+#pragma unroll 1
+      for (; j < A; ++j) l[j] = g1(l[j]);
+    }
+  }
+  l[a] += wpg;
+}
+
 // Last CTA to arrive (ticket) reduces the per-CTA partials in index order and writes the
 // loss terms; deterministic for a given grid.
 __device__ __forceinline__ void loss_finalize(const LossParams& p, float* s_red, float ec, float invN) {
@@ -344,15 +477,12 @@ vtrace_loss_kernel(const LossParams p) {
   // ---- phase A: behaviour logits ------------------------------------------
   tile_copy<true>(s_logits, p.bl + (size_t)b0 * A, T, B, A, BB, nb, tid);
   __syncthreads();
-  const int rot = (tid >> 4) & 1;   // half-warps start one column apart: conflict-free for even A
   for (int i = tid; i < rows; i += kLossThreads) {
     const int c = i % BB;
     if (c < nb) {
       const float* l = s_logits + (size_t)i * A;
-      float m = -INFINITY;
-      for (int jj = 0, j = rot < A ? rot : 0; jj < A; ++jj, j = (j + 1 == A ? 0 : j + 1)) m = fmaxf(m, l[j]);
-      float se = 0.f;
-      for (int jj = 0, j = rot < A ? rot : 0; jj < A; ++jj, j = (j + 1 == A ? 0 : j + 1)) se += expf(l[j] - m);
+      const float m = row_max<0>(l, A);
+      const float se = row_sumexp<0>(l, A, m);
       int a = s_act[i];
       a = a < 0 ? 0 : (a >= A ? A - 1 : a);
       s_blp[i] = l[a] - (m + logf(se));                    // :97-98
@@ -366,15 +496,9 @@ vtrace_loss_kernel(const LossParams p) {
     const int c = i % BB;
     if (c < nb) {
       const float* l = s_logits + (size_t)i * A;
-      float m = -INFINITY;
-      for (int jj = 0, j = rot < A ? rot : 0; jj < A; ++jj, j = (j + 1 == A ? 0 : j + 1)) m = fmaxf(m, l[j]);
-      float se = 0.f, sel = 0.f;
-      for (int jj = 0, j = rot < A ? rot : 0; jj < A; ++jj, j = (j + 1 == A ? 0 : j + 1)) {
-        const float d = l[j] - m;
-        const float e = expf(d);
-        se += e;
-        sel = fmaf(e, d, sel);
-      }
+      const float m = row_max<0>(l, A);
+      float se, sel;
+      row_sumexp_ent<0>(l, A, m, &se, &sel);
       const float lg = logf(se);
       int a = s_act[i];
       a = a < 0 ? 0 : (a >= A ? A - 1 : a);
@@ -434,13 +558,7 @@ vtrace_loss_kernel(const LossParams p) {
       const float wpg = -(s_tlp[i] + kc) * invN, wec = ec * invN;
       int a = s_act[i];
       a = a < 0 ? 0 : (a >= A ? A - 1 : a);
-      for (int jj = 0, j = rot < A ? rot : 0; jj < A; ++jj, j = (j + 1 == A ? 0 : j + 1)) {
-        const float logp = l[j] - lse;
-        const float pj = expf(logp);
-        // d(-mean(tlp*pg))/dl_j = -pg/N (1[j=a]-p_j); d(kc*mean(blp-tlp)) = -kc/N (1[j=a]-p_j)
-        // d(-ec*mean(H))/dl_j  = ec/N * p_j (log p_j + H)
-        l[j] = wpg * ((j == a ? 1.f : 0.f) - pj) + wec * pj * (logp + ent);
-      }
+      row_grad<0>(l, A, a, lse, ent, wpg, wec);
     }
   }
   __syncthreads();
@@ -473,21 +591,23 @@ vtrace_loss_kernel(const LossParams p) {
 // ---------------------------------------------------------------------------
 // (a2, streaming form)  Same math, laid out for HBM throughput at large B.
 //
-// One persistent CTA per SM walks tiles of BB columns x T steps.  The two logits tiles of
-// a tile (behaviour, learner) are fetched by the TMA engine (cp.async.bulk, one 1-D bulk
-// copy of BB*A floats per time step) into a ring of three shared-memory buffers; the
-// gradient tile is written in place and leaves through cp.async.bulk stores.  Order of
-// bulk loads is bl_0, ll_0, bl_1, ll_1, ... (load k -> buffer k % 3), so while tile i is
-// being computed both tiles of tile i+1 are in flight and the dlogits store of tile i-1
-// drains: the memory system never idles behind the math.  The small per-row inputs
-// (reward, done, action, baseline) of tile i+1 are prefetched into registers during tile i.
+// Persistent CTAs walk tiles of BB columns x T steps.  Each logits tile is ONE TMA tensor
+// copy (cp.async.bulk.tensor.2d: box = [T] x [BB*A floats] of the [T+1, B*A] matrix) into a
+// ring of three shared-memory buffers; the gradient tile is written in place and leaves
+// through one TMA tensor store.  Load order is bl_0, ll_0, bl_1, ll_1, ... (load k ->
+// buffer k % 3): both tiles of tile i+1 are requested right after phase A of tile i, so
+// they stream in behind phases B..D while the dlogits store of tile i-1 drains -- HBM never
+// idles behind the math.  The small per-row inputs (reward, done, action, baseline) of
+// tile i+1 are prefetched into registers during tile i.
 //   phase A   thread-per-row: behaviour log-prob                      (frees that buffer)
 //   phase B   thread-per-row: lse, target log-prob, entropy, rho -> (delta_t, d_t*c_t, clipped pg rho)
-//   scan      thread-per-column: acc_t = delta_t + (d_t c_t) acc_{t+1}   (one FMA per step)
+//   scan      warp-per-column: acc_t = delta_t + (d_t c_t) acc_{t+1} as a suffix scan of affine
+//             maps x -> Q + P x over lanes (each lane owns ceil(T/32) steps)
 //   phase D   thread-per-row: pg advantage, loss sums, gradient in place, dbaseline
 // Loss sums are kept per thread over all tiles of the CTA (fixed tile->CTA map =>
 // deterministic), reduced once per CTA, finalised by the last CTA in index order.
-constexpr int kStreamThreadsMax = 512;
+constexpr int kStreamThreadsMax = 1024;
+constexpr size_t kStreamSmemMax = 227 * 1024 - 2048;   // dynamic part; the kernel has ~1.2 KB static
 constexpr int kStreamRounds = 4;    // register-prefetch rounds for the per-row inputs
 
 __device__ __forceinline__ uint32_t sm_u32(const void* p) {
@@ -514,16 +634,18 @@ struct SmallRegs {
   uint8_t done[kStreamRounds];
 };
 
+template <int AS>
 __global__ void __launch_bounds__(kStreamThreadsMax)
-vtrace_loss_stream_kernel(const LossParams p, const int ntiles) {
+vtrace_loss_stream_kernel(const LossParams p, const int ntiles, const int tile_stride_f,
+                          const __grid_constant__ CUtensorMap tm_bl,
+                          const __grid_constant__ CUtensorMap tm_ll,
+                          const __grid_constant__ CUtensorMap tm_dl) {
   extern __shared__ __align__(128) float smem[];
-  const int T = p.T, B = p.B, A = p.A, BB = p.BB;
+  const int T = p.T, B = p.B, A = AS ? AS : p.A, BB = p.BB;
   const int rows = T * BB;
-  const int tile_f = rows * A;                       // floats per logits tile (multiple of 4)
-  const uint32_t chunk_bytes = (uint32_t)(BB * A) * 4u;
-  const uint32_t tile_bytes = (uint32_t)tile_f * 4u;
-  float* s_tiles = smem;                             // [3][T][BB][A]
-  float* s_tlp = s_tiles + (size_t)3 * tile_f;       // [rows] target logp
+  const uint32_t tile_bytes = (uint32_t)(rows * A) * 4u;
+  float* s_tiles = smem;                             // [3] x [T][BB][A], 128-byte aligned each
+  float* s_tlp = s_tiles + (size_t)3 * tile_stride_f;   // [rows] target logp
   float* s_acc = s_tlp + rows;                       // [rows] behaviour logp -> delta -> vs - V
   float* s_lse = s_acc + rows;
   float* s_ent = s_lse + rows;
@@ -542,32 +664,30 @@ vtrace_loss_stream_kernel(const LossParams p, const int ntiles) {
   const bool hcp = !isnan(p.cfg.clip_pg_rho_threshold);
   const float invN = 1.0f / ((float)T * (float)B);
   const float kc = p.cfg.kl_cost;
-  const int rot = (tid >> 4) & 1;
 
   if (tid == 0) {
 #pragma unroll
     for (int k = 0; k < 3; ++k)
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sm_u32(s_full + k)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_bl)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_ll)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_dl)) : "memory");
   }
   __syncthreads();
 
-  // warp 0: one bulk copy per time step; lanes stride t.
-  auto issue_load = [&](int k, const float* gbase, int tile) {
+  float sum_tp = 0.f, sum_ve2 = 0.f, sum_h = 0.f, sum_kl = 0.f, sum_v = 0.f, max_a = 0.f;
+  // one thread, one instruction per tile
+  auto issue_load = [&](int k, const CUtensorMap* tm, int tile) {
     uint64_t* bar = s_full + (k % 3);
-    if (lane == 0)
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sm_u32(bar)),
-                   "r"(tile_bytes)
-                   : "memory");
-    __syncwarp();
-    float* dst = s_tiles + (size_t)(k % 3) * tile_f;
-    const float* src = gbase + (size_t)tile * BB * A;
-    for (int t = lane; t < T; t += 32)
-      asm volatile(
-          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-              sm_u32(dst + (size_t)t * BB * A)),
-          "l"(src + (size_t)t * B * A), "r"(chunk_bytes), "r"(sm_u32(bar))
-          : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sm_u32(bar)),
+                 "r"(tile_bytes)
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            sm_u32(s_tiles + (size_t)(k % 3) * tile_stride_f)),
+        "l"(reinterpret_cast<uint64_t>(tm)), "r"(tile * BB * A), "r"(0), "r"(sm_u32(bar))
+        : "memory");
   };
   auto load_small = [&](int tile, SmallRegs& r) {
 #pragma unroll
@@ -597,7 +717,9 @@ vtrace_loss_stream_kernel(const LossParams p, const int ntiles) {
             rw = fminf(fmaxf(rw, -p.cfg.max_abs_reward), p.cfg.max_abs_reward);
           s_rew[i] = rw;
           s_dis[i] = r.done[k] ? 0.f : p.cfg.discounting;  // :93
-          s_act[i] = r.act[k];
+          const int a = r.act[k];
+          max_a = fmaxf(max_a, fabsf((float)a));
+          s_act[i] = a < 0 ? 0 : (a >= A ? A - 1 : a);
         }
       }
     }
@@ -606,64 +728,52 @@ vtrace_loss_stream_kernel(const LossParams p, const int ntiles) {
   const int n_my = (ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   SmallRegs sm;
   if (n_my > 0) {
-    if (warp == 0) {
-      issue_load(0, p.bl, blockIdx.x);
-      issue_load(1, p.ll, blockIdx.x);
+    if (tid == 0) {
+      issue_load(0, &tm_bl, blockIdx.x);
+      issue_load(1, &tm_ll, blockIdx.x);
     }
     load_small(blockIdx.x, sm);
     store_small(sm);
   }
   __syncthreads();
 
-  float sum_tp = 0.f, sum_ve2 = 0.f, sum_h = 0.f, sum_kl = 0.f, sum_v = 0.f, max_a = 0.f;
   for (int it = 0; it < n_my; ++it) {
     const int tile = blockIdx.x + it * gridDim.x;
     const int next = tile + gridDim.x;
     const bool has_next = it + 1 < n_my;
     const int k0 = 2 * it;
-    if (warp == 0) {
-      // the dlogits store of the previous tile has finished reading its buffer
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      __syncwarp();
-      if (has_next) issue_load(k0 + 2, p.bl, next);
-    }
     if (has_next) load_small(next, sm);
 
     // ---- phase A: behaviour logits ----------------------------------------------------
     mbar_wait_or_trap(s_full + (k0 % 3), (uint32_t)((k0 / 3) & 1));
     {
-      const float* tileA = s_tiles + (size_t)(k0 % 3) * tile_f;
+      const float* tileA = s_tiles + (size_t)(k0 % 3) * tile_stride_f;
       for (int i = tid; i < rows; i += nthreads) {
         const float* l = tileA + (size_t)i * A;
-        float m = -INFINITY;
-        for (int jj = 0, j = rot < A ? rot : 0; jj < A; ++jj, j = (j + 1 == A ? 0 : j + 1)) m = fmaxf(m, l[j]);
-        float se = 0.f;
-        for (int jj = 0, j = rot < A ? rot : 0; jj < A; ++jj, j = (j + 1 == A ? 0 : j + 1)) se += expf(l[j] - m);
-        int a = s_act[i];
-        a = a < 0 ? 0 : (a >= A ? A - 1 : a);
-        s_acc[i] = l[a] - (m + logf(se));                  // :97-98
+        const float m = row_max<AS>(l, A);
+        const float se = row_sumexp<AS>(l, A, m);
+        s_acc[i] = l[s_act[i]] - (m + logf(se));           // :97-98
       }
     }
     __syncthreads();
-    if (warp == 0 && has_next) issue_load(k0 + 3, p.ll, next);   // into the buffer just freed
+    if (tid == 0 && has_next) {
+      // buffer (k0+2)%3 held the gradient tile of the previous iteration: its store has had
+      // all of phase A to finish reading shared memory
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      issue_load(k0 + 2, &tm_bl, next);
+      issue_load(k0 + 3, &tm_ll, next);                    // into the buffer phase A just freed
+    }
 
     // ---- phase B: learner logits, importance weights ----------------------------------
     mbar_wait_or_trap(s_full + ((k0 + 1) % 3), (uint32_t)(((k0 + 1) / 3) & 1));
-    float* tileB = s_tiles + (size_t)((k0 + 1) % 3) * tile_f;
+    float* tileB = s_tiles + (size_t)((k0 + 1) % 3) * tile_stride_f;
     for (int i = tid; i < rows; i += nthreads) {
       const float* l = tileB + (size_t)i * A;
-      float m = -INFINITY;
-      for (int jj = 0, j = rot < A ? rot : 0; jj < A; ++jj, j = (j + 1 == A ? 0 : j + 1)) m = fmaxf(m, l[j]);
-      float se = 0.f, sel = 0.f;
-      for (int jj = 0, j = rot < A ? rot : 0; jj < A; ++jj, j = (j + 1 == A ? 0 : j + 1)) {
-        const float d = l[j] - m;
-        const float e = expf(d);
-        se += e;
-        sel = fmaf(e, d, sel);
-      }
+      const float m = row_max<AS>(l, A);
+      float se, sel;
+      row_sumexp_ent<AS>(l, A, m, &se, &sel);
       const float lg = logf(se);
-      int a = s_act[i];
-      a = a < 0 ? 0 : (a >= A ? A - 1 : a);
+      const int a = s_act[i];
       const float tl = l[a] - (m + lg);                    // :95-96
       const float bp = s_acc[i];
       const float ent = lg - sel / se;                     // :119-120
@@ -680,27 +790,36 @@ vtrace_loss_stream_kernel(const LossParams p, const int ntiles) {
       s_dc[i] = d * cc;
       s_cpg[i] = hcp ? fminf(p.cfg.clip_pg_rho_threshold, rho) : rho;
       sum_v += v;
-      max_a = fmaxf(max_a, fabsf((float)s_act[i]));
     }
     __syncthreads();
 
     // ---- scan: acc_t = delta_t + d_t c_t acc_{t+1} (vtrace.py:128), in place -------------
-    if (tid < BB) {
-      float acc = 0.f;
-      int t = T - 1;
-      for (; t >= 3; t -= 4) {
-        const int i = t * BB + tid;
-        const float e0 = s_acc[i], e1 = s_acc[i - BB], e2 = s_acc[i - 2 * BB], e3 = s_acc[i - 3 * BB];
-        const float c0 = s_dc[i], c1 = s_dc[i - BB], c2 = s_dc[i - 2 * BB], c3 = s_dc[i - 3 * BB];
-        acc = e0 + c0 * acc; s_acc[i] = acc;
-        acc = e1 + c1 * acc; s_acc[i - BB] = acc;
-        acc = e2 + c2 * acc; s_acc[i - 2 * BB] = acc;
-        acc = e3 + c3 * acc; s_acc[i - 3 * BB] = acc;
-      }
-      for (; t >= 0; --t) {
-        const int i = t * BB + tid;
-        acc = s_acc[i] + s_dc[i] * acc;
-        s_acc[i] = acc;
+    // lane l owns steps [l K, (l+1) K): its K steps compose to x -> Q + P x; a suffix scan over
+    // lanes gives every lane the accumulator entering its segment.
+    {
+      const int K = (T + 31) >> 5;
+      const int t_lo = lane * K, t_hi = min(t_lo + K, T);
+      for (int c = warp; c < BB; c += nthreads >> 5) {
+        float P = 1.f, Q = 0.f;
+        for (int t = t_hi - 1; t >= t_lo; --t) {
+          const float cf = s_dc[t * BB + c];
+          Q = fmaf(cf, Q, s_acc[t * BB + c]);
+          P *= cf;
+        }
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const float Pd = __shfl_down_sync(0xffffffffu, P, d), Qd = __shfl_down_sync(0xffffffffu, Q, d);
+          if (lane + d < 32) {
+            Q = fmaf(P, Qd, Q);
+            P *= Pd;
+          }
+        }
+        float acc = __shfl_down_sync(0xffffffffu, Q, 1);
+        if (lane == 31) acc = 0.f;
+        for (int t = t_hi - 1; t >= t_lo; --t) {
+          acc = fmaf(s_dc[t * BB + c], acc, s_acc[t * BB + c]);
+          s_acc[t * BB + c] = acc;
+        }
       }
     }
     __syncthreads();
@@ -718,38 +837,27 @@ vtrace_loss_stream_kernel(const LossParams p, const int ntiles) {
       if (p.vs_out) p.vs_out[g] = verr + v;
       if (p.pg_out) p.pg_out[g] = pg;
       p.dbaseline[g] = -p.cfg.baseline_cost * verr * invN;
-      float* l = tileB + (size_t)i * A;
-      const float lse = s_lse[i], ent = s_ent[i];
-      const float wpg = -(pg + kc) * invN, wec = ec * invN;
-      int a = s_act[i];
-      a = a < 0 ? 0 : (a >= A ? A - 1 : a);
-      for (int jj = 0, j = rot < A ? rot : 0; jj < A; ++jj, j = (j + 1 == A ? 0 : j + 1)) {
-        const float logp = l[j] - lse;
-        const float pj = expf(logp);
-        l[j] = wpg * ((j == a ? 1.f : 0.f) - pj) + wec * pj * (logp + ent);
-      }
+      row_grad<AS>(tileB + (size_t)i * A, A, s_act[i], s_lse[i], s_ent[i], -(pg + kc) * invN, ec * invN);
     }
-    // generic-proxy writes of the gradient tile -> visible to the bulk-copy (async) proxy
+    // generic-proxy writes of the gradient tile -> visible to the TMA (async) proxy
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
-    if (warp == 0) {
-      float* dst = p.dlogits + (size_t)tile * BB * A;
-      for (int t = lane; t < T; t += 32)
-        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
-                         dst + (size_t)t * B * A),
-                     "r"(sm_u32(tileB + (size_t)t * BB * A)), "r"(chunk_bytes)
-                     : "memory");
+    if (tid == 0) {
+      asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                       reinterpret_cast<uint64_t>(&tm_dl)),
+                   "r"(tile * BB * A), "r"(0), "r"(sm_u32(tileB))
+                   : "memory");
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    } else {
-      // bootstrap step: zero gradient
+    }
+    {  // bootstrap step: zero gradient
       float* dz = p.dlogits + ((size_t)T * B + (size_t)tile * BB) * A;
-      for (int e = tid - 32; e < BB * A; e += nthreads - 32) dz[e] = 0.f;
-      for (int c = tid - 32; c < BB; c += nthreads - 32) p.dbaseline[(size_t)T * B + (size_t)tile * BB + c] = 0.f;
+      for (int e = tid; e < BB * A; e += nthreads) dz[e] = 0.f;
+      if (tid < BB) p.dbaseline[(size_t)T * B + (size_t)tile * BB + tid] = 0.f;
     }
     if (has_next) store_small(sm);   // every read of the per-row arrays is behind the barrier above
     __syncthreads();
   }
-  if (warp == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 
   // ---- per-CTA partials, then last-CTA finalisation (same as vtrace_loss_kernel) ---------
   float r;
@@ -763,21 +871,131 @@ vtrace_loss_stream_kernel(const LossParams p, const int ntiles) {
   loss_finalize(p, s_red, ec, invN);
 }
 
-static int pick_bb(int T, int A, size_t* smem_bytes) {
-  for (int BB = 16; BB >= 1; BB >>= 1) {
-    const size_t rows = (size_t)T * BB;
-    const size_t bytes = (((rows * A + 3) & ~(size_t)3) + rows * 6 + (size_t)(T + 1) * BB + rows + 32) * 4;
-    if (bytes <= 200 * 1024) {
-      *smem_bytes = bytes;
-      return BB;
-    }
+static size_t loss_smem_bytes(int T, int A, int BB) {
+  const size_t rows = (size_t)T * BB;
+  return (((rows * A + 3) & ~(size_t)3) + rows * 6 + (size_t)(T + 1) * BB + rows + 32) * 4;
+}
+
+// Columns per CTA for vtrace_loss_kernel: the largest power of two <= 16 whose tile fits in
+// shared memory, then halved while the grid would leave SMs idle (small B: latency matters,
+// not bandwidth) as long as rows stay float4-copyable.
+static int pick_bb(int T, int B, int A, size_t* smem_bytes) {
+  int BB = 16;
+  while (BB >= 1 && loss_smem_bytes(T, A, BB) > 200 * 1024) BB >>= 1;
+  if (BB == 0) return 0;
+  while (BB > 1 && ceil_div(B, BB) < 148 && (((BB / 2) * A) & 3) == 0) BB >>= 1;
+  *smem_bytes = loss_smem_bytes(T, A, BB);
+  return BB;
+}
+
+static int stream_tile_stride_f(int T, int A, int BB) {   // floats per ring buffer, 128-byte multiple
+  return (T * BB * A + 31) & ~31;
+}
+static size_t stream_smem_bytes(int T, int A, int BB) {
+  const size_t rows = (size_t)T * BB;
+  return (3 * (size_t)stream_tile_stride_f(T, A, BB) + 8 * rows + (size_t)(T + 1) * BB + rows + 32) * 4 + 3 * 8 + 128;
+}
+
+static int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &qr) == cudaSuccess &&
+        qr == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(q);
+    (void)cudaGetLastError();
+  }
+  return fn;
+}
+// [T1, B*A] fp32 matrix, box = T rows x BB*A floats (one tile), dense in shared memory.
+static bool make_tile_map(CUtensorMap* tm, const float* base, int T1, int T, int B, int A, int BB) {
+  const cuuint64_t gdim[2] = {(cuuint64_t)B * A, (cuuint64_t)T1};
+  const cuuint64_t gstr[1] = {(cuuint64_t)B * A * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)(BB * A), (cuuint32_t)T};
+  const cuuint32_t estr[2] = {1, 1};
+  return encode_tiled()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// The streaming kernel applies when every tile is full, the TMA box is legal (inner extent
+// BB*A <= 256 floats and a 16-byte multiple, T <= 256 rows, 16-byte aligned bases and row
+// pitch), and there is at least one tile per SM.  Returns BB (0 = use vtrace_loss_kernel).
+static int pick_stream(const LossParams& p, int* threads, size_t* smem_bytes) {
+  const int T = p.T, B = p.B, A = p.A;
+  auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (!aligned16(p.ll) || !aligned16(p.bl) || !aligned16(p.dlogits)) return 0;
+  if (T > 256 || (((size_t)B * A) & 3) != 0 || !encode_tiled()) return 0;
+  for (int BB = 16; BB >= 2; BB >>= 1) {
+    if (B % BB != 0 || ((BB * A) & 3) != 0 || BB * A > 256) continue;
+    if (B / BB < num_sms()) continue;
+    const size_t bytes = stream_smem_bytes(T, A, BB);
+    if (bytes > kStreamSmemMax) continue;
+    const int rows = T * BB;
+    const int rounds = ceil_div(rows, kStreamThreadsMax);
+    int th = ceil_div(ceil_div(rows, rounds), 32) * 32;
+    if (th < 128) th = 128;
+    if ((T + 1) * BB > kStreamRounds * th) continue;
+    *threads = th;
+    *smem_bytes = bytes;
+    return BB;
   }
   return 0;
+}
+
+template <int AS>
+static cudaError_t launch_stream(const LossParams& p, int ntiles, int threads, size_t smem, cudaStream_t stream,
+                                 const CUtensorMap& tm_bl, const CUtensorMap& tm_ll, const CUtensorMap& tm_dl) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(vtrace_loss_stream_kernel<AS>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStreamSmemMax);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  // persistent CTAs: as many per SM as shared memory and threads allow (small T: several,
+  // so one CTA's barriers and scan hide behind another's copies)
+  int per_sm = (int)((size_t)(228 * 1024) / (smem + 2048 + 1024));   // 228 KB/SM, 1 KB/CTA reserved
+  if (per_sm > 2048 / threads) per_sm = 2048 / threads;
+  if (per_sm > 6) per_sm = 6;
+  if (per_sm < 1) per_sm = 1;
+  int grid = num_sms() * per_sm;
+  if (grid > ntiles) grid = ntiles;
+  vtrace_loss_stream_kernel<AS><<<grid, threads, smem, stream>>>(
+      p, ntiles, stream_tile_stride_f(p.T, p.A, p.BB), tm_bl, tm_ll, tm_dl);
+  return cudaSuccess;
 }
 
 }  // namespace seedrl
 
 using namespace seedrl;
+
+static int g_loss_stream_enabled = 1;
+
+// Test hook: 0 forces vtrace_loss_kernel for every shape, 1 (default) lets large aligned
+// batches take vtrace_loss_stream_kernel.
+extern "C" int seedrl_debug_set_loss_stream(int enabled) {
+  g_loss_stream_enabled = enabled ? 1 : 0;
+  return SEEDRL_OK;
+}
 
 extern "C" int seedrl_vtrace_from_importance_weights(
     int T, int B, const float* tlp, const float* blp, const float* disc, const float* rew,
@@ -835,10 +1053,8 @@ extern "C" int seedrl_categorical_sample(int N, int A, const float* logits,
 }
 
 extern "C" size_t seedrl_vtrace_loss_scratch_bytes(int T1, int B, int A) {
-  size_t smem;
-  const int BB = pick_bb(T1 > 1 ? T1 - 1 : 1, A, &smem);
-  const size_t grid = BB ? (size_t)ceil_div(B, BB) : (size_t)B;
-  return 256 + grid * kLossPartials * sizeof(float);
+  (void)T1; (void)A;   // one partial slot per CTA; at most one CTA per column
+  return 256 + (size_t)(B > 148 ? B : 148) * kLossPartials * sizeof(float);
 }
 
 extern "C" int seedrl_vtrace_loss_fwd_bwd(
@@ -855,8 +1071,6 @@ extern "C" int seedrl_vtrace_loss_fwd_bwd(
   LossParams p;
   p.T = T1 - 1; p.B = B; p.A = A;
   size_t smem = 0;
-  p.BB = pick_bb(p.T, A, &smem);
-  SEEDRL_CHECK_ARG(p.BB > 0, "unroll_length * num_actions too large for shared memory");
   p.AP = A | 1;
   p.ll = learner_logits; p.lb = learner_baseline; p.bl = behaviour_logits;
   p.act = actions; p.rew = rewards; p.done = done; p.cfg = *cfg; p.ecp = entropy_cost_param;
@@ -870,7 +1084,27 @@ extern "C" int seedrl_vtrace_loss_fwd_bwd(
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  vtrace_loss_kernel<<<ceil_div(B, p.BB), kLossThreads, smem, (cudaStream_t)stream>>>(p);
+  int threads = 0;
+  p.BB = g_loss_stream_enabled ? pick_stream(p, &threads, &smem) : 0;
+  alignas(64) CUtensorMap tm_bl, tm_ll, tm_dl;
+  if (p.BB > 0 && !(make_tile_map(&tm_bl, p.bl, T1, p.T, B, A, p.BB) &&
+                    make_tile_map(&tm_ll, p.ll, T1, p.T, B, A, p.BB) &&
+                    make_tile_map(&tm_dl, p.dlogits, T1, p.T, B, A, p.BB)))
+    p.BB = 0;
+  if (p.BB > 0) {
+    const int ntiles = B / p.BB;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (A) {   // compile-time action counts of the reference's environments
+      case 9:  SEEDRL_CUDA(launch_stream<9>(p, ntiles, threads, smem, st, tm_bl, tm_ll, tm_dl)); break;    // DMLab
+      case 18: SEEDRL_CUDA(launch_stream<18>(p, ntiles, threads, smem, st, tm_bl, tm_ll, tm_dl)); break;   // Atari
+      case 19: SEEDRL_CUDA(launch_stream<19>(p, ntiles, threads, smem, st, tm_bl, tm_ll, tm_dl)); break;   // football
+      default: SEEDRL_CUDA(launch_stream<0>(p, ntiles, threads, smem, st, tm_bl, tm_ll, tm_dl)); break;
+    }
+  } else {
+    p.BB = pick_bb(p.T, B, A, &smem);
+    SEEDRL_CHECK_ARG(p.BB > 0, "unroll_length * num_actions too large for shared memory");
+    vtrace_loss_kernel<<<ceil_div(B, p.BB), kLossThreads, smem, (cudaStream_t)stream>>>(p);
+  }
   count_launch(PC_LOSS, (cudaStream_t)stream);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;

@@ -195,6 +195,55 @@ def test_vtrace_loss_fwd_bwd_vs_oracle(T1, B, A, kw):
   assert float(r['dlogits'][-1].abs().max()) == 0.0 and float(r['dbaseline'][-1].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize('T1,B,A,kw', [
+    (6, 2368, 18, {}),                      # BB=8 (TMA box <= 256 floats), 296 tiles
+    (21, 2368, 9, {}), (5, 1184, 19, dict(kl_cost=0.2)),   # DMLab / football action counts
+    (21, 3552, 18, dict(kl_cost=0.3, entropy_cost=0.01, max_abs_reward=1.0, target_entropy=1.5, lambda_=0.9)),
+    (101, 4736, 18, {}),                    # BB=8, 592 tiles: four per CTA, ring wraps
+    (11, 1184, 6, dict(kl_cost=0.1)),       # BB=8
+    (9, 2960, 15, {}),                      # BB=16, 185 tiles, run-time A
+    (3, 592, 2, {})])                       # BB=4, T=2
+def test_vtrace_loss_streaming_kernel_vs_oracle(T1, B, A, kw):
+  """Large aligned batches take vtrace_loss_stream_kernel (TMA bulk-copy ring, persistent
+  CTAs): same parity bar against the oracle as vtrace_loss_kernel, the two kernels agree
+  with each other to fp32 summation-order noise, and the result is deterministic."""
+  from seed_rl_b200 import _lib
+  from seed_rl_b200.agents.vtrace import learner
+  c, _ = _loss_case(T1, B, A, 13)
+  cfg = loss_oracle.default_config(**kw)
+  total, logs, dl, db, dep, aux = loss_oracle.loss_and_grads(cfg, c['ll'], c['lb'], c['bl'], c['act'], c['rew'], c['done'])
+  st = learner.default_loss_settings(**kw)
+  ecp = torch.tensor(np.log(cfg.entropy_cost) / cfg.entropy_cost_adjustment_speed, dtype=torch.float32).cuda()
+  args = [_cuda(c[k]) for k in ('ll', 'lb', 'bl', 'act', 'rew', 'done')]
+  res = {}
+  try:
+    for stream in (0, 1, 1):
+      _lib.check(_lib.lib().seedrl_debug_set_loss_stream(stream))
+      r = learner.vtrace_loss_fwd_bwd(st, *args, ecp, want_vtrace=True)
+      torch.cuda.synchronize()
+      res.setdefault(stream, []).append({k: v.clone() for k, v in r.items() if torch.is_tensor(v)})
+  finally:
+    _lib.check(_lib.lib().seedrl_debug_set_loss_stream(1))
+  r, r_again, old = res[1][0], res[1][1], res[0][0]
+  lt = r['loss_terms'].cpu().numpy()
+  for k, key in {'losses/total': 'total', 'losses/policy': 'policy', 'losses/V': 'V', 'losses/entropy': 'entropy',
+                 'losses/kl': 'kl', 'V/value function': 'v_mean', 'V/L2 error': 'v_l2_error',
+                 'policy/entropy': 'mean_entropy', 'policy/kl(old|new)': 'mean_kl',
+                 'policy/max_action_abs(before_tanh)': 'max_action_abs'}.items():
+    np.testing.assert_allclose(lt[_lib.LT[key]], logs[k], rtol=3e-5, atol=3e-6, err_msg=k)
+  np.testing.assert_allclose(r['vs'].cpu().numpy(), aux['vs'].numpy(), rtol=1e-5, atol=1e-5)
+  np.testing.assert_allclose(r['pg_advantages'].cpu().numpy(), aux['pg_advantages'].numpy(), rtol=1e-5, atol=1e-5)
+  np.testing.assert_allclose(r['dlogits'].cpu().numpy(), dl, rtol=1e-4, atol=1e-9)
+  np.testing.assert_allclose(r['dbaseline'].cpu().numpy(), db, rtol=1e-4, atol=1e-9)
+  np.testing.assert_allclose(float(r['d_entropy_cost_param']), dep, rtol=1e-4, atol=1e-8)
+  assert float(r['dlogits'][-1].abs().max()) == 0.0 and float(r['dbaseline'][-1].abs().max()) == 0.0
+  for k in ('dlogits', 'dbaseline', 'vs', 'pg_advantages'):
+    np.testing.assert_allclose(r[k].cpu().numpy(), old[k].cpu().numpy(), rtol=1e-4,
+                               atol=1e-5 if k in ('vs', 'pg_advantages') else 1e-9, err_msg=k)
+    assert torch.equal(r[k], r_again[k]), k
+  assert torch.equal(r['loss_terms'], r_again['loss_terms'])
+
+
 def test_vtrace_loss_large_batch_properties():
   """B = 16384 (4096 CTAs): gradient rows sum to zero over actions (softmax Jacobian),
   loss is invariant to a per-row logit shift, partial reduction is deterministic."""
