@@ -664,6 +664,9 @@ vtrace_loss_stream_kernel(const LossParams p, const int ntiles, const int tile_s
   const bool hcp = !isnan(p.cfg.clip_pg_rho_threshold);
   const float invN = 1.0f / ((float)T * (float)B);
   const float kc = p.cfg.kl_cost;
+  const int bb_sh = 31 - __clz(BB);                      // BB is a power of two
+  int lpc = 32;                                          // lanes per column in the scan
+  while (lpc > 1 && T <= lpc * 4) lpc >>= 1;
 
   if (tid == 0) {
 #pragma unroll
@@ -694,7 +697,7 @@ vtrace_loss_stream_kernel(const LossParams p, const int ntiles, const int tile_s
     for (int k = 0; k < kStreamRounds; ++k) {
       const int i = tid + k * nthreads;
       if (i < (T + 1) * BB) {
-        const int t = i / BB, c = i - t * BB;
+        const int t = i >> bb_sh, c = i & (BB - 1);
         const size_t g = (size_t)t * B + (size_t)tile * BB + c;
         r.val[k] = __ldg(p.lb + g);
         if (t < T) {
@@ -794,39 +797,44 @@ vtrace_loss_stream_kernel(const LossParams p, const int ntiles, const int tile_s
     __syncthreads();
 
     // ---- scan: acc_t = delta_t + d_t c_t acc_{t+1} (vtrace.py:128), in place -------------
-    // lane l owns steps [l K, (l+1) K): its K steps compose to x -> Q + P x; a suffix scan over
-    // lanes gives every lane the accumulator entering its segment.
+    // LPC lanes share a column (32 / LPC columns per warp); a lane owns K = ceil(T / LPC)
+    // consecutive steps, which compose to the affine map x -> Q + P x; a suffix scan of those
+    // maps over the column's lanes gives every lane the accumulator entering its segment.
     {
-      const int K = (T + 31) >> 5;
-      const int t_lo = lane * K, t_hi = min(t_lo + K, T);
-      for (int c = warp; c < BB; c += nthreads >> 5) {
+      const int sub = lane & (lpc - 1);                    // lane within its column group
+      const int K = (T + lpc - 1) / lpc;
+      const int t_lo = sub * K, t_hi = min(t_lo + K, T);
+      const int cols_per_warp = 32 / lpc;
+      for (int c = warp * cols_per_warp + lane / lpc; c - lane / lpc < BB; c += (nthreads >> 5) * cols_per_warp) {
+        const bool live = c < BB;
         float P = 1.f, Q = 0.f;
-        for (int t = t_hi - 1; t >= t_lo; --t) {
-          const float cf = s_dc[t * BB + c];
-          Q = fmaf(cf, Q, s_acc[t * BB + c]);
-          P *= cf;
-        }
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
+        if (live)
+          for (int t = t_hi - 1; t >= t_lo; --t) {
+            const float cf = s_dc[t * BB + c];
+            Q = fmaf(cf, Q, s_acc[t * BB + c]);
+            P *= cf;
+          }
+        for (int d = 1; d < lpc; d <<= 1) {
           const float Pd = __shfl_down_sync(0xffffffffu, P, d), Qd = __shfl_down_sync(0xffffffffu, Q, d);
-          if (lane + d < 32) {
+          if (sub + d < lpc) {
             Q = fmaf(P, Qd, Q);
             P *= Pd;
           }
         }
         float acc = __shfl_down_sync(0xffffffffu, Q, 1);
-        if (lane == 31) acc = 0.f;
-        for (int t = t_hi - 1; t >= t_lo; --t) {
-          acc = fmaf(s_dc[t * BB + c], acc, s_acc[t * BB + c]);
-          s_acc[t * BB + c] = acc;
-        }
+        if (sub == lpc - 1) acc = 0.f;
+        if (live)
+          for (int t = t_hi - 1; t >= t_lo; --t) {
+            acc = fmaf(s_dc[t * BB + c], acc, s_acc[t * BB + c]);
+            s_acc[t * BB + c] = acc;
+          }
       }
     }
     __syncthreads();
 
     // ---- phase D: advantages, loss sums, gradient in place -------------------------------
     for (int i = tid; i < rows; i += nthreads) {
-      const int t = i / BB, c = i - t * BB;
+      const int t = i >> bb_sh, c = i & (BB - 1);
       const float v = s_val[i], verr = s_acc[i];           // vs_t - V_t, :115
       const float vs_next = t + 1 < T ? s_acc[i + BB] + s_val[i + BB] : s_val[T * BB + c];
       const float pg = s_cpg[i] * (s_rew[i] + s_dis[i] * vs_next - v);   // vtrace.py:143-144
@@ -939,16 +947,21 @@ static bool make_tile_map(CUtensorMap* tm, const float* base, int T1, int T, int
 // The streaming kernel applies when every tile is full, the TMA box is legal (inner extent
 // BB*A <= 256 floats and a 16-byte multiple, T <= 256 rows, 16-byte aligned bases and row
 // pitch), and there is at least one tile per SM.  Returns BB (0 = use vtrace_loss_kernel).
-static int pick_stream(const LossParams& p, int* threads, size_t* smem_bytes) {
+static int pick_stream(const LossParams& p, int forced_bb, int* threads, size_t* smem_bytes) {
   const int T = p.T, B = p.B, A = p.A;
   auto aligned16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   if (!aligned16(p.ll) || !aligned16(p.bl) || !aligned16(p.dlogits)) return 0;
   if (T > 256 || (((size_t)B * A) & 3) != 0 || !encode_tiled()) return 0;
+  // two passes: first the largest BB that leaves room for two CTAs per SM (one CTA's
+  // barriers and scan then hide behind the other's phases), else the largest that fits
+  for (int pass = 0; pass < 2; ++pass)
   for (int BB = 16; BB >= 2; BB >>= 1) {
+    if (forced_bb > 1 && BB != forced_bb) continue;
     if (B % BB != 0 || ((BB * A) & 3) != 0 || BB * A > 256) continue;
     if (B / BB < num_sms()) continue;
     const size_t bytes = stream_smem_bytes(T, A, BB);
     if (bytes > kStreamSmemMax) continue;
+    if (pass == 0 && forced_bb <= 1 && 2 * (bytes + 2048 + 1024) > (size_t)228 * 1024) continue;
     const int rows = T * BB;
     const int rounds = ceil_div(rows, kStreamThreadsMax);
     int th = ceil_div(ceil_div(rows, rounds), 32) * 32;
@@ -991,9 +1004,9 @@ using namespace seedrl;
 static int g_loss_stream_enabled = 1;
 
 // Test hook: 0 forces vtrace_loss_kernel for every shape, 1 (default) lets large aligned
-// batches take vtrace_loss_stream_kernel.
+// batches take vtrace_loss_stream_kernel, 2/4/8/16 additionally pins its columns per tile.
 extern "C" int seedrl_debug_set_loss_stream(int enabled) {
-  g_loss_stream_enabled = enabled ? 1 : 0;
+  g_loss_stream_enabled = enabled < 0 ? 0 : enabled;
   return SEEDRL_OK;
 }
 
@@ -1085,7 +1098,7 @@ extern "C" int seedrl_vtrace_loss_fwd_bwd(
     attr_set = true;
   }
   int threads = 0;
-  p.BB = g_loss_stream_enabled ? pick_stream(p, &threads, &smem) : 0;
+  p.BB = g_loss_stream_enabled ? pick_stream(p, g_loss_stream_enabled, &threads, &smem) : 0;
   alignas(64) CUtensorMap tm_bl, tm_ll, tm_dl;
   if (p.BB > 0 && !(make_tile_map(&tm_bl, p.bl, T1, p.T, B, A, p.BB) &&
                     make_tile_map(&tm_ll, p.ll, T1, p.T, B, A, p.BB) &&

@@ -13,7 +13,7 @@ for T1, A in ((21, 18), (101, 18)):
     act = torch.randint(0, A, (T1, Bs), device='cuda', generator=g)
     rew = torch.randn(T1, Bs, device='cuda', generator=g); dn = torch.rand(T1, Bs, device='cuda', generator=g) < 0.02
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
-    for stream in (0, 1):
+    for stream in (0, 1, 4, 8):
       _lib.lib().seedrl_debug_set_loss_stream(stream)
       for _ in range(3):
         learner.vtrace_loss_fwd_bwd(st, ll, lb, bl, act, rew, dn, ecp)
