@@ -293,6 +293,9 @@ int seedrl_debug_conv3x3(int cin, int cout, int in_mode, int N, int H, int W,
 int seedrl_debug_conv3x3_flip(int cin, int cout, const float* w, float* wt,
                               seedrl_stream_t stream);
 size_t seedrl_debug_wgrad_partial_bytes(void);
+/* Host-side: the kernels' tall-image position -> pixel map (-1 = zero padding); which = 0
+ * padded-input positions, 1 output positions.  CPU-only check of the multiply-high division. */
+int seedrl_debug_conv_pixels(int N, int H, int W, int which, int start, int count, int* out);
 /* 0: every shape takes vtrace_loss_kernel; 1 (default): large aligned batches take the
  * TMA-streamed vtrace_loss_stream_kernel.  Lets the tests run both on the same inputs. */
 int seedrl_debug_set_loss_stream(int enabled);
@@ -312,7 +315,7 @@ int seedrl_debug_conv3x3_tc(int cin, int cout, int in_mode, int split, int N, in
                             seedrl_stream_t stream);
 /* tcgen05 weight gradient (MN-major operands, one TMEM accumulator per tap). */
 int seedrl_debug_conv3x3_wgrad_tc(int cin, int cout, int in_mode, int split, int N, int H, int W,
-                                  const float* x, const float* dy, float* dw, float* db,
+                                  const void* x, const float* dy, float* dw, float* db,
                                   float* partial, size_t partial_bytes, int* error_flag,
                                   seedrl_stream_t stream);
 int seedrl_debug_maxpool(int backward, int N, int H, int W, int C, const float* x_or_dy,

@@ -84,6 +84,18 @@ __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 template <>
+__device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <>
 __device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, float* v) {
   tmem_ld<16>(taddr, v);
   tmem_ld<16>(taddr + 16, v + 16);
@@ -323,22 +335,29 @@ static int launch_tc(int N, int H, int W, const float* in, const uint4* wq, cons
 
 // ---------------------------------------------------------------------------------------
 // Weight gradient on the tensor cores.
-//   dW[tap][ci][co] = sum_p x~[p + tap][ci] * dy[p][co]      (x~ = relu(x) for the res convs)
-// as a GEMM with M = ci, N = co, K = positions.  Both operands are MN-major: for a fixed
-// position (K index) the 8 channels of a group are contiguous -- which is again exactly the
-// channel-group plane layout used by the forward kernel:
+//   dW[kh][kw][ci][co] = sum_p x~[p + kh*PW + kw][ci] * dy[p][co]   (x~ = relu(x) for the res convs,
+//                                                                    frame/255 for the first conv)
+// as a GEMM with M = co, N = (kw, ci), K = positions, one accumulator per kernel row kh.
+// Both operands are MN-major: for a fixed position (K index) the 8 channels of a group are
+// contiguous -- the channel-group plane layout of the forward kernel:
 //     core matrix = 8 positions (K) x 8 channels (MN), 128 B;  K-group stride (LBO) = 128 B;
-//     MN-group stride (SBO) = plane stride;  tap = descriptor start address + off*16 B.
-// UMMA M is 128, so rows >= CIN of every accumulator are junk (they read whatever follows
-// the x planes in shared memory) and are never read back; the MMA cost equals M = 64.
-// One accumulator per tap (9 * COUT TMEM columns) lives across ALL chunks of a persistent
-// CTA (1 CTA / SM).  Warp-specialised pipeline over kWgBufs shared-memory stages:
-//     warps 1..15  producers: fp32 global -> registers (prefetched one chunk ahead) ->
+//     MN-group stride (SBO) = plane stride.
+// A = dy planes [COUT/8][128].  B = x planes [3][CP/8][Lk]: plane (kw, g) holds x shifted by kw
+// positions (the producers store every x unit three times), so that the three taps of a
+// kernel row are consecutive N-groups of ONE MMA (N = 3*CP instead of three N = COUT
+// MMAs: the tensor pipe's per-instruction floor, not its FLOP rate, is what small-N MMAs
+// pay); kh is a descriptor start-address offset of kh*PW positions.  UMMA M is 64, rows
+// >= COUT of the accumulators are junk (they read whatever follows the dy planes in shared
+// memory) and are never read back.  The 3 accumulators (3 * 3*CP TMEM columns) live across
+// ALL chunks of a persistent CTA (1 CTA / SM).  Warp-specialised pipeline over `nb` stages:
+//     warps 1..15  producers: global -> registers (prefetched two chunks ahead) ->
 //                  bf16 planes in smem -> fence.proxy.async -> arrive on full[stage]
-//     warp 0       one lane waits full[stage], issues the 72 (x3 when SPLIT) MMAs by
+//     warp 0       waits full[stage]; one elected lane issues the 24 (x3 when SPLIT) MMAs by
 //                  bumping the descriptor start-address field, commits to empty[stage]
-// SPLIT = bf16x3: operands are split x = hi + lo (two bf16 planes) and the product is
+// SPLIT = bf16x3: operands are split v = hi + lo (two bf16 planes) and the product is
 // hi*hi + lo*hi + hi*lo, i.e. fp32-faithful (~2^-16 relative) contraction on tensor cores.
+// uint8 frames (first conv, CIN = 4 padded to one 8-channel group) are exact in bf16: no lo
+// plane; the 1/255 scale is applied to the accumulators.
 // Per-CTA partial dW/db are reduced in fixed order by wgrad_reduce (deterministic).
 __host__ __device__ constexpr uint32_t umma_idesc_mn(int M, int N) {
   return umma_idesc(M, N) | (1u << 15) | (1u << 16);
@@ -346,7 +365,7 @@ __host__ __device__ constexpr uint32_t umma_idesc_mn(int M, int N) {
 
 constexpr int kWgThreads = 512;
 constexpr int kWgProducers = kWgThreads - 32;
-constexpr int kWgBufs = 3;
+constexpr int kWgMaxBufs = 3;
 
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, bool* timed_out) {
   uint32_t done = 0;
@@ -365,29 +384,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, bool* 
 
 template <int CIN, int COUT, int IN_MODE, bool SPLIT>
 __global__ void __launch_bounds__(kWgThreads, 1)
-conv3x3_wgrad_tc_kernel(ConvGeom g, const float* __restrict__ x, const float* __restrict__ dy,
-                        float* __restrict__ partial, int* __restrict__ error_flag) {
-  constexpr int G = CIN / 8, GO = COUT / 8, S = SPLIT ? 2 : 1;
-  constexpr int TCOLS = (9 * COUT <= 256) ? 256 : 512;
+conv3x3_wgrad_tc_kernel(ConvGeom g, const void* __restrict__ x_, const float* __restrict__ dy,
+                        float* __restrict__ partial, const int nb, int* __restrict__ error_flag) {
+  constexpr int CP = CIN < 8 ? 8 : CIN;                   // channels per position in the x planes
+  constexpr int G = CP / 8, GO = COUT / 8;
+  constexpr bool XSPLIT = SPLIT && IN_MODE != IN_U8;
+  constexpr int SX = XSPLIT ? 2 : 1, SD = SPLIT ? 2 : 1;
+  constexpr int NN = 3 * CP;                              // UMMA N: (kw, ci)
+  constexpr int TCOLS = 3 * NN <= 128 ? 128 : (3 * NN <= 256 ? 256 : 512);
   constexpr int NW = 9 * CIN * COUT + COUT;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int PW = g.PW;
-  const int L = kTcM + 2 * PW + 2;
-  const int LPl = L | 1;                                  // x plane stride (16-byte units)
+  const int L = kTcM + 2 * PW + 2;                        // x positions a chunk touches
+  const int Lk = kTcM + 2 * PW;                           // positions per shifted plane
+  const int LPk = Lk | 1;                                 // x plane stride (16-byte units)
   // one stage: [x hi planes | x lo planes | dy hi planes | dy lo planes]
-  const uint32_t xs_units = (uint32_t)G * LPl, ds_units = (uint32_t)GO * kTcM;
-  const uint32_t buf_units = S * (xs_units + ds_units);
+  const uint32_t xs_units = (uint32_t)(3 * G) * LPk, ds_units = (uint32_t)GO * kTcM;
+  const uint32_t buf_units = SX * xs_units + SD * ds_units;
   uint4* s_buf = reinterpret_cast<uint4*>(smem_raw);
   // (whatever follows the last stage is only ever READ, by the junk rows of A)
-  uint64_t* s_full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kWgBufs * buf_units * 16);
-  uint64_t* s_empty = s_full + kWgBufs;
-  uint64_t* s_done = s_empty + kWgBufs;
+  uint64_t* s_full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)nb * buf_units * 16);
+  uint64_t* s_empty = s_full + kWgMaxBufs;
+  uint64_t* s_done = s_empty + kWgMaxBufs;
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_done + 1);
   float* s_bias = reinterpret_cast<float*>(smem_raw);     // reused after the pipeline drains
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int i = 0; i < kWgBufs; ++i) {
+    for (int i = 0; i < kWgMaxBufs; ++i) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(s_full + i)), "r"(kWgProducers / 32));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_empty + i)));
     }
@@ -403,7 +427,7 @@ conv3x3_wgrad_tc_kernel(ConvGeom g, const float* __restrict__ x, const float* __
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(s_tmem);
-  constexpr uint32_t idesc = umma_idesc_mn(64, COUT);   // M = 64: only 8 channel-group rows of A are read
+  constexpr uint32_t idesc = umma_idesc_mn(64, NN);       // M = 64: 8 channel-group rows of A are read
 
   const int nchunks = (int)((g.Q + kTcM - 1) / kTcM);
   const int my_chunks = ((int)blockIdx.x < nchunks) ? (nchunks - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -416,30 +440,28 @@ conv3x3_wgrad_tc_kernel(ConvGeom g, const float* __restrict__ x, const float* __
     // ================================ MMA issuer ===========================================
     // (the whole warp walks the loop converged; one elected lane issues)
     for (int it = 0; it < my_chunks; ++it) {
-      const int b = it % kWgBufs;
-      mbar_wait(s_full + b, (uint32_t)((it / kWgBufs) & 1), &timed_out);
+      const int b = it % nb;
+      mbar_wait(s_full + b, (uint32_t)((it / nb) & 1), &timed_out);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (elect_one()) {
         const uint32_t xbase = smem_u32(s_buf + (size_t)b * buf_units);
-        const uint32_t dbase = xbase + S * xs_units * 16u;
+        const uint32_t dbase = xbase + SX * xs_units * 16u;
         // descriptors with start address 0; the address field counts 16-byte units
-        const uint64_t ax = umma_desc(0u, 128u, (uint32_t)LPl * 16u);
-        const uint64_t bd = umma_desc(0u, 128u, (uint32_t)kTcM * 16u);
-        const uint64_t xh = ax + (xbase >> 4), xl = xh + xs_units;
-        const uint64_t dh = bd + (dbase >> 4), dl = dh + ds_units;
+        const uint64_t bx = umma_desc(0u, 128u, (uint32_t)LPk * 16u);
+        const uint64_t ad = umma_desc(0u, 128u, (uint32_t)kTcM * 16u);
+        const uint64_t xh = bx + (xbase >> 4), xl = xh + xs_units;
+        const uint64_t dh = ad + (dbase >> 4), dl = dh + ds_units;
         const uint32_t acc0 = it > 0 ? 1u : 0u;
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          const uint32_t off = (uint32_t)((tap / 3) * PW + (tap % 3));
-          const uint32_t d_tmem = tmem_base + (uint32_t)(tap * COUT);
+        for (int kh = 0; kh < 3; ++kh) {
+          const uint32_t off = (uint32_t)(kh * PW);
+          const uint32_t d_tmem = tmem_base + (uint32_t)(kh * NN);
 #pragma unroll
           for (int ks = 0; ks < kTcM / 16; ++ks) {
             const uint32_t ko = (uint32_t)(ks * 16);
-            umma_f16(d_tmem, xh + ko + off, dh + ko, idesc, (ks > 0) ? 1u : acc0);
-            if (SPLIT) {
-              umma_f16(d_tmem, xl + ko + off, dh + ko, idesc, 1u);
-              umma_f16(d_tmem, xh + ko + off, dl + ko, idesc, 1u);
-            }
+            umma_f16(d_tmem, dh + ko, xh + ko + off, idesc, (ks > 0) ? 1u : acc0);
+            if (SPLIT) umma_f16(d_tmem, dl + ko, xh + ko + off, idesc, 1u);
+            if (XSPLIT) umma_f16(d_tmem, dh + ko, xl + ko + off, idesc, 1u);
           }
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
@@ -460,20 +482,27 @@ conv3x3_wgrad_tc_kernel(ConvGeom g, const float* __restrict__ x, const float* __
     const int pt = tid - 32;
     constexpr int IX = 2;                                             // host checks L*G <= IX*producers
     constexpr int ID = (kTcM * GO + kWgProducers - 1) / kWgProducers;
-    struct Regs { float4 xa[IX], xb[IX], dya[ID], dyb[ID]; };
+    const float* xf = reinterpret_cast<const float*>(x_);
+    const uint32_t* xu = reinterpret_cast<const uint32_t*>(x_);       // IN_U8: 4 channels = one word
+    struct Regs { float4 xa[IX], xb[IX], dya[ID], dyb[ID]; uint32_t xw[IX]; };
     auto issue_loads = [&](Regs& r, int q0) {
 #pragma unroll
       for (int k = 0; k < IX; ++k) {
         const int i = pt + k * kWgProducers;
         r.xa[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         r.xb[k] = r.xa[k];
+        r.xw[k] = 0u;
         if (i < L * G) {
           const int s = i / G, gch = i - s * G;
           const int pix = in_pixel(g, q0 + s);
           if (pix >= 0) {
-            const float4* src = reinterpret_cast<const float4*>(x + (size_t)pix * CIN + gch * 8);
-            r.xa[k] = __ldg(src);
-            r.xb[k] = __ldg(src + 1);
+            if (IN_MODE == IN_U8) {
+              r.xw[k] = __ldg(xu + pix);
+            } else {
+              const float4* src = reinterpret_cast<const float4*>(xf + (size_t)pix * CIN + gch * 8);
+              r.xa[k] = __ldg(src);
+              r.xb[k] = __ldg(src + 1);
+            }
           }
         }
       }
@@ -495,22 +524,42 @@ conv3x3_wgrad_tc_kernel(ConvGeom g, const float* __restrict__ x, const float* __
     };
     auto chunk_q0 = [&](int it) { return ((int)blockIdx.x + it * (int)gridDim.x) * kTcM; };
     auto stage = [&](Regs& r, int it) {
-      const int b = it % kWgBufs;
-      uint4* s_x = s_buf + (size_t)b * buf_units;
-      uint4* s_d = s_x + (size_t)S * xs_units;
-      if (it >= kWgBufs) mbar_wait(s_empty + b, (uint32_t)(((it / kWgBufs) - 1) & 1), &timed_out);
+      const int pb = it % nb;
+      uint4* s_x = s_buf + (size_t)pb * buf_units;
+      uint4* s_d = s_x + (size_t)SX * xs_units;
+      if (it >= nb) mbar_wait(s_empty + pb, (uint32_t)(((it / nb) - 1) & 1), &timed_out);
 #pragma unroll
       for (int k = 0; k < IX; ++k) {
         const int i = pt + k * kWgProducers;
         if (i < L * G) {
           const int s = i / G, gch = i - s * G;
-          float4 a = r.xa[k], c = r.xb[k];
-          if (IN_MODE == IN_RELU) {
-            a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
-            c.x = fmaxf(c.x, 0.f); c.y = fmaxf(c.y, 0.f); c.z = fmaxf(c.z, 0.f); c.w = fmaxf(c.w, 0.f);
+          uint4 hi, lo = make_uint4(0u, 0u, 0u, 0u);
+          if (IN_MODE == IN_U8) {
+            const uint32_t w = r.xw[k];     // exact in bf16; channels 4..7 are zero padding
+            // byte k -> float without I2F: 0x4B0000kk is 2^23 + kk
+            hi = pack8_bf16(make_float4(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)) - 8388608.0f,
+                                        __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541)) - 8388608.0f,
+                                        __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7542)) - 8388608.0f,
+                                        __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7543)) - 8388608.0f),
+                            make_float4(0.f, 0.f, 0.f, 0.f));
+          } else {
+            float4 a = r.xa[k], c = r.xb[k];
+            if (IN_MODE == IN_RELU) {
+              a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
+              c.x = fmaxf(c.x, 0.f); c.y = fmaxf(c.y, 0.f); c.z = fmaxf(c.z, 0.f); c.w = fmaxf(c.w, 0.f);
+            }
+            hi = pack8_bf16(a, c);
+            if (XSPLIT) lo = pack8_bf16(bf16_resid4(a), bf16_resid4(c));
           }
-          s_x[(size_t)gch * LPl + s] = pack8_bf16(a, c);
-          if (SPLIT) s_x[xs_units + (size_t)gch * LPl + s] = pack8_bf16(bf16_resid4(a), bf16_resid4(c));
+          // plane (kw, gch)[p] = x[p + kw]
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const int p = s - kw;
+            if (p >= 0 && p < Lk) {
+              s_x[(size_t)(kw * G + gch) * LPk + p] = hi;
+              if (XSPLIT) s_x[xs_units + (size_t)(kw * G + gch) * LPk + p] = lo;
+            }
+          }
         }
       }
       // a thread always stages the same co-group (kWgProducers % GO == 0) => bsum[] is per
@@ -532,7 +581,7 @@ conv3x3_wgrad_tc_kernel(ConvGeom g, const float* __restrict__ x, const float* __
       __syncwarp();
       if (lane == 0)
         asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(
-                         smem_u32(s_full + b))
+                         smem_u32(s_full + pb))
                      : "memory");
     };
     Regs r0, r1;
@@ -549,20 +598,21 @@ conv3x3_wgrad_tc_kernel(ConvGeom g, const float* __restrict__ x, const float* __
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   __syncthreads();
 
-  // ---- epilogue: rows 0..CIN-1 of each tap's accumulator -> this CTA's partial --------------
+  // ---- epilogue: rows 0..COUT-1 of each kernel row's accumulator -> this CTA's partial -------
   float* dst = partial + (size_t)blockIdx.x * NW;
   // UMMA M = 64 accumulator layout (cute tmem_frg_1sm, M_MMA == 64): row m lives in TMEM
   // lane (m % 16) + 32 * (m / 16), i.e. 16 rows per 32-lane sub-partition.
-  if (warp < (CIN + 15) / 16) {
+  if (warp < (COUT + 15) / 16) {
+    const float scale = IN_MODE == IN_U8 ? (1.0f / 255.0f) : 1.0f;
 #pragma unroll 1
-    for (int tap = 0; tap < 9; ++tap) {
-      float v[COUT];
-      tmem_ld<COUT>(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(tap * COUT), v);
-      const int row = warp * 16 + lane;
-      if (lane < 16 && row < CIN) {
+    for (int t = 0; t < 9; ++t) {                          // t = kh*3 + kw
+      float v[CP];
+      tmem_ld<CP>(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((t / 3) * NN + (t % 3) * CP), v);
+      const int co = warp * 16 + lane;
+      if (lane < 16 && co < COUT) {
 #pragma unroll
-        for (int c = 0; c < COUT; ++c)
-          dst[((size_t)tap * CIN + row) * COUT + c] = my_chunks > 0 ? v[c] : 0.f;
+        for (int ci = 0; ci < CIN; ++ci)
+          dst[((size_t)t * CIN + ci) * COUT + co] = my_chunks > 0 ? v[ci] * scale : 0.f;
       }
     }
   }
@@ -586,41 +636,44 @@ conv3x3_wgrad_tc_kernel(ConvGeom g, const float* __restrict__ x, const float* __
 }
 
 template <int CIN, int COUT, int IN_MODE, bool SPLIT>
-static int launch_wgrad_tc(int N, int H, int W, const float* x, const float* dy, float* dw, float* db,
+static int launch_wgrad_tc(int N, int H, int W, const void* x, const float* dy, float* dw, float* db,
                            float* partial, size_t partial_bytes, int* err, cudaStream_t st) {
   const ConvGeom g = make_geom(N, H, W);
+  constexpr int CP = CIN < 8 ? 8 : CIN;
+  constexpr int SX = (SPLIT && IN_MODE != IN_U8) ? 2 : 1, SD = SPLIT ? 2 : 1;
   const int L = kTcM + 2 * g.PW + 2;
-  constexpr int S = SPLIT ? 2 : 1;
-  const size_t plane = (size_t)(L | 1) * 16;
-  const size_t buf = S * ((size_t)(CIN / 8) * plane + (size_t)(COUT / 8) * kTcM * 16);
-  // A's junk rows reach 16 plane strides past the start of the last stage's (lo) x planes
-  size_t smem = (kWgBufs - 1) * buf + (S - 1) * (size_t)(CIN / 8) * plane + 8 * plane + 256;
-  const size_t need = kWgBufs * buf + 256;
-  if (smem < need) smem = need;
+  const size_t plane = (size_t)((kTcM + 2 * g.PW) | 1) * 16;
+  const size_t buf = SX * 3 * (size_t)(CP / 8) * plane + SD * (size_t)(COUT / 8) * kTcM * 16;
+  // A's junk rows reach 8 dy-plane strides (16 KB) past the start of the last stage's dy planes
+  const size_t tail = 8 * (size_t)kTcM * 16 + 256;
+  const size_t budget = 224 * 1024;
+  int nb = kWgMaxBufs;
+  while (nb > 1 && nb * buf + tail > budget) --nb;
+  if (nb < 2 || (size_t)L * (CP / 8) > (size_t)2 * kWgProducers)
+    return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "wgrad_tc: image too wide");
+  size_t smem = nb * buf + tail;
   if (smem < (size_t)kWgProducers * 8 * 4) smem = (size_t)kWgProducers * 8 * 4;
   static bool attr = false;
   if (!attr) {
     SEEDRL_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_tc_kernel<CIN, COUT, IN_MODE, SPLIT>,
-                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
     attr = true;
   }
-  if (smem > 224 * 1024 || (size_t)L * (CIN / 8) > (size_t)2 * kWgProducers)
-    return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "wgrad_tc: image too wide");
   if (g.Q + kTcM + 4 * g.PW >= (1LL << 31))
     return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "wgrad_tc: batch too large for 32-bit positions");
   constexpr int NW = 9 * CIN * COUT + COUT;
   const long long nchunks = (g.Q + kTcM - 1) / kTcM;
-  int grid = kNumSMs;                       // 1 CTA per SM (TMEM: 9*COUT accumulator columns)
+  int grid = kNumSMs;                       // 1 CTA per SM (TMEM-resident accumulators)
   if (grid > nchunks) grid = (int)nchunks;
   if ((size_t)grid * NW * sizeof(float) > partial_bytes)
     return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "wgrad_tc: partial buffer too small");
-  conv3x3_wgrad_tc_kernel<CIN, COUT, IN_MODE, SPLIT><<<grid, kWgThreads, smem, st>>>(g, x, dy, partial, err);
+  conv3x3_wgrad_tc_kernel<CIN, COUT, IN_MODE, SPLIT><<<grid, kWgThreads, smem, st>>>(g, x, dy, partial, nb, err);
   count_launch(PC_CONV_WGRAD, st);
   SEEDRL_CHECK_LAUNCH();
   return wgrad_reduce(grid, 9 * CIN * COUT, COUT, partial, dw, db, st);
 }
 
-int conv3x3_wgrad_tc(int cin, int cout, int in_mode, int split, int N, int H, int W, const float* x,
+int conv3x3_wgrad_tc(int cin, int cout, int in_mode, int split, int N, int H, int W, const void* x,
                      const float* dy, float* dw, float* db, float* partial, size_t partial_bytes,
                      int* err, cudaStream_t st) {
 #define SEEDRL_WGTC_CASE(CI, CO_, MODE)                                                          \
@@ -628,6 +681,7 @@ int conv3x3_wgrad_tc(int cin, int cout, int in_mode, int split, int N, int H, in
     if (split) return launch_wgrad_tc<CI, CO_, MODE, true>(N, H, W, x, dy, dw, db, partial, partial_bytes, err, st); \
     return launch_wgrad_tc<CI, CO_, MODE, false>(N, H, W, x, dy, dw, db, partial, partial_bytes, err, st);           \
   }
+  SEEDRL_WGTC_CASE(4, 16, IN_U8)
   SEEDRL_WGTC_CASE(16, 16, IN_RELU)
   SEEDRL_WGTC_CASE(16, 32, IN_F32)
   SEEDRL_WGTC_CASE(32, 32, IN_F32)
@@ -637,7 +691,8 @@ int conv3x3_wgrad_tc(int cin, int cout, int in_mode, int split, int N, int H, in
 }
 
 bool conv3x3_wgrad_tc_supported(int cin, int cout, int in_mode) {
-  return (cin == 16 && cout == 16 && in_mode == IN_RELU) || (cin == 16 && cout == 32 && in_mode == IN_F32) ||
+  return (cin == 4 && cout == 16 && in_mode == IN_U8) || (cin == 16 && cout == 16 && in_mode == IN_RELU) ||
+         (cin == 16 && cout == 32 && in_mode == IN_F32) ||
          (cin == 32 && cout == 32 && (in_mode == IN_F32 || in_mode == IN_RELU));
 }
 

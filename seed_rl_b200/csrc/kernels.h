@@ -13,43 +13,62 @@ struct ConvGeom {
   int PW;            // W + 2
   int RH;            // H + 1 (rows per image in the tall layout)
   long long Q;       // N * RH * PW flattened output positions
+  // division by PW / RH as multiply-high + shift (positions are < 2^31, checked on the host):
+  // l = ceil(log2 d), m = ceil(2^(31+l) / d) < 2^32, n / d == umulhi(n, m) >> (l - 1).
+  // [error n*e/2^(31+l) < 2^-l <= 1/d with 0 <= e < 1, so the floor is exact]
+  unsigned int pw_mul, rh_mul;
+  int pw_sh, rh_sh;
 };
+
+__host__ __device__ inline void fast_div_setup(unsigned int d, unsigned int* mul, int* sh) {
+  int l = 1;                                   // d >= 2
+  while ((1u << l) < d) ++l;
+  *mul = (unsigned int)(((1ULL << (31 + l)) + d - 1) / d);
+  *sh = l - 1;
+}
+__host__ __device__ __forceinline__ unsigned int fast_div(unsigned int n, unsigned int mul, int sh) {
+#ifdef __CUDA_ARCH__
+  return __umulhi(n, mul) >> sh;
+#else
+  return (unsigned int)(((unsigned long long)n * mul) >> 32) >> sh;
+#endif
+}
 
 __host__ __device__ inline ConvGeom make_geom(int N, int H, int W) {
   ConvGeom g;
   g.N = N; g.H = H; g.W = W; g.PW = W + 2; g.RH = H + 1;
   g.Q = (long long)N * g.RH * g.PW;
+  fast_div_setup((unsigned int)g.PW, &g.pw_mul, &g.pw_sh);   // PW >= 3, RH >= 2
+  fast_div_setup((unsigned int)g.RH, &g.rh_mul, &g.rh_sh);
   return g;
 }
 
-#ifdef __CUDACC__
 // padded-input position -> pixel index (n*H + h)*W + w, or -1 for padding.
 // (positions fit in 31 bits: checked on the host)
-__device__ __forceinline__ int in_pixel(const ConvGeom& g, int gp) {
-  const int Rp = gp / g.PW;
+__host__ __device__ __forceinline__ int in_pixel(const ConvGeom& g, int gp) {
+  const int Rp = (int)fast_div((unsigned int)gp, g.pw_mul, g.pw_sh);
   const int c = gp - Rp * g.PW;
-  const int n = Rp / g.RH;
+  const int n = (int)fast_div((unsigned int)Rp, g.rh_mul, g.rh_sh);
   const int rr = Rp - n * g.RH;
   if (rr == 0 || c == 0 || c > g.W || n >= g.N) return -1;
   return (n * g.H + (rr - 1)) * g.W + (c - 1);
 }
 // output position -> pixel index or -1.
-__device__ __forceinline__ int out_pixel(const ConvGeom& g, int p) {
-  const int Ro = p / g.PW;
+__host__ __device__ __forceinline__ int out_pixel(const ConvGeom& g, int p) {
+  const int Ro = (int)fast_div((unsigned int)p, g.pw_mul, g.pw_sh);
   const int c = p - Ro * g.PW;
-  const int n = Ro / g.RH;
+  const int n = (int)fast_div((unsigned int)Ro, g.rh_mul, g.rh_sh);
   const int h = Ro - n * g.RH;
   if (h >= g.H || c >= g.W || n >= g.N) return -1;
   return (n * g.H + h) * g.W + c;
 }
-#endif
 
 // conv_tc_kernels.cu (tcgen05 tensor-core path)
 bool conv3x3_tc_supported(int cin, int cout, int in_mode);
 int conv3x3_tc_pack_weights(int cin, int cout, int flip, int split, const float* w, void* wq,
                             cudaStream_t st);
 bool conv3x3_wgrad_tc_supported(int cin, int cout, int in_mode);
-int conv3x3_wgrad_tc(int cin, int cout, int in_mode, int split, int N, int H, int W, const float* x,
+int conv3x3_wgrad_tc(int cin, int cout, int in_mode, int split, int N, int H, int W, const void* x,
                      const float* dy, float* dw, float* db, float* partial, size_t partial_bytes,
                      int* err, cudaStream_t st);
 int conv3x3_tc_forward(int cin, int cout, int in_mode, int split, int N, int H, int W, const float* in,

@@ -423,8 +423,7 @@ static int conv_bwd(const seedrl_net* n, const float* prm, float* grd, const Con
                     const float* dres, float* dx, void* ws, const Plan& pl, cudaStream_t st) {
   // weight + bias gradient
   if (n->conv_mode >= 1 && conv3x3_wgrad_tc_supported(l.cin, l.cout, x_mode)) {
-    SEEDRL_TRY(conv3x3_wgrad_tc(l.cin, l.cout, x_mode, n->conv_mode == 2, N, H, Wd,
-                                reinterpret_cast<const float*>(x), dy,
+    SEEDRL_TRY(conv3x3_wgrad_tc(l.cin, l.cout, x_mode, n->conv_mode == 2, N, H, Wd, x, dy,
                                 G(n, grd, l.w), G(n, grd, l.b), W<float>(ws, pl.partial),
                                 conv3x3_wgrad_partial_bytes(), W<int>(ws, pl.tcerr), st));
   } else {
@@ -596,8 +595,17 @@ extern "C" int seedrl_debug_sgemm(int ta, int tb, int M, int N, int K, const flo
 // data-gradient) into `wq_scratch` (>= 9*cin*cout*2 bytes) and runs the tensor-core conv.
 // `variant` bit0/bit1 swap LBO/SBO of the A/B descriptors (bring-up aid); *error_flag is
 // set to 1 by the kernel if its bounded mbarrier wait expires.
+// Host evaluation of the tall-image position -> pixel maps the conv kernels use (multiply-high
+// division): which = 0 padded-input position, 1 output position.  No GPU involved.
+extern "C" int seedrl_debug_conv_pixels(int N, int H, int W, int which, int start, int count, int* out) {
+  SEEDRL_CHECK_ARG(N >= 1 && H >= 1 && W >= 1 && start >= 0 && count >= 0 && out, "bad arguments");
+  const ConvGeom g = make_geom(N, H, W);
+  for (int i = 0; i < count; ++i) out[i] = which ? out_pixel(g, start + i) : in_pixel(g, start + i);
+  return SEEDRL_OK;
+}
+
 extern "C" int seedrl_debug_conv3x3_wgrad_tc(int cin, int cout, int in_mode, int split, int N, int H, int W,
-                                             const float* x, const float* dy, float* dw, float* db,
+                                             const void* x, const float* dy, float* dw, float* db,
                                              float* partial, size_t partial_bytes, int* error_flag,
                                              seedrl_stream_t stream) {
   SEEDRL_CHECK_ARG(conv3x3_wgrad_tc_supported(cin, cout, in_mode), "unsupported (cin,cout,mode)");

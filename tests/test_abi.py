@@ -216,3 +216,33 @@ def test_structured_fifo_queue_capacity_and_close():
   q.close()
   with pytest.raises(utils.QueueClosedError):
     q.dequeue()
+
+
+def test_conv_position_maps_on_host():
+  """The conv kernels' tall-image geometry (N images stacked with one shared zero row between
+  them, one zero column each side; positions flattened) and its multiply-high division,
+  evaluated on the host through the C-ABI against a straightforward numpy statement."""
+  import ctypes
+  import numpy as np
+  from seed_rl_b200 import _lib
+  L = _lib.lib()
+  for N, H, W in [(3, 84, 84), (5, 42, 42), (7, 21, 21), (9, 11, 11), (4, 9, 7), (2, 5, 3), (3, 1, 1),
+                  (1344, 84, 84), (2, 126, 126)]:
+    PW, RH = W + 2, H + 1
+    Q = N * RH * PW
+    for which in (0, 1):
+      starts = [0] if Q < 400000 else [0, Q // 2 - 1000, Q - 100000]
+      for start in starts:
+        count = min(Q + 3 * PW - start, 200000)
+        out = np.empty(count, np.int32)
+        _lib.check(L.seedrl_debug_conv_pixels(N, H, W, which, start, count, out.ctypes.data_as(ctypes.c_void_p)))
+        p = np.arange(start, start + count, dtype=np.int64)
+        R, c = p // PW, p % PW
+        n, r = R // RH, R % RH
+        if which == 0:
+          ok = (r != 0) & (c != 0) & (c <= W) & (n < N)
+          want = np.where(ok, (n * H + (r - 1)) * W + (c - 1), -1)
+        else:
+          ok = (r < H) & (c < W) & (n < N)
+          want = np.where(ok, (n * H + r) * W + c, -1)
+        np.testing.assert_array_equal(out, want)

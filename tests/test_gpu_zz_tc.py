@@ -97,13 +97,20 @@ def test_conv3x3_tc_data_gradient(cin, cout, N, H, W, split):
 
 @pytest.mark.parametrize('split', [0, 1])
 @pytest.mark.parametrize('cin,cout,mode,N,H,W', [(32, 32, 1, 3, 21, 21), (32, 32, 0, 40, 11, 11), (16, 16, 1, 5, 42, 42),
-                                                 (16, 32, 0, 2, 42, 42), (32, 32, 1, 700, 21, 21), (32, 32, 0, 1, 4, 4)])
+                                                 (16, 32, 0, 2, 42, 42), (32, 32, 1, 700, 21, 21), (32, 32, 0, 1, 4, 4),
+                                                 (4, 16, 2, 3, 84, 84), (4, 16, 2, 40, 9, 7), (16, 16, 1, 300, 42, 42)])
 def test_conv3x3_tc_weight_gradient(cin, cout, mode, N, H, W, split):
-  """dW, db on the tensor cores (MN-major operands, per-tap TMEM accumulators) == autograd."""
+  """dW, db on the tensor cores (MN-major operands, one TMEM accumulator per kernel row with
+  the three taps of the row stacked along N) == autograd.  mode 2 = uint8 frames / 255."""
   rng = np.random.default_rng(cin + cout + N)
-  x = rng.normal(size=(N, H, W, cin)).astype(np.float32)
+  if mode == 2:
+    x = rng.integers(0, 256, (N, H, W, cin), dtype=np.uint8)
+  else:
+    x = rng.normal(size=(N, H, W, cin)).astype(np.float32)
   dy = rng.normal(size=(N, H, W, cout)).astype(np.float32)
   xin = torch.relu(torch.as_tensor(x)) if mode == 1 else torch.as_tensor(x)
+  if mode == 2:
+    xin = xin.float() / 255.0
   wt = torch.zeros(3, 3, cin, cout, requires_grad=True); bt = torch.zeros(cout, requires_grad=True)
   (net_oracle._conv_nhwc(xin, wt, bt, 1, True) * torch.as_tensor(dy)).sum().backward()
   dw, db, err = _run_wgrad(cin, cout, mode, N, H, W, x, dy, split)
