@@ -354,8 +354,9 @@ def main():
           'algorithmic_bytes_per_launch': nbytes / max(cats[dom][1], 1),
           'avg_launch_ms': ms_dom / max(cats[dom][1], 1), 'launches_per_step': cats[dom][1],
           'share_of_step': ms_dom / tot if tot else None, 'peak_source': peak_src,
-          'note': 'fp32 SIMT kernels: FMA-bound today; the HBM roofline is the bound a '
-                  'tensor-core (tcgen05) implementation of this layer would have'}
+          'note': 'category time from CUDA events around every launch of the timed steps; tcgen05 path: '
+                  'operands are converted fp32->bf16 on the way into shared memory, so the bound is the '
+                  'fp32 activation traffic (HBM), not tensor FLOPs'}
 
     if rank == 0 and world == 1:
       # ---- the fused V-trace loss kernel: B sweep (north star: >= 60% HBM at streaming size)

@@ -299,17 +299,23 @@ int seedrl_debug_conv_pixels(int N, int H, int W, int which, int start, int coun
 /* 0: every shape takes vtrace_loss_kernel; 1 (default): large aligned batches take the
  * TMA-streamed vtrace_loss_stream_kernel.  Lets the tests run both on the same inputs. */
 int seedrl_debug_set_loss_stream(int enabled);
+/* K positions per pipeline stage of the tensor-core weight-gradient kernel: the largest of 512 / 256 / 128
+ * not above `kc` whose stages fit shared memory is used (default 512). */
+int seedrl_debug_set_wgrad_chunk(int kc);
+/* Output positions per tile of the tensor-core forward / data-gradient kernel: the largest
+ * of 512 / 256 / 128 not above `mt` that keeps two CTAs per SM is used (default 512). */
+int seedrl_debug_set_conv_tile(int mt);
 int seedrl_debug_conv3x3_wgrad(int cin, int cout, int in_mode, int N, int H, int W,
                                const void* x, const float* dy, float* dw, float* db,
                                float* partial, size_t partial_bytes,
                                seedrl_stream_t stream);
 /* tcgen05 (tensor-core, bf16 x bf16 -> fp32) 3x3 convolution: packs fp32 HWIO weights
  * (flip != 0: flipped + transposed, i.e. the data-gradient; split != 0: bf16x3 hi/lo
- * operands, fp32-faithful) into wq_scratch (>= 2*9*cin*cout*2 bytes) and runs the implicit-GEMM kernel.  variant bit0/bit1 swap the
+ * operands, fp32-faithful) into wq_scratch (>= 2*9*max(cin,16)*cout*2 bytes) and runs the implicit-GEMM kernel.  variant bit0/bit1 swap the
  * LBO/SBO fields of the A/B shared-memory descriptors (bring-up aid); *error_flag becomes 1
  * if the kernel's bounded mbarrier wait expires. */
 int seedrl_debug_conv3x3_tc(int cin, int cout, int in_mode, int split, int N, int H, int W,
-                            const float* in, const float* w, const float* bias,
+                            const void* in, const float* w, const float* bias,
                             const float* mask, const float* res, float* out, int flip,
                             int variant, void* wq_scratch, int* error_flag,
                             seedrl_stream_t stream);

@@ -103,6 +103,8 @@ SIGNATURES = {
     'seedrl_debug_wgrad_partial_bytes': (c_size_t, []),
     'seedrl_debug_conv_pixels': (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P]),
     'seedrl_debug_set_loss_stream': (c_int, [c_int]),
+    'seedrl_debug_set_wgrad_chunk': (c_int, [c_int]),
+    'seedrl_debug_set_conv_tile': (c_int, [c_int]),
     'seedrl_debug_conv3x3_wgrad_tc':
         (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, c_size_t, P, P]),
     'seedrl_debug_conv3x3_wgrad':

@@ -68,10 +68,12 @@ bool conv3x3_tc_supported(int cin, int cout, int in_mode);
 int conv3x3_tc_pack_weights(int cin, int cout, int flip, int split, const float* w, void* wq,
                             cudaStream_t st);
 bool conv3x3_wgrad_tc_supported(int cin, int cout, int in_mode);
+void conv3x3_wgrad_tc_set_chunk(int kc);   // upper bound: 512 (default), 256 or 128
 int conv3x3_wgrad_tc(int cin, int cout, int in_mode, int split, int N, int H, int W, const void* x,
                      const float* dy, float* dw, float* db, float* partial, size_t partial_bytes,
                      int* err, cudaStream_t st);
-int conv3x3_tc_forward(int cin, int cout, int in_mode, int split, int N, int H, int W, const float* in,
+void conv3x3_tc_set_tile(int mt);           // upper bound: 512 (default), 256 or 128
+int conv3x3_tc_forward(int cin, int cout, int in_mode, int split, int N, int H, int W, const void* in,
                        const void* wq, const float* bias, const float* mask, const float* res,
                        float* out, int variant, int* err, cudaStream_t st);
 

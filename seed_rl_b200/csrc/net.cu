@@ -181,8 +181,8 @@ static int run_conv(const seedrl_net* n, void* ws, const Plan& pl, int cin, int 
     void* wq = W<void>(ws, pl.wq);
     const int split = n->conv_mode == 2;
     SEEDRL_TRY(conv3x3_tc_pack_weights(cin, cout, flip, split, w, wq, st));
-    return conv3x3_tc_forward(cin, cout, in_mode, split, N, H, Wd, reinterpret_cast<const float*>(in),
-                              wq, bias, mask, res, out, 0, W<int>(ws, pl.tcerr), st);
+    return conv3x3_tc_forward(cin, cout, in_mode, split, N, H, Wd, in, wq, bias, mask, res, out, 0,
+                              W<int>(ws, pl.tcerr), st);
   }
   if (flip) {
     float* wt = W<float>(ws, pl.wt);
@@ -592,7 +592,7 @@ extern "C" int seedrl_debug_sgemm(int ta, int tb, int M, int N, int K, const flo
 }
 
 // tcgen05 conv test hook: packs fp32 HWIO weights (optionally flipped/transposed for the
-// data-gradient) into `wq_scratch` (>= 9*cin*cout*2 bytes) and runs the tensor-core conv.
+// data-gradient) into `wq_scratch` (>= 2*9*max(cin,16)*cout*2 bytes) and runs the tensor-core conv.
 // `variant` bit0/bit1 swap LBO/SBO of the A/B descriptors (bring-up aid); *error_flag is
 // set to 1 by the kernel if its bounded mbarrier wait expires.
 // Host evaluation of the tall-image position -> pixel maps the conv kernels use (multiply-high
@@ -604,6 +604,14 @@ extern "C" int seedrl_debug_conv_pixels(int N, int H, int W, int which, int star
   return SEEDRL_OK;
 }
 
+// Bench knob: K positions per pipeline stage of the tensor-core weight-gradient kernel
+// (the largest of 512/256/128 not above `kc` whose stages fit shared memory is used; default 512).
+extern "C" int seedrl_debug_set_wgrad_chunk(int kc) {
+  SEEDRL_CHECK_ARG(kc == 128 || kc == 256 || kc == 512, "chunk must be 128, 256 or 512");
+  conv3x3_wgrad_tc_set_chunk(kc);
+  return SEEDRL_OK;
+}
+
 extern "C" int seedrl_debug_conv3x3_wgrad_tc(int cin, int cout, int in_mode, int split, int N, int H, int W,
                                              const void* x, const float* dy, float* dw, float* db,
                                              float* partial, size_t partial_bytes, int* error_flag,
@@ -612,8 +620,16 @@ extern "C" int seedrl_debug_conv3x3_wgrad_tc(int cin, int cout, int in_mode, int
   return conv3x3_wgrad_tc(cin, cout, in_mode, split, N, H, W, x, dy, dw, db, partial, partial_bytes,
                           error_flag, (cudaStream_t)stream);
 }
+// Bench knob: output positions per tile of the tensor-core forward / data-gradient kernel
+// (the largest of 512/256/128 not above `mt` that keeps >= 2 CTAs per SM is used; default 512).
+extern "C" int seedrl_debug_set_conv_tile(int mt) {
+  SEEDRL_CHECK_ARG(mt == 128 || mt == 256 || mt == 512, "tile must be 128, 256 or 512");
+  conv3x3_tc_set_tile(mt);
+  return SEEDRL_OK;
+}
+
 extern "C" int seedrl_debug_conv3x3_tc(int cin, int cout, int in_mode, int split, int N, int H, int W,
-                                       const float* in, const float* w, const float* bias,
+                                       const void* in, const float* w, const float* bias,
                                        const float* mask, const float* res, float* out, int flip,
                                        int variant, void* wq_scratch, int* error_flag,
                                        seedrl_stream_t stream) {

@@ -20,13 +20,15 @@ pytestmark = pytest.mark.gpu
 TOL = {0: 1.5e-2, 1: 2e-4}
 CASES = [(16, 16, 1, 5, 42, 42), (16, 32, 0, 2, 42, 42), (32, 32, 1, 7, 21, 21),
          (32, 32, 0, 9, 11, 11), (32, 16, 0, 2, 42, 42), (16, 16, 0, 1, 5, 3),
-         (32, 32, 1, 300, 11, 11)]
+         (32, 32, 1, 300, 11, 11), (4, 16, 2, 3, 84, 84), (4, 16, 2, 11, 9, 7), (16, 16, 1, 64, 42, 42)]
 
 
 def _ref(x, w, b, mode):
   xt = torch.as_tensor(x)
   if mode == 1:
     xt = torch.relu(xt)
+  if mode == 2:
+    xt = xt.float() / 255.0
   return net_oracle._conv_nhwc(xt, torch.as_tensor(w), None if b is None else torch.as_tensor(b), 1, True)
 
 
@@ -36,7 +38,7 @@ def _run(cin, cout, mode, N, H, W, x, w, b, mask, res, flip, variant, split=0):
   c = lambda a: None if a is None else torch.as_tensor(np.asarray(a)).cuda()
   xc, wc, bc, mc, rc = c(x), c(w), c(b), c(mask), c(res)
   out = torch.full((N, H, W, cout), float('nan')).cuda()
-  wq = torch.empty(2 * 9 * cin * cout * 2, dtype=torch.uint8).cuda()
+  wq = torch.empty(2 * 9 * max(cin, 16) * cout * 2, dtype=torch.uint8).cuda()
   err = torch.zeros(1, dtype=torch.int32).cuda()
   _lib.check(L.seedrl_debug_conv3x3_tc(cin, cout, mode, split, N, H, W, _lib.ptr(xc), _lib.ptr(wc),
                                        _lib.ptr(bc), _lib.ptr(mc), _lib.ptr(rc), _lib.ptr(out), flip,
@@ -65,11 +67,22 @@ def _relerr(a, b):
   return float(np.nanmax(np.abs(np.nan_to_num(a, nan=1e30) - b)) / (np.abs(b).max() + 1e-30))
 
 
+@pytest.fixture(params=[512, 256, 128])
+def conv_tile(request):
+  from seed_rl_b200 import _lib
+  _lib.check(_lib.lib().seedrl_debug_set_conv_tile(request.param))
+  yield request.param
+  _lib.check(_lib.lib().seedrl_debug_set_conv_tile(512))
+
+
 @pytest.mark.parametrize('split', [0, 1])
 @pytest.mark.parametrize('cin,cout,mode,N,H,W', CASES)
-def test_conv3x3_tc_forward(cin, cout, mode, N, H, W, split):
+def test_conv3x3_tc_forward(cin, cout, mode, N, H, W, split, conv_tile):
   rng = np.random.default_rng(cin * 100 + cout + H)
-  x = rng.normal(size=(N, H, W, cin)).astype(np.float32)
+  if mode == 2:
+    x = rng.integers(0, 256, (N, H, W, cin), dtype=np.uint8)
+  else:
+    x = rng.normal(size=(N, H, W, cin)).astype(np.float32)
   w = (rng.normal(size=(3, 3, cin, cout)) * 0.2).astype(np.float32)
   b = rng.normal(size=(cout,)).astype(np.float32)
   mask = rng.normal(size=(N, H, W, cout)).astype(np.float32)
@@ -83,7 +96,7 @@ def test_conv3x3_tc_forward(cin, cout, mode, N, H, W, split):
 
 @pytest.mark.parametrize('split', [0, 1])
 @pytest.mark.parametrize('cin,cout,N,H,W', [(16, 16, 5, 42, 42), (16, 32, 2, 42, 42), (32, 32, 7, 21, 21)])
-def test_conv3x3_tc_data_gradient(cin, cout, N, H, W, split):
+def test_conv3x3_tc_data_gradient(cin, cout, N, H, W, split, conv_tile):
   """dX = tc_conv(dY, flipped/transposed weights) == autograd of the forward conv."""
   rng = np.random.default_rng(cin + cout)
   x = torch.tensor(rng.normal(size=(N, H, W, cin)).astype(np.float32), requires_grad=True)
@@ -95,11 +108,19 @@ def test_conv3x3_tc_data_gradient(cin, cout, N, H, W, split):
   assert err == 0 and _relerr(got, x.grad.numpy()) < TOL[split]
 
 
+@pytest.fixture(params=[512, 256, 128])
+def wgrad_chunk(request):
+  from seed_rl_b200 import _lib
+  _lib.check(_lib.lib().seedrl_debug_set_wgrad_chunk(request.param))
+  yield request.param
+  _lib.check(_lib.lib().seedrl_debug_set_wgrad_chunk(512))
+
+
 @pytest.mark.parametrize('split', [0, 1])
 @pytest.mark.parametrize('cin,cout,mode,N,H,W', [(32, 32, 1, 3, 21, 21), (32, 32, 0, 40, 11, 11), (16, 16, 1, 5, 42, 42),
                                                  (16, 32, 0, 2, 42, 42), (32, 32, 1, 700, 21, 21), (32, 32, 0, 1, 4, 4),
                                                  (4, 16, 2, 3, 84, 84), (4, 16, 2, 40, 9, 7), (16, 16, 1, 300, 42, 42)])
-def test_conv3x3_tc_weight_gradient(cin, cout, mode, N, H, W, split):
+def test_conv3x3_tc_weight_gradient(cin, cout, mode, N, H, W, split, wgrad_chunk):
   """dW, db on the tensor cores (MN-major operands, one TMEM accumulator per kernel row with
   the three taps of the row stacked along N) == autograd.  mode 2 = uint8 frames / 255."""
   rng = np.random.default_rng(cin + cout + N)

@@ -1,6 +1,6 @@
 """Per-layer timing of the 3x3 conv kernels at the learner's shapes (N = 21*64 = 1344 frames):
 back-to-back launches between CUDA events; prints us and algorithmic GB/s.
-  python tools/conv_bench.py [wgrad|fwd|all] [split]"""
+  python tools/conv_bench.py [wgrad|fwd|all] [split] [wgrad chunk 128|256]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -12,6 +12,9 @@ split = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 N = 1344
 LAYERS = [(4, 16, 2, 84), (16, 16, 1, 42), (16, 32, 0, 42), (32, 32, 1, 21), (32, 32, 0, 21), (32, 32, 1, 11)]
 REP = 10
+if len(sys.argv) > 3:
+  _lib.check(L.seedrl_debug_set_wgrad_chunk(int(sys.argv[3])))
+  _lib.check(L.seedrl_debug_set_conv_tile(int(sys.argv[3])))
 
 
 def timed(fn):
@@ -49,9 +52,9 @@ for cin, cout, mode, H in LAYERS:
       us = timed(fn)
       print('%-10s cin=%2d cout=%2d mode=%d %2dx%-2d  %8.1f us  %7.0f GB/s (x %d MB + dy %d MB)' %
             (name, cin, cout, mode, H, W, us, (xb + yb) / us / 1e3, xb >> 20, yb >> 20), flush=True)
-  if what in ('fwd', 'all') and mode != 2:
+  if what in ('fwd', 'all'):
     w = torch.randn(3, 3, cin, cout, device='cuda') * 0.1; b = torch.randn(cout, device='cuda')
-    out = torch.empty(N, H, W, cout, device='cuda'); wq = torch.empty(2 * 9 * cin * cout * 2, dtype=torch.uint8, device='cuda')
+    out = torch.empty(N, H, W, cout, device='cuda'); wq = torch.empty(2 * 9 * max(cin, 16) * cout * 2, dtype=torch.uint8, device='cuda')
     us = timed(lambda: _lib.check(L.seedrl_debug_conv3x3_tc(cin, cout, mode, split, N, H, W, _lib.ptr(x), _lib.ptr(w), _lib.ptr(b),
                                                            None, None, _lib.ptr(out), 0, 0, _lib.ptr(wq), _lib.ptr(err), _lib.stream_ptr())))
     print('%-10s cin=%2d cout=%2d mode=%d %2dx%-2d  %8.1f us  %7.0f GB/s (incl. weight pack launch)' %
