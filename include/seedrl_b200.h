@@ -326,6 +326,13 @@ int seedrl_debug_conv3x3_wgrad_tc(int cin, int cout, int in_mode, int split, int
                                   seedrl_stream_t stream);
 int seedrl_debug_maxpool(int backward, int N, int H, int W, int C, const float* x_or_dy,
                          float* y_or_dx, uint8_t* idx, seedrl_stream_t stream);
+/* C[M,N] (=|+=) op(A) op(B) on the tensor cores (tcgen05, bf16 or bf16x3 operands, fp32
+ * accumulate): ta: A stored [K,M]; tb: B stored [N,K]; epilogue bias / relu / mask / accumulate
+ * as seedrl_debug_sgemm.  ws (may be NULL) takes split-K partials. */
+int seedrl_debug_gemm_tc(int ta, int tb, int split, int M, int N, int K, const float* A, int lda,
+                         const float* B, int ldb, float* C, int ldc, const float* bias,
+                         const float* mask, int ldm, int relu, int accumulate, int a_relu,
+                         float* ws, size_t ws_bytes, int* error_flag, seedrl_stream_t stream);
 int seedrl_debug_sgemm(int ta, int tb, int M, int N, int K, const float* A, int lda,
                        const float* B, int ldb, float* C, int ldc, const float* bias,
                        const float* mask, int ldm, int relu, int accumulate, int a_relu,

@@ -110,6 +110,9 @@ SIGNATURES = {
     'seedrl_debug_conv3x3_wgrad':
         (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, c_size_t, P]),
     'seedrl_debug_maxpool': (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
+    'seedrl_debug_gemm_tc':
+        (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_int, P, c_int, P, P, c_int, c_int, c_int,
+                 c_int, P, c_size_t, P, P]),
     'seedrl_debug_sgemm':
         (c_int, [c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_int, P, c_int, P, P, c_int,
                  c_int, c_int, c_int, P]),

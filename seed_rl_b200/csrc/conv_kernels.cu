@@ -415,20 +415,20 @@ int conv3x3_wgrad(int cin, int cout, int in_mode, int N, int H, int W, const voi
 // pad_before = total/2 where total = max((Ho-1)*2+3-H, 0): (0 before, 1 after) for
 // 84->42 and 42->21, (1,1) for 21->11.  Stores the argmax tap (0..8) per element
 // so that the backward is a gather.  One thread = 4 channels of one output pixel.
+// One CTA per output row (n, ho) [blockIdx.x], threads over (wo, c4) [+ blockIdx.y chunks]:
+// no per-thread division, 32-bit indexing (host checks the element counts fit).
 __global__ void maxpool3s2_fwd_kernel(int N, int H, int W, int C, int Ho, int Wo, int pt, int pl,
                                       const float* __restrict__ x, float* __restrict__ y,
                                       uint8_t* __restrict__ idx) {
   const int C4 = C >> 2;
-  const long long total = (long long)N * Ho * Wo * C4;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c4 = (int)(i % C4);
-  long long r = i / C4;
-  const int wo = (int)(r % Wo); r /= Wo;
-  const int ho = (int)(r % Ho);
-  const long long n = r / Ho;
+  const int row = blockIdx.x;                 // n * Ho + ho
+  const int n = row / Ho, ho = row - n * Ho;
+  const int j = blockIdx.y * blockDim.x + threadIdx.x;   // wo * C4 + c4
+  if (j >= Wo * C4) return;
+  const int wo = (C4 & (C4 - 1)) == 0 ? j >> (31 - __clz(C4)) : j / C4, c4 = j - wo * C4;
   float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
   uchar4 arg = make_uchar4(0, 0, 0, 0);
+  const float4* xn = reinterpret_cast<const float4*>(x) + (size_t)n * H * W * C4;
 #pragma unroll
   for (int kh = 0; kh < 3; ++kh) {
     const int h = ho * 2 - pt + kh;
@@ -437,7 +437,7 @@ __global__ void maxpool3s2_fwd_kernel(int N, int H, int W, int C, int Ho, int Wo
     for (int kw = 0; kw < 3; ++kw) {
       const int w = wo * 2 - pl + kw;
       if (w < 0 || w >= W) continue;
-      const float4 v = __ldg(reinterpret_cast<const float4*>(x) + ((n * H + h) * W + w) * C4 + c4);
+      const float4 v = __ldg(xn + (h * W + w) * C4 + c4);
       const unsigned char t = (unsigned char)(kh * 3 + kw);
       if (v.x > best.x) { best.x = v.x; arg.x = t; }
       if (v.y > best.y) { best.y = v.y; arg.y = t; }
@@ -445,37 +445,41 @@ __global__ void maxpool3s2_fwd_kernel(int N, int H, int W, int C, int Ho, int Wo
       if (v.w > best.w) { best.w = v.w; arg.w = t; }
     }
   }
-  reinterpret_cast<float4*>(y)[i] = best;
-  reinterpret_cast<uchar4*>(idx)[i] = arg;
+  const size_t o = (size_t)row * Wo * C4 + j;
+  reinterpret_cast<float4*>(y)[o] = best;
+  reinterpret_cast<uchar4*>(idx)[o] = arg;
 }
 
 // dx[n,h,w,c] = sum over the <=4 windows containing (h,w) whose argmax is (h,w).
+// One CTA per input row (n, h); the (at most two) output rows whose windows cover h are
+// resolved once per CTA.
 __global__ void maxpool3s2_bwd_kernel(int N, int H, int W, int C, int Ho, int Wo, int pt, int pl,
                                       const float* __restrict__ dy, const uint8_t* __restrict__ idx,
                                       float* __restrict__ dx) {
   const int C4 = C >> 2;
-  const long long total = (long long)N * H * W * C4;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c4 = (int)(i % C4);
-  long long r = i / C4;
-  const int w = (int)(r % W); r /= W;
-  const int h = (int)(r % H);
-  const long long n = r / H;
+  const int row = blockIdx.x;                 // n * H + h
+  const int n = row / H, h = row - n * H;
+  const int j = blockIdx.y * blockDim.x + threadIdx.x;   // w * C4 + c4
+  if (j >= W * C4) return;
+  const int w = (C4 & (C4 - 1)) == 0 ? j >> (31 - __clz(C4)) : j / C4, c4 = j - w * C4;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   // windows: ho with ho*2 - pt <= h <= ho*2 - pt + 2
   const int hp = h + pt, wp = w + pl;
-  for (int ho = (hp - 1) >> 1; ho <= hp >> 1; ++ho) {
-    if (ho < 0 || ho >= Ho) continue;
+  const float4* dyn = reinterpret_cast<const float4*>(dy) + (size_t)n * Ho * Wo * C4;
+  const uchar4* idn = reinterpret_cast<const uchar4*>(idx) + (size_t)n * Ho * Wo * C4;
+#pragma unroll
+  for (int dh = 0; dh < 2; ++dh) {
+    const int ho = ((hp - 1) >> 1) + dh;
     const int kh = hp - ho * 2;
-    if (kh < 0 || kh > 2) continue;
-    for (int wo = (wp - 1) >> 1; wo <= wp >> 1; ++wo) {
-      if (wo < 0 || wo >= Wo) continue;
+    if (ho < 0 || ho >= Ho || kh < 0 || kh > 2 || (dh == 1 && ho > (hp >> 1))) continue;
+#pragma unroll
+    for (int dw = 0; dw < 2; ++dw) {
+      const int wo = ((wp - 1) >> 1) + dw;
       const int kw = wp - wo * 2;
-      if (kw < 0 || kw > 2) continue;
-      const long long o = ((n * Ho + ho) * Wo + wo) * C4 + c4;
-      const uchar4 a = __ldg(reinterpret_cast<const uchar4*>(idx) + o);
-      const float4 g = __ldg(reinterpret_cast<const float4*>(dy) + o);
+      if (wo < 0 || wo >= Wo || kw < 0 || kw > 2 || (dw == 1 && wo > (wp >> 1))) continue;
+      const int o = (ho * Wo + wo) * C4 + c4;
+      const uchar4 a = __ldg(idn + o);
+      const float4 g = __ldg(dyn + o);
       const unsigned char t = (unsigned char)(kh * 3 + kw);
       if (a.x == t) acc.x += g.x;
       if (a.y == t) acc.y += g.y;
@@ -483,7 +487,7 @@ __global__ void maxpool3s2_bwd_kernel(int N, int H, int W, int C, int Ho, int Wo
       if (a.w == t) acc.w += g.w;
     }
   }
-  reinterpret_cast<float4*>(dx)[i] = acc;
+  reinterpret_cast<float4*>(dx)[(size_t)row * W * C4 + j] = acc;
 }
 
 static void same_pad(int n, int k, int s, int* out, int* before) {
@@ -499,8 +503,11 @@ int maxpool3s2_forward(int N, int H, int W, int C, const float* x, float* y, uin
   same_pad(H, 3, 2, &Ho, &pt);
   same_pad(W, 3, 2, &Wo, &pl);
   const long long total = (long long)N * Ho * Wo * (C / 4);
-  maxpool3s2_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(N, H, W, C, Ho, Wo, pt, pl,
-                                                                         x, y, idx);
+  (void)total;
+  const int per_row = Wo * (C / 4);
+  const int threads = per_row >= 256 ? 256 : ((per_row + 31) / 32) * 32;
+  maxpool3s2_fwd_kernel<<<dim3((unsigned)(N * Ho), (unsigned)ceil_div(per_row, threads)), threads, 0, st>>>(
+      N, H, W, C, Ho, Wo, pt, pl, x, y, idx);
   count_launch(PC_POOL, st);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
@@ -512,8 +519,11 @@ int maxpool3s2_backward(int N, int H, int W, int C, const float* dy, const uint8
   same_pad(H, 3, 2, &Ho, &pt);
   same_pad(W, 3, 2, &Wo, &pl);
   const long long total = (long long)N * H * W * (C / 4);
-  maxpool3s2_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(N, H, W, C, Ho, Wo, pt, pl,
-                                                                         dy, idx, dx);
+  (void)total;
+  const int per_row = W * (C / 4);
+  const int threads = per_row >= 256 ? 256 : ((per_row + 31) / 32) * 32;
+  maxpool3s2_bwd_kernel<<<dim3((unsigned)(N * H), (unsigned)ceil_div(per_row, threads)), threads, 0, st>>>(
+      N, H, W, C, Ho, Wo, pt, pl, dy, idx, dx);
   count_launch(PC_POOL, st);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;

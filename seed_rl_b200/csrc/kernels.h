@@ -116,6 +116,13 @@ inline GemmEpi epi_none() { return GemmEpi{nullptr, nullptr, 0, 0, 0, 0}; }
 int sgemm(bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
           float* C, int ldc, const GemmEpi& e, cudaStream_t st);
 int colsum(int M, int N, const float* X, int ld, float* out, cudaStream_t st);
+// gemm_tc_kernels.cu (tcgen05): same contract as sgemm; split = bf16x3 operands; `ws` holds
+// split-K partials (gemm_tc_workspace_bytes()); *err is set if a bounded mbarrier wait expires.
+bool gemm_tc_supported(int M, int N, int K);
+size_t gemm_tc_workspace_bytes();
+int gemm_tc(bool ta, bool tb, int split, int M, int N, int K, const float* A, int lda, const float* B,
+            int ldb, float* C, int ldc, const GemmEpi& e, float* ws, size_t ws_bytes, int* err,
+            cudaStream_t st);
 int core_input_tail(int Nrows, int D, int A, const float* reward, const int64_t* prev_action,
                     float* core_in, cudaStream_t st);
 int lstm_mask_state(int B, int Hd, const uint8_t* done, const float* h_src, float* h_dst,

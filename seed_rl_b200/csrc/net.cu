@@ -96,7 +96,7 @@ struct Plan {
   size_t sh_a1, sh_a2;         // shallow conv outputs (post-relu)
   size_t xc, z, hp, cs, hs, c0buf;
   // backward scratch
-  size_t dhs, dz, dhrec, dc0, dc1, dd, gA, gB, gC, gFull, wt, partial, wq, tcerr, counter;
+  size_t dhs, dz, dhrec, dc0, dc1, dd, gA, gB, gC, gFull, wt, partial, wq, tcerr, counter, gemm_ws;
   size_t total;
 };
 
@@ -147,6 +147,7 @@ static Plan make_plan(const seedrl_net* n, int T1, int B) {
   p.gFull = b.take(full_max * 4);
   p.wt = b.take(64 * 1024 * 4);
   p.wq = b.take(2 * 64 * 1024 * 2);
+  p.gemm_ws = b.take(gemm_tc_workspace_bytes());
   p.tcerr = b.take(256);
   p.counter = b.take(256);
   p.partial = b.take(conv3x3_wgrad_partial_bytes());
@@ -169,6 +170,17 @@ static inline float* G(const seedrl_net* n, float* arena, int idx) {
 template <typename T>
 static inline T* W(void* ws, size_t off) {
   return reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + off);
+}
+
+// One dense contraction of the schedule: tcgen05 when the net runs in tensor-core mode and the
+// shape is worth a 128-row tile, else the fp32 SIMT kernel.
+static int run_gemm(const seedrl_net* n, void* ws, const Plan& pl, bool ta, bool tb, int M, int N, int K,
+                    const float* A, int lda, const float* B, int ldb, float* C, int ldc, const GemmEpi& e,
+                    cudaStream_t st) {
+  if (n->conv_mode >= 1 && gemm_tc_supported(M, N, K))
+    return gemm_tc(ta, tb, n->conv_mode == 2, M, N, K, A, lda, B, ldb, C, ldc, e, W<float>(ws, pl.gemm_ws),
+                   gemm_tc_workspace_bytes(), W<int>(ws, pl.tcerr), st);
+  return sgemm(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, e, st);
 }
 
 // One 3x3 'same' convolution of the schedule.  flip != 0: data-gradient (weights flipped and
@@ -372,13 +384,13 @@ extern "C" int seedrl_net_forward(const seedrl_net* n, const float* prm, int T1,
   // Dense(256) + relu written straight into the first 256 columns of the core input
   GemmEpi e = epi_none();
   e.bias = P(n, prm, n->p_dense_b); e.relu = 1; e.a_relu = flat_relu;
-  SEEDRL_TRY(sgemm(false, false, N, kHidden, n->flat, flat_src, n->flat, P(n, prm, n->p_dense_w),
+  SEEDRL_TRY(run_gemm(n, ws, pl, false, false, N, kHidden, n->flat, flat_src, n->flat, P(n, prm, n->p_dense_w),
                    kHidden, xc, CI, e, st));
   SEEDRL_TRY(core_input_tail(N, kHidden, A, reward, prev_actions, xc, st));
   // input projection for all T at once: z = xc W + b
   e = epi_none();
   e.bias = P(n, prm, n->p_core_b);
-  SEEDRL_TRY(sgemm(false, false, N, 4 * kHidden, CI, xc, CI, P(n, prm, n->p_core_w), 4 * kHidden, z,
+  SEEDRL_TRY(run_gemm(n, ws, pl, false, false, N, 4 * kHidden, CI, xc, CI, P(n, prm, n->p_core_w), 4 * kHidden, z,
                    4 * kHidden, e, st));
   SEEDRL_CUDA(cudaMemcpyAsync(c0buf, c0, (size_t)B * kHidden * 4, cudaMemcpyDeviceToDevice, st));
   GemmEpi eacc = epi_none();
@@ -392,7 +404,7 @@ extern "C" int seedrl_net_forward(const seedrl_net* n, const float* prm, int T1,
   }
   for (int t = 0; t < T1 && n->lstm_mode == 0; ++t) {
     float* zt = z + (size_t)t * B * 4 * kHidden;
-    SEEDRL_TRY(sgemm(false, false, B, 4 * kHidden, kHidden, hp + (size_t)t * B * kHidden, kHidden,
+    SEEDRL_TRY(run_gemm(n, ws, pl, false, false, B, 4 * kHidden, kHidden, hp + (size_t)t * B * kHidden, kHidden,
                      P(n, prm, n->p_core_u), 4 * kHidden, zt, 4 * kHidden, eacc, st));
     const bool last = (t + 1 == T1);
     SEEDRL_TRY(lstm_pointwise_fwd(B, kHidden, zt, t == 0 ? c0buf : cs + (size_t)(t - 1) * B * kHidden,
@@ -403,10 +415,10 @@ extern "C" int seedrl_net_forward(const seedrl_net* n, const float* prm, int T1,
   // heads, networks.py:116-118
   e = epi_none();
   e.bias = P(n, prm, n->p_pol_b);
-  SEEDRL_TRY(sgemm(false, false, N, A, kHidden, hs, kHidden, P(n, prm, n->p_pol_w), A, policy_logits,
+  SEEDRL_TRY(run_gemm(n, ws, pl, false, false, N, A, kHidden, hs, kHidden, P(n, prm, n->p_pol_w), A, policy_logits,
                    A, e, st));
   e.bias = P(n, prm, n->p_base_b);
-  SEEDRL_TRY(sgemm(false, false, N, 1, kHidden, hs, kHidden, P(n, prm, n->p_base_w), 1, baseline, 1,
+  SEEDRL_TRY(run_gemm(n, ws, pl, false, false, N, 1, kHidden, hs, kHidden, P(n, prm, n->p_base_w), 1, baseline, 1,
                    e, st));
   if (h_out)
     SEEDRL_CUDA(cudaMemcpyAsync(h_out, hs + (size_t)(T1 - 1) * B * kHidden, (size_t)B * kHidden * 4,
@@ -506,14 +518,14 @@ extern "C" int seedrl_net_backward(const seedrl_net* n, const float* prm, int T1
 
   // heads
   GemmEpi e = epi_none();
-  SEEDRL_TRY(sgemm(true, false, kHidden, A, N, hs, kHidden, dlogits, A, G(n, grd, n->p_pol_w), A, e, st));
+  SEEDRL_TRY(run_gemm(n, ws, pl, true, false, kHidden, A, N, hs, kHidden, dlogits, A, G(n, grd, n->p_pol_w), A, e, st));
   SEEDRL_TRY(colsum(N, A, dlogits, A, G(n, grd, n->p_pol_b), st));
-  SEEDRL_TRY(sgemm(true, false, kHidden, 1, N, hs, kHidden, dbaseline, 1, G(n, grd, n->p_base_w), 1, e, st));
+  SEEDRL_TRY(run_gemm(n, ws, pl, true, false, kHidden, 1, N, hs, kHidden, dbaseline, 1, G(n, grd, n->p_base_w), 1, e, st));
   SEEDRL_TRY(colsum(N, 1, dbaseline, 1, G(n, grd, n->p_base_b), st));
-  SEEDRL_TRY(sgemm(false, true, N, kHidden, A, dlogits, A, P(n, prm, n->p_pol_w), A, dhs, kHidden, e, st));
+  SEEDRL_TRY(run_gemm(n, ws, pl, false, true, N, kHidden, A, dlogits, A, P(n, prm, n->p_pol_w), A, dhs, kHidden, e, st));
   GemmEpi eacc = epi_none();
   eacc.accumulate = 1;
-  SEEDRL_TRY(sgemm(false, true, N, kHidden, 1, dbaseline, 1, P(n, prm, n->p_base_w), 1, dhs, kHidden,
+  SEEDRL_TRY(run_gemm(n, ws, pl, false, true, N, kHidden, 1, dbaseline, 1, P(n, prm, n->p_base_w), 1, dhs, kHidden,
                    eacc, st));
   // BPTT
   if (n->lstm_mode == 1)
@@ -528,30 +540,30 @@ extern "C" int seedrl_net_backward(const seedrl_net* n, const float* prm, int T1
                                   last ? nullptr : dhrec, last ? nullptr : dcb[(t + 1) & 1],
                                   dz + (size_t)t * B * 4 * kHidden, dcb[t & 1], st));
     if (t > 0)
-      SEEDRL_TRY(sgemm(false, true, B, kHidden, 4 * kHidden, dz + (size_t)t * B * 4 * kHidden,
+      SEEDRL_TRY(run_gemm(n, ws, pl, false, true, B, kHidden, 4 * kHidden, dz + (size_t)t * B * 4 * kHidden,
                        4 * kHidden, P(n, prm, n->p_core_u), 4 * kHidden, dhrec, kHidden, e, st));
   }
-  SEEDRL_TRY(sgemm(true, false, kHidden, 4 * kHidden, N, hp, kHidden, dz, 4 * kHidden,
+  SEEDRL_TRY(run_gemm(n, ws, pl, true, false, kHidden, 4 * kHidden, N, hp, kHidden, dz, 4 * kHidden,
                    G(n, grd, n->p_core_u), 4 * kHidden, e, st));
-  SEEDRL_TRY(sgemm(true, false, CI, 4 * kHidden, N, xc, CI, dz, 4 * kHidden, G(n, grd, n->p_core_w),
+  SEEDRL_TRY(run_gemm(n, ws, pl, true, false, CI, 4 * kHidden, N, xc, CI, dz, 4 * kHidden, G(n, grd, n->p_core_w),
                    4 * kHidden, e, st));
   SEEDRL_TRY(colsum(N, 4 * kHidden, dz, 4 * kHidden, G(n, grd, n->p_core_b), st));
   // d dense_out = (dz W[:256,:]^T) * (dense_out > 0)
   GemmEpi em = epi_none();
   em.mask = xc; em.ldm = CI;
-  SEEDRL_TRY(sgemm(false, true, N, kHidden, 4 * kHidden, dz, 4 * kHidden, P(n, prm, n->p_core_w),
+  SEEDRL_TRY(run_gemm(n, ws, pl, false, true, N, kHidden, 4 * kHidden, dz, 4 * kHidden, P(n, prm, n->p_core_w),
                    4 * kHidden, dd, kHidden, em, st));
   // Dense(256)
   const float* flat_src = n->cfg.net == SEEDRL_NET_DEEP ? W<float>(ws, pl.st.back().o1)
                                                         : W<float>(ws, pl.sh_a2);
   GemmEpi ea = epi_none();
   ea.a_relu = n->cfg.net == SEEDRL_NET_DEEP ? 1 : 0;
-  SEEDRL_TRY(sgemm(true, false, n->flat, kHidden, N, flat_src, n->flat, dd, kHidden,
+  SEEDRL_TRY(run_gemm(n, ws, pl, true, false, n->flat, kHidden, N, flat_src, n->flat, dd, kHidden,
                    G(n, grd, n->p_dense_w), kHidden, ea, st));
   SEEDRL_TRY(colsum(N, kHidden, dd, kHidden, G(n, grd, n->p_dense_b), st));
   GemmEpi ef = epi_none();
   ef.mask = flat_src; ef.ldm = n->flat;
-  SEEDRL_TRY(sgemm(false, true, N, n->flat, kHidden, dd, kHidden, P(n, prm, n->p_dense_w), kHidden,
+  SEEDRL_TRY(run_gemm(n, ws, pl, false, true, N, n->flat, kHidden, dd, kHidden, P(n, prm, n->p_dense_w), kHidden,
                    W<float>(ws, pl.gA), n->flat, ef, st));
   if (n->cfg.net == SEEDRL_NET_DEEP) return torso_backward_deep(n, prm, grd, pl, observation, ws, st);
   return torso_backward_shallow(n, prm, grd, pl, observation, ws, st);
@@ -583,6 +595,18 @@ extern "C" int seedrl_debug_maxpool(int backward, int N, int H, int W, int C, co
   if (backward) return maxpool3s2_backward(N, H, W, C, x_or_dy, idx, y_or_dx, (cudaStream_t)stream);
   return maxpool3s2_forward(N, H, W, C, x_or_dy, y_or_dx, idx, (cudaStream_t)stream);
 }
+// tcgen05 GEMM test hook (same contract as seedrl_debug_sgemm; split != 0: bf16x3 operands;
+// ws: >= ws_bytes of scratch for split-K partials, may be null).
+extern "C" int seedrl_debug_gemm_tc(int ta, int tb, int split, int M, int N, int K, const float* A, int lda,
+                                    const float* B, int ldb, float* C, int ldc, const float* bias,
+                                    const float* mask, int ldm, int relu, int accumulate, int a_relu,
+                                    float* ws, size_t ws_bytes, int* error_flag, seedrl_stream_t stream) {
+  SEEDRL_CHECK_ARG(M >= 1 && N >= 1 && K >= 1 && A && B && C, "bad arguments");
+  GemmEpi e{bias, mask, ldm, relu, accumulate, a_relu};
+  return gemm_tc(ta != 0, tb != 0, split, M, N, K, A, lda, B, ldb, C, ldc, e, ws, ws_bytes, error_flag,
+                 (cudaStream_t)stream);
+}
+
 extern "C" int seedrl_debug_sgemm(int ta, int tb, int M, int N, int K, const float* A, int lda,
                                   const float* B, int ldb, float* C, int ldc, const float* bias,
                                   const float* mask, int ldm, int relu, int accumulate, int a_relu,

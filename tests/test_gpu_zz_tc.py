@@ -195,3 +195,64 @@ def test_network_step_plain_bf16_is_reported_not_parity():
   assert max(errs.values()) < 0.5
   heads = [v for k, v in errs.items() if k.split('/')[0] in ('policy_logits', 'baseline', 'core')]
   assert max(heads) < 3e-2
+
+
+# ---------------------------------------------------------------- dense GEMMs on tcgen05
+GEMM_CASES = [
+    # ta, tb, M, N, K, epilogue
+    (0, 0, 1344, 256, 3872, dict(bias=True, relu=True, a_relu=True)),     # Dense(256) forward (split-K)
+    (0, 0, 300, 1024, 275, dict(bias=True)),                               # LSTM input projection, lda = 275
+    (1, 0, 275, 1024, 333, {}),                                            # xc^T dz (TA, unaligned ld)
+    (1, 0, 3872, 256, 1344, dict(a_relu=True)),                            # Dense weight gradient
+    (0, 1, 1344, 3872, 256, dict(mask=True)),                              # Dense data gradient (TB)
+    (0, 1, 200, 256, 1024, dict(mask=True, accumulate=True)),
+    (1, 1, 129, 40, 100, dict(bias=True)),
+    (0, 0, 64, 16, 32, {}), (0, 0, 130, 19, 70, dict(relu=True)), (0, 1, 65, 300, 33, {})]
+
+
+@pytest.mark.parametrize('split', [0, 1])
+@pytest.mark.parametrize('ta,tb,M,N,K,epi', GEMM_CASES)
+def test_gemm_tc_matches_numpy(ta, tb, M, N, K, epi, split):
+  """C = op(A) op(B) with fp32 storage on the tensor cores (K-major / MN-major operand
+  layouts chosen by the storage order, split-K, fused epilogue) against float64 numpy."""
+  from seed_rl_b200 import _lib
+  L = _lib.lib()
+  rng = np.random.default_rng(M + 3 * N + 7 * K + ta + 2 * tb)
+  A = rng.normal(size=(K, M) if ta else (M, K)).astype(np.float32)
+  B = rng.normal(size=(N, K) if tb else (K, N)).astype(np.float32)
+  bias = rng.normal(size=N).astype(np.float32) if epi.get('bias') else None
+  mask = rng.normal(size=(M, N + 3)).astype(np.float32) if epi.get('mask') else None
+  C0 = rng.normal(size=(M, N + 5)).astype(np.float32)          # ldc > N: the padding must survive
+  a64 = A.astype(np.float64).T if ta else A.astype(np.float64)
+  if epi.get('a_relu'):
+    a64 = np.maximum(a64, 0)
+  b64 = B.astype(np.float64).T if tb else B.astype(np.float64)
+  want = a64 @ b64
+  scale = np.abs(want).max()
+  if bias is not None:
+    want = want + bias
+  if epi.get('relu'):
+    want = np.maximum(want, 0)
+  if mask is not None:
+    want = np.where(mask[:, :N] > 0, want, 0)
+  if epi.get('accumulate'):
+    want = want + C0[:, :N]
+  c = lambda a: None if a is None else torch.as_tensor(a).cuda()
+  Ac, Bc, bc, mc, Cc = c(A), c(B), c(bias), c(mask), c(C0)
+  ws = torch.empty(48 << 18, device='cuda')                     # 48 MB of fp32
+  err = torch.zeros(1, dtype=torch.int32, device='cuda')
+  outs = []
+  for _ in range(2):
+    Cc.copy_(torch.as_tensor(C0))
+    _lib.check(L.seedrl_debug_gemm_tc(ta, tb, split, M, N, K, _lib.ptr(Ac), A.shape[1], _lib.ptr(Bc), B.shape[1],
+                                      _lib.ptr(Cc), N + 5, _lib.ptr(bc), _lib.ptr(mc), N + 3,
+                                      int(bool(epi.get('relu'))), int(bool(epi.get('accumulate'))),
+                                      int(bool(epi.get('a_relu'))), _lib.ptr(ws), ws.numel() * 4, _lib.ptr(err),
+                                      _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    outs.append(Cc.cpu().numpy().copy())
+  assert int(err.item()) == 0
+  got = outs[0]
+  assert np.array_equal(got[:, N:], C0[:, N:])                  # nothing written past column N
+  assert np.array_equal(outs[0], outs[1])                       # deterministic (split-K in slice order)
+  assert np.abs(got[:, :N] - want).max() < TOL[split] * scale
