@@ -84,9 +84,19 @@ sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
   }
 }
 
+__global__ void colsum_kernel(int M, int N, const float* __restrict__ X, int ld, const float* __restrict__ w,
+                              int ldw, float* __restrict__ out);
+
 int sgemm(bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
           float* C, int ldc, const GemmEpi& e, cudaStream_t st) {
   if (M <= 0 || N <= 0) return SEEDRL_OK;
+  if (ta && N == 1 && ldc == 1 && !e.bias && !e.mask && !e.relu && !e.accumulate && !e.a_relu) {
+    // C[M,1] = A^T b: a weighted column sum spread over M/32 CTAs (the tiled kernel would run 4 CTAs)
+    colsum_kernel<<<ceil_div(M, 32), 1024, 0, st>>>(K, M, A, lda, B, ldb, C);
+    count_launch(PC_GEMM, st);
+    SEEDRL_CHECK_LAUNCH();
+    return SEEDRL_OK;
+  }
   dim3 grid(ceil_div(N, 64), ceil_div(M, 64));
   if (!ta && !tb) sgemm_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, e);
   else if (ta && !tb) sgemm_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, e);
@@ -99,26 +109,41 @@ int sgemm(bool ta, bool tb, int M, int N, int K, const float* A, int lda, const 
 
 // out[n] = sum_m X[m*ld + n], m < M, n < N.  One CTA per 32 columns; fixed-order
 // (deterministic) reduction.
-__global__ void colsum_kernel(int M, int N, const float* __restrict__ X, int ld,
-                              float* __restrict__ out) {
-  __shared__ float red[8][33];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;   // 8 warps
+// w != nullptr: out[n] = sum_m X[m*ld + n] * w[m*ldw]  (= X^T w, the N == 1 weight gradient).
+// 32 warps stride the rows, four independent loads in flight per lane.
+__global__ void __launch_bounds__(1024)
+colsum_kernel(int M, int N, const float* __restrict__ X, int ld, const float* __restrict__ w, int ldw,
+              float* __restrict__ out) {
+  __shared__ float red[32][33];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;   // 32 warps
   const int n = blockIdx.x * 32 + lane;
-  float s = 0.f;
-  if (n < N)
-    for (int m = w; m < M; m += 8) s += X[(size_t)m * ld + n];
-  red[w][lane] = s;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (n < N) {
+    int m = wid;
+    for (; m + 96 < M; m += 128) {
+      const float x0 = X[(size_t)m * ld + n], x1 = X[(size_t)(m + 32) * ld + n];
+      const float x2 = X[(size_t)(m + 64) * ld + n], x3 = X[(size_t)(m + 96) * ld + n];
+      if (w) {
+        s0 = fmaf(x0, w[(size_t)m * ldw], s0); s1 = fmaf(x1, w[(size_t)(m + 32) * ldw], s1);
+        s2 = fmaf(x2, w[(size_t)(m + 64) * ldw], s2); s3 = fmaf(x3, w[(size_t)(m + 96) * ldw], s3);
+      } else {
+        s0 += x0; s1 += x1; s2 += x2; s3 += x3;
+      }
+    }
+    for (; m < M; m += 32) s0 += X[(size_t)m * ld + n] * (w ? w[(size_t)m * ldw] : 1.f);
+  }
+  red[wid][lane] = (s0 + s1) + (s2 + s3);
   __syncthreads();
-  if (w == 0 && n < N) {
+  if (wid == 0 && n < N) {
     float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += red[k][lane];
+    for (int k = 0; k < 32; ++k) t += red[k][lane];
     out[n] = t;
   }
 }
 
 int colsum(int M, int N, const float* X, int ld, float* out, cudaStream_t st) {
-  colsum_kernel<<<ceil_div(N, 32), 256, 0, st>>>(M, N, X, ld, out);
+  colsum_kernel<<<ceil_div(N, 32), 1024, 0, st>>>(M, N, X, ld, nullptr, 0, out);
   count_launch(PC_GEMM, st);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;

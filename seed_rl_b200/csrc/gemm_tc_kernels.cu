@@ -40,32 +40,38 @@ struct GemmTcParams {
   int* error_flag;
 };
 
-// 8 consecutive elements along the contiguous direction of a row-major matrix -> one bf16x8
-// unit (+ residual unit).  `row` / `col0` are global coordinates; rows/cols outside
-// [0,R) x [0,Cn) read as zero.
-template <bool SPLIT>
-__device__ __forceinline__ void load_unit(const float* __restrict__ P, int ld, int row, int col0, int R, int Cn,
-                                          bool vec, bool relu, uint4* hi, uint4* lo) {
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
-  if (row < R) {
+// 8 consecutive elements along the contiguous direction of a row-major matrix (raw fp32, two
+// float4).  `row` / `col0` are global coordinates; rows/cols outside [0,R) x [0,Cn) read as zero.
+struct RawUnit { float4 a, b; };
+__device__ __forceinline__ RawUnit load_raw(const float* __restrict__ P, int ld, int row, int col0, int R, int Cn,
+                                            bool vec) {
+  RawUnit r;
+  r.a = make_float4(0.f, 0.f, 0.f, 0.f);
+  r.b = r.a;
+  if (row < R && col0 < Cn) {
     const float* src = P + (size_t)row * ld + col0;
     if (vec && col0 + 8 <= Cn) {
-      a = __ldg(reinterpret_cast<const float4*>(src));
-      b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+      r.a = __ldg(reinterpret_cast<const float4*>(src));
+      r.b = __ldg(reinterpret_cast<const float4*>(src) + 1);
     } else {
       float v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = col0 + j < Cn ? __ldg(src + j) : 0.f;
-      a = make_float4(v[0], v[1], v[2], v[3]);
-      b = make_float4(v[4], v[5], v[6], v[7]);
+      r.a = make_float4(v[0], v[1], v[2], v[3]);
+      r.b = make_float4(v[4], v[5], v[6], v[7]);
     }
   }
+  return r;
+}
+// -> one bf16x8 unit (+ the residual unit for bf16x3)
+template <bool SPLIT>
+__device__ __forceinline__ void store_unit(RawUnit r, bool relu, uint4* hi_dst, uint4* lo_dst) {
   if (relu) {
-    a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
-    b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f); b.z = fmaxf(b.z, 0.f); b.w = fmaxf(b.w, 0.f);
+    r.a.x = fmaxf(r.a.x, 0.f); r.a.y = fmaxf(r.a.y, 0.f); r.a.z = fmaxf(r.a.z, 0.f); r.a.w = fmaxf(r.a.w, 0.f);
+    r.b.x = fmaxf(r.b.x, 0.f); r.b.y = fmaxf(r.b.y, 0.f); r.b.z = fmaxf(r.b.z, 0.f); r.b.w = fmaxf(r.b.w, 0.f);
   }
-  *hi = pack8_bf16(a, b);
-  if (SPLIT) *lo = pack8_bf16(bf16_resid4(a), bf16_resid4(b));
+  *hi_dst = pack8_bf16(r.a, r.b);
+  if (SPLIT) *lo_dst = pack8_bf16(bf16_resid4(r.a), bf16_resid4(r.b));
 }
 
 template <bool TA, bool TB, bool SPLIT>
@@ -74,8 +80,13 @@ gemm_tc_kernel(const GemmTcParams p) {
   constexpr int S = SPLIT ? 2 : 1;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int BN = p.BN;
-  // one stage: [A hi | A lo | B hi | B lo]; A = 128 x 64 = 1024 units, B = BN x 64 = 8*BN units
-  const uint32_t a_units = kGtBM * kGtBK / 8, b_units = (uint32_t)BN * kGtBK / 8;
+  // one stage: [A hi | A lo | B hi | B lo].  Plane strides are padded by one 16-byte unit so
+  // that the 8 lanes of a store phase (8 consecutive planes, same row) hit 8 different banks.
+  constexpr uint32_t a_ps = TA ? (kGtBK + 1) : (kGtBM + 1);            // A plane stride (units)
+  constexpr uint32_t a_units = TA ? (kGtBM / 8) * a_ps : (kGtBK / 8) * a_ps;
+  const uint32_t b_ps = TB ? (uint32_t)BN + 1 : (uint32_t)kGtBK + 1;    // B plane stride (units)
+  const uint32_t b_units = TB ? (kGtBK / 8) * b_ps : (uint32_t)(BN / 8) * b_ps;
+  const int b_items = BN * kGtBK / 8;                                  // 16-byte units actually staged
   const uint32_t stage_units = S * (a_units + b_units);
   uint4* s_buf = reinterpret_cast<uint4*>(smem_raw);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)2 * stage_units * 16);   // [2] stage free
@@ -112,38 +123,42 @@ gemm_tc_kernel(const GemmTcParams p) {
     const int k0 = (kb0 + kb) * kGtBK;
     uint4* sA = s_buf + (size_t)st * stage_units;
     uint4* sB = sA + (size_t)S * a_units;
-    // the MMAs that read this stage two K-blocks ago have completed
-    if (kb >= 2) ok = mbar_wait_bounded(s_bar + st, (uint32_t)(((kb >> 1) - 1) & 1)) && ok;
-    // ---- A tile: 1024 units, 4 per thread -------------------------------------------------
+    // ---- stage the K-block: every global load is issued before the first conversion -------
+    // consecutive threads take consecutive 8-element groups of the SAME row (coalesced).
+    constexpr int AI = (kGtBM * kGtBK / 8) / kGtThreads;   // 4 A units per thread
+    constexpr int BI = (256 * kGtBK / 8) / kGtThreads;     // <= 8 B units per thread
+    RawUnit ra[AI], rb[BI];
 #pragma unroll
-    for (int r = 0; r < (kGtBM * kGtBK / 8) / kGtThreads; ++r) {
+    for (int r = 0; r < AI; ++r) {
       const int u = tid + r * kGtThreads;
-      uint4 hi, lo;
-      if (!TA) {      // A[M,K], k contiguous: K-major planes [8 kg][128 m]
-        const int m = u & (kGtBM - 1), kg = u >> 7;
-        load_unit<SPLIT>(p.A, p.lda, m0 + m, k0 + kg * 8, p.M, p.K, p.vecA != 0, p.e.a_relu != 0, &hi, &lo);
-        sA[kg * kGtBM + m] = hi;
-        if (SPLIT) sA[a_units + kg * kGtBM + m] = lo;
-      } else {        // A stored [K,M], m contiguous: MN-major planes [16 mg][64 k]
-        const int mg = u & 15, k = u >> 4;
-        load_unit<SPLIT>(p.A, p.lda, k0 + k, m0 + mg * 8, p.K, p.M, p.vecA != 0, p.e.a_relu != 0, &hi, &lo);
-        sA[mg * kGtBK + k] = hi;
-        if (SPLIT) sA[a_units + mg * kGtBK + k] = lo;
+      if (!TA) ra[r] = load_raw(p.A, p.lda, m0 + (u >> 3), k0 + (u & 7) * 8, p.M, p.K, p.vecA != 0);   // A[M,K]
+      else     ra[r] = load_raw(p.A, p.lda, k0 + (u >> 4), m0 + (u & 15) * 8, p.K, p.M, p.vecA != 0);  // A stored [K,M]
+    }
+    const int bng = BN >> 3;
+#pragma unroll
+    for (int r = 0; r < BI; ++r) {
+      const int u = tid + r * kGtThreads;
+      if (u < b_items) {
+        if (TB) rb[r] = load_raw(p.B, p.ldb, n0 + (u >> 3), k0 + (u & 7) * 8, p.N, p.K, p.vecB != 0);  // B stored [N,K]
+        else    rb[r] = load_raw(p.B, p.ldb, k0 + u / bng, n0 + (u % bng) * 8, p.K, p.N, p.vecB != 0); // B[K,N]
       }
     }
-    // ---- B tile: 8*BN units -------------------------------------------------------------
-    for (int u = tid; u < (int)b_units; u += kGtThreads) {
-      uint4 hi, lo;
-      if (TB) {       // B stored [N,K], k contiguous: K-major planes [8 kg][BN n]
-        const int n = u % BN, kg = u / BN;
-        load_unit<SPLIT>(p.B, p.ldb, n0 + n, k0 + kg * 8, p.N, p.K, p.vecB != 0, false, &hi, &lo);
-        sB[kg * BN + n] = hi;
-        if (SPLIT) sB[b_units + kg * BN + n] = lo;
-      } else {        // B[K,N], n contiguous: MN-major planes [BN/8 ng][64 k]
-        const int ng = u % (BN >> 3), k = u / (BN >> 3);
-        load_unit<SPLIT>(p.B, p.ldb, k0 + k, n0 + ng * 8, p.K, p.N, p.vecB != 0, false, &hi, &lo);
-        sB[ng * kGtBK + k] = hi;
-        if (SPLIT) sB[b_units + ng * kGtBK + k] = lo;
+    // the MMAs that read this stage two K-blocks ago have completed
+    if (kb >= 2) ok = mbar_wait_bounded(s_bar + st, (uint32_t)(((kb >> 1) - 1) & 1)) && ok;
+#pragma unroll
+    for (int r = 0; r < AI; ++r) {
+      const int u = tid + r * kGtThreads;
+      // K-major planes [8 kg][128 m] / MN-major planes [16 mg][64 k]
+      const uint32_t o = !TA ? (uint32_t)(u & 7) * a_ps + (u >> 3) : (uint32_t)(u & 15) * a_ps + (u >> 4);
+      store_unit<SPLIT>(ra[r], p.e.a_relu != 0, sA + o, sA + a_units + o);
+    }
+#pragma unroll
+    for (int r = 0; r < BI; ++r) {
+      const int u = tid + r * kGtThreads;
+      if (u < b_items) {
+        // K-major planes [8 kg][BN n] / MN-major planes [BN/8 ng][64 k]
+        const uint32_t o = TB ? (uint32_t)(u & 7) * b_ps + (u >> 3) : (uint32_t)(u % bng) * b_ps + u / bng;
+        store_unit<SPLIT>(rb[r], false, sB + o, sB + b_units + o);
       }
     }
     // generic-proxy smem writes -> visible to the tensor core's async proxy
@@ -155,10 +170,10 @@ gemm_tc_kernel(const GemmTcParams p) {
 #pragma unroll
       for (int ks = 0; ks < kGtBK / 16; ++ks) {
         // K-major: two K-groups = two planes (LBO = plane stride);  MN-major: 16 k-rows = 256 B
-        const uint64_t da = TA ? umma_desc(a_addr + ks * 256u, 128u, kGtBK * 16u)
-                               : umma_desc(a_addr + ks * 2u * kGtBM * 16u, kGtBM * 16u, 128u);
-        const uint64_t db = TB ? umma_desc(b_addr + ks * 2u * (uint32_t)BN * 16u, (uint32_t)BN * 16u, 128u)
-                               : umma_desc(b_addr + ks * 256u, 128u, kGtBK * 16u);
+        const uint64_t da = TA ? umma_desc(a_addr + ks * 256u, 128u, a_ps * 16u)
+                               : umma_desc(a_addr + ks * 2u * a_ps * 16u, a_ps * 16u, 128u);
+        const uint64_t db = TB ? umma_desc(b_addr + ks * 2u * b_ps * 16u, b_ps * 16u, 128u)
+                               : umma_desc(b_addr + ks * 256u, 128u, b_ps * 16u);
         const uint32_t acc = (kb > 0 || ks > 0) ? 1u : 0u;
         umma_f16(tmem_base, da, db, idesc, acc);
         if (SPLIT) {   // the address field counts 16-byte units
@@ -244,8 +259,12 @@ int gemm_tc(bool ta, bool tb, int split, int M, int N, int K, const float* A, in
   p.M = M; p.N = N; p.K = K; p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;
   p.e = e; p.error_flag = err;
   const int n16 = ((N + 15) / 16) * 16;
-  const int bn_max = split ? 128 : 256;                 // shared memory: 2 stages x (hi + lo)
-  p.BN = n16 < bn_max ? n16 : bn_max;
+  int bn = split ? 128 : 256;                           // shared memory: 2 stages x (hi + lo)
+  if (bn > n16) bn = n16;
+  // narrower tiles until the grid can cover the SMs (with split-K below)
+  const int nkb_all = ceil_div(K, kGtBK);
+  while (bn > 64 && ceil_div(M, kGtBM) * ceil_div(N, bn) * (nkb_all >= 4 ? nkb_all / 2 : 1) < kNumSMs) bn >>= 1;
+  p.BN = ((bn + 15) / 16) * 16;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.vecA = al16(A) && (lda & 3) == 0;
   p.vecB = al16(B) && (ldb & 3) == 0;
@@ -254,14 +273,16 @@ int gemm_tc(bool ta, bool tb, int split, int M, int N, int K, const float* A, in
   // split-K until the grid covers the SMs, keeping >= 4 K-blocks per slice and the
   // partials inside the workspace
   int splits = 1;
-  while (tiles * splits < kNumSMs && nkb / (splits * 2) >= 4 &&
+  while (tiles * splits < 2 * kNumSMs && nkb / (splits * 2) >= 2 &&
          (size_t)(splits * 2) * M * N * sizeof(float) <= ws_bytes && ws)
     splits *= 2;
   p.kblocks_per_split = ceil_div(nkb, splits);
   splits = ceil_div(nkb, p.kblocks_per_split);
   p.ws = splits > 1 ? ws : nullptr;
   const int S = split ? 2 : 1;
-  const size_t smem = (size_t)2 * S * (kGtBM * kGtBK / 8 + p.BN * kGtBK / 8) * 16 + 64;
+  const size_t a_un = ta ? (size_t)(kGtBM / 8) * (kGtBK + 1) : (size_t)(kGtBK / 8) * (kGtBM + 1);
+  const size_t b_un = tb ? (size_t)(kGtBK / 8) * (p.BN + 1) : (size_t)(p.BN / 8) * (kGtBK + 1);
+  const size_t smem = (size_t)2 * S * (a_un + b_un) * 16 + 64;
   dim3 grid(ceil_div(N, p.BN), ceil_div(M, kGtBM), splits);
 #define SEEDRL_GT_LAUNCH(TA_, TB_, SP_)                                                         \
   do {                                                                                          \
