@@ -79,17 +79,31 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_fwd_persistent_kernel(const
     for (int b0 = 0; b0 < B; b0 += kLBt) {
       const int nb = min(kLBt, B - b0);
       // ---- recurrent input of step t for this batch tile -> smem --------------------------
-      for (int i = tid; i < nb * (kLH / 4); i += kLThreads) {
-        const int b = i / (kLH / 4), k4 = i - b * (kLH / 4);
-        float4 v;
-        if (t == 0) {
-          v = done_t[b0 + b] ? make_float4(0.f, 0.f, 0.f, 0.f)
-                             : __ldg(reinterpret_cast<const float4*>(a.h0 + (size_t)(b0 + b) * kLH) + k4);
-          if (blockIdx.x == 0) reinterpret_cast<float4*>(hp_t + (size_t)(b0 + b) * kLH)[k4] = v;
-        } else {
-          v = __ldcg(reinterpret_cast<const float4*>(hp_t + (size_t)(b0 + b) * kLH) + k4);
+      // (8 independent 16-byte loads in flight per thread: the step is latency-bound)
+      for (int i0 = tid; i0 < nb * (kLH / 4); i0 += 8 * kLThreads) {
+        float4 v[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int i = i0 + r * kLThreads;
+          v[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < nb * (kLH / 4)) {
+            const int b = i / (kLH / 4), k4 = i - b * (kLH / 4);
+            if (t == 0) {
+              if (!done_t[b0 + b]) v[r] = __ldg(reinterpret_cast<const float4*>(a.h0 + (size_t)(b0 + b) * kLH) + k4);
+            } else {
+              v[r] = __ldcg(reinterpret_cast<const float4*>(hp_t + (size_t)(b0 + b) * kLH) + k4);
+            }
+          }
         }
-        *reinterpret_cast<float4*>(s_h + b * (kLH + 4) + k4 * 4) = v;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int i = i0 + r * kLThreads;
+          if (i < nb * (kLH / 4)) {
+            const int b = i / (kLH / 4), k4 = i - b * (kLH / 4);
+            if (t == 0 && blockIdx.x == 0) reinterpret_cast<float4*>(hp_t + (size_t)(b0 + b) * kLH)[k4] = v[r];
+            *reinterpret_cast<float4*>(s_h + b * (kLH + 4) + k4 * 4) = v[r];
+          }
+        }
       }
       __syncthreads();
       // ---- z[b, 8 cols] = x-part + h . U : thread = (b, column pair) ----------------------
@@ -153,8 +167,8 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_bwd_persistent_kernel(const
   extern __shared__ float sm[];
   constexpr int KC = 128, KS = KC + 4;           // dZ chunk width (+pad)
   float* s_Ur = sm;                              // [2][1024] rows u0, u0+1 of U
-  float* s_dz = s_Ur + kLUnits * 4 * kLH;        // [64][KS]
-  float* s_dh = s_dz + kLBt * KS;                // [64][2] recurrent part of dh
+  float* s_dz = s_Ur + kLUnits * 4 * kLH;        // [2][64][KS] double-buffered
+  float* s_dh = s_dz + 2 * kLBt * KS;            // [64][2] recurrent part of dh
   float* s_dc = s_dh + kLBt * kLUnits;           // [B][2] dc flowing to the previous step
   const int tid = threadIdx.x;
   const int u0 = blockIdx.x * kLUnits;
@@ -176,15 +190,32 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_bwd_persistent_kernel(const
       float acc0 = 0.f, acc1 = 0.f;
       if (!last) {
         const float* dzn = a.dz + ((size_t)(t + 1) * B + b0) * 4 * kLH;
-        for (int k0 = 0; k0 < 4 * kLH; k0 += KC) {
-          for (int i = tid; i < nb * (KC / 4); i += kLThreads) {
-            const int r = i / (KC / 4), k4 = i - r * (KC / 4);
-            *reinterpret_cast<float4*>(s_dz + r * KS + k4 * 4) =
-                __ldcg(reinterpret_cast<const float4*>(dzn + (size_t)r * 4 * kLH + k0) + k4);
+        // chunk c+1 travels L2 -> registers while chunk c is consumed from shared memory
+        constexpr int NL = (kLBt * (KC / 4)) / kLThreads;   // 8 x 16-byte loads per thread per chunk
+        float4 pre[NL];
+        auto load_chunk = [&](int k0) {
+#pragma unroll
+          for (int r = 0; r < NL; ++r) {
+            const int i = tid + r * kLThreads;
+            const int rr = i / (KC / 4), k4 = i - rr * (KC / 4);
+            pre[r] = rr < nb ? __ldcg(reinterpret_cast<const float4*>(dzn + (size_t)rr * 4 * kLH + k0) + k4)
+                             : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        };
+        load_chunk(0);
+        for (int c = 0; c < (4 * kLH) / KC; ++c) {
+          const int k0 = c * KC;
+          float* buf = s_dz + (c & 1) * (kLBt * KS);
+#pragma unroll
+          for (int r = 0; r < NL; ++r) {
+            const int i = tid + r * kLThreads;
+            const int rr = i / (KC / 4), k4 = i - rr * (KC / 4);
+            *reinterpret_cast<float4*>(buf + rr * KS + k4 * 4) = pre[r];
           }
           __syncthreads();
+          if (c + 1 < (4 * kLH) / KC) load_chunk(k0 + KC);
           if (b < nb) {
-            const float* drow = s_dz + b * KS + part * (KC / 4);
+            const float* drow = buf + b * KS + part * (KC / 4);
             const float* u0r = s_Ur + k0 + part * (KC / 4);
             const float* u1r = u0r + 4 * kLH;
 #pragma unroll 8
@@ -194,8 +225,8 @@ __global__ void __launch_bounds__(kLThreads, 1) lstm_bwd_persistent_kernel(const
               acc1 = fmaf(d, u1r[k], acc1);
             }
           }
-          __syncthreads();
         }
+        __syncthreads();   // the last chunk's buffer is free before the next batch tile / step
         // reduce the 4 K-parts (adjacent lanes)
         acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1); acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
         acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
@@ -235,7 +266,7 @@ static size_t lstm_fwd_smem(int B) {
   return ((size_t)kLH * 8 + (size_t)kLBt * (kLH + 4) + kLBt * 8 + (size_t)B * kLUnits) * sizeof(float);
 }
 static size_t lstm_bwd_smem(int B) {
-  return ((size_t)kLUnits * 4 * kLH + (size_t)kLBt * 132 + kLBt * kLUnits + (size_t)B * kLUnits) * sizeof(float);
+  return ((size_t)kLUnits * 4 * kLH + (size_t)2 * kLBt * 132 + kLBt * kLUnits + (size_t)B * kLUnits) * sizeof(float);
 }
 
 int lstm_forward_persistent(int T1, int B, const float* U, const uint8_t* done, float* z,
