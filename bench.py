@@ -43,7 +43,7 @@ def parse_args():
   p.add_argument('--unroll', type=int, default=20)
   p.add_argument('--cpu-batch', type=int, default=8, help='unrolls per CPU-baseline step')
   p.add_argument('--conv', default='tc', choices=['simt', 'tc', 'tc3'],
-                 help="contraction path of the 16/32-channel convs: fp32 SIMT, tcgen05 bf16, or "
+                 help="contraction path of the convs and dense layers: fp32 SIMT, tcgen05 bf16, or "
                       "tcgen05 bf16x3 (fp32-faithful split operands; the parity mode)")
   p.add_argument('--no-extras', action='store_true',
                  help='skip the profiling pass, the loss-kernel sweep and the CPU baseline')

@@ -166,7 +166,8 @@ size_t seedrl_net_num_params(const seedrl_net* net);          /* excl. entropy p
 /* Length (floats) of the flat arena: every tensor start is aligned to 64 floats,
  * the last slot is the scalar entropy_cost_param (param index == num tensors). */
 size_t seedrl_net_arena_floats(const seedrl_net* net);
-/* Contraction path of the 16/32-channel 3x3 convolutions (forward + data gradient):
+/* Contraction path of every 3x3 convolution (forward, data and weight gradient) and of the
+ * Dense / LSTM-projection / head GEMMs:
  * 0 = fp32 SIMT (bit-reproducible fp32 reference path), 1 = tcgen05 tensor cores, bf16
  * operands with fp32 accumulation, 2 = tcgen05 with bf16x3 split operands (hi*hi + lo*hi +
  * hi*lo: fp32-faithful to ~2^-16 relative). */

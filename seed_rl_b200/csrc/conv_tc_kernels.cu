@@ -1,9 +1,9 @@
-// conv3x3 'same' on the 5th-gen tensor cores (tcgen05 + TMEM), bf16 operands, fp32
-// accumulation -- forward and data-gradient of dmlab/networks.py:26-60 for the 16/32
-// channel layers (the uint8 4->16 first layer stays on the SIMT kernel).
+// conv3x3 'same' on the 5th-gen tensor cores (tcgen05 + TMEM), bf16 (or bf16x3) operands,
+// fp32 accumulation -- forward, data-gradient and weight-gradient of every convolution of
+// dmlab/networks.py:26-60, the uint8 4->16 first layer included.
 //
-// Implicit GEMM on the "tall image" (see conv_kernels.cu): a CTA owns M = 128
-// consecutive flattened output positions.  Activations are staged in shared memory as
+// Implicit GEMM on the "tall image" (see conv_kernels.cu): a CTA owns tiles of MT = 128..512
+// consecutive flattened output positions (MT / 128 UMMA row blocks).  Activations are staged in shared memory as
 // channel-group planes [CIN/8][positions][8 ch] bf16 (16 B per position per plane), which
 // IS the canonical no-swizzle K-major UMMA layout:
 //     8 consecutive positions x 8 channels  = one 128-byte core matrix
