@@ -53,6 +53,39 @@ __global__ void pack_w_tc_kernel(int CIN, int COUT, int cin_src, int flip, int s
   if (split) wq[9 * CIN * COUT + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
+// All layers' weights packed by ONE launch (blockIdx.y = job): the per-conv pack launches were
+// ~27 launches of ~3 us per learner step.
+__global__ void pack_w_tc_batch_kernel(const __grid_constant__ PackTable t, int split) {
+  const PackJob j = t.jobs[blockIdx.y];
+  const int CIN = j.ck, COUT = j.cout;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 9 * CIN * COUT) return;
+  const int e = i & 7;                       // ci % 8
+  const int r = (i >> 3) & 7;                // co % 8
+  int rest = i >> 6;
+  const int cog = rest % (COUT / 8); rest /= (COUT / 8);
+  const int kc = rest & 1; rest >>= 1;
+  const int NS = CIN / 16;
+  const int slab = rest % NS;
+  const int tap = rest / NS;
+  const int ci = slab * 16 + kc * 8 + e, co = cog * 8 + r;
+  const float v = ci >= j.cin_src ? 0.f
+                  : (j.flip ? j.w[((size_t)(8 - tap) * COUT + co) * CIN + ci]
+                            : j.w[((size_t)tap * j.cin_src + ci) * COUT + co]);
+  __nv_bfloat16* wq = reinterpret_cast<__nv_bfloat16*>(j.wq);
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  wq[i] = hi;
+  if (split) wq[9 * CIN * COUT + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+int conv3x3_tc_pack_weights_batch(const PackTable& t, int split, cudaStream_t st) {
+  if (t.n == 0) return SEEDRL_OK;
+  pack_w_tc_batch_kernel<<<dim3(ceil_div(9 * 32 * 32, 256), t.n), 256, 0, st>>>(t, split);
+  count_launch(PC_MISC, st);
+  SEEDRL_CHECK_LAUNCH();
+  return SEEDRL_OK;
+}
+
 constexpr int kTcThreads = 256;
 constexpr int kTcM = 128;
 
@@ -67,7 +100,7 @@ constexpr int kTcM = 128;
 // K-group re-reads it (LBO = 0) against zero weights; exact in bf16 (no lo plane); the 1/255
 // scale is applied to the accumulator.
 template <int CIN, int COUT, int IN_MODE, bool SPLIT, int MT>
-__global__ void __launch_bounds__(kTcThreads, 3)
+__global__ void __launch_bounds__(kTcThreads, COUT <= 16 ? 4 : 3)
 conv3x3_tc_kernel(ConvGeom g, const void* __restrict__ in_, const uint4* __restrict__ wq,
                   const float* __restrict__ bias, const float* __restrict__ mask,
                   const float* __restrict__ res, float* __restrict__ out, int variant,
@@ -636,7 +669,8 @@ conv3x3_wgrad_tc_kernel(ConvGeom g, const void* __restrict__ x_, const float* __
 constexpr int kWgTryNext = -12345;
 template <int CIN, int COUT, int IN_MODE, bool SPLIT, int KC>
 static int launch_wgrad_tc(int N, int H, int W, const void* x, const float* dy, float* dw, float* db,
-                           float* partial, size_t partial_bytes, int* err, cudaStream_t st) {
+                           float* partial, size_t partial_bytes, int* err, WgradBatch* batch,
+                           cudaStream_t st) {
   const ConvGeom g = make_geom(N, H, W);
   constexpr int CP = CIN < 8 ? 8 : CIN;
   constexpr int SX = (SPLIT && IN_MODE != IN_U8) ? 2 : 1, SD = SPLIT ? 2 : 1;
@@ -663,18 +697,55 @@ static int launch_wgrad_tc(int N, int H, int W, const void* x, const float* dy, 
   const long long nchunks = (g.Q + KC - 1) / KC;
   int grid = kNumSMs;                       // 1 CTA per SM (TMEM-resident accumulators)
   if (grid > nchunks) grid = (int)nchunks;
-  if ((size_t)grid * NW * sizeof(float) > partial_bytes)
+  // deferred reduction: this layer's partials get their own slice of the batch buffer and are
+  // reduced together with every other layer's by ONE launch at the end of the backward pass
+  const bool defer = batch && batch->n < kMaxReduceJobs &&
+                     batch->used + (size_t)grid * NW <= batch->cap_floats;
+  if (defer) {
+    partial = batch->buf + batch->used;
+    batch->used += (size_t)grid * NW;
+  } else if ((size_t)grid * NW * sizeof(float) > partial_bytes) {
     return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "wgrad_tc: partial buffer too small");
+  }
   conv3x3_wgrad_tc_kernel<CIN, COUT, IN_MODE, SPLIT, KC><<<grid, kWgThreads, smem, st>>>(g, x, dy, partial, nb, err);
   count_launch(PC_CONV_WGRAD, st);
   SEEDRL_CHECK_LAUNCH();
+  if (defer) {
+    batch->jobs[batch->n++] = ReduceJob{partial, dw, db, grid, 9 * CIN * COUT, COUT};
+    return SEEDRL_OK;
+  }
   return wgrad_reduce(grid, 9 * CIN * COUT, COUT, partial, dw, db, st);
+}
+
+__global__ void wgrad_reduce_batch_kernel(const __grid_constant__ ReduceTable t) {
+  const ReduceJob j = t.jobs[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= j.nw + j.nb) return;
+  float s = 0.f;
+  for (int k = 0; k < j.nparts; ++k) s += j.partial[(size_t)k * (j.nw + j.nb) + i];   // fixed order
+  if (i < j.nw) j.dw[i] = s; else j.db[i - j.nw] = s;
+}
+
+int wgrad_reduce_batch(WgradBatch* b, cudaStream_t st) {
+  if (!b || b->n == 0) return SEEDRL_OK;
+  ReduceTable t;
+  int maxn = 0;
+  for (int i = 0; i < b->n; ++i) {
+    t.jobs[i] = b->jobs[i];
+    if (b->jobs[i].nw + b->jobs[i].nb > maxn) maxn = b->jobs[i].nw + b->jobs[i].nb;
+  }
+  wgrad_reduce_batch_kernel<<<dim3(ceil_div(maxn, 256), b->n), 256, 0, st>>>(t);
+  count_launch(PC_CONV_WGRAD, st);
+  SEEDRL_CHECK_LAUNCH();
+  b->n = 0;
+  b->used = 0;
+  return SEEDRL_OK;
 }
 
 int conv3x3_wgrad_tc(int cin, int cout, int in_mode, int split, int N, int H, int W, const void* x,
                      const float* dy, float* dw, float* db, float* partial, size_t partial_bytes,
-                     int* err, cudaStream_t st) {
-#define SEEDRL_WGTC_ARGS N, H, W, x, dy, dw, db, partial, partial_bytes, err, st
+                     int* err, WgradBatch* batch, cudaStream_t st) {
+#define SEEDRL_WGTC_ARGS N, H, W, x, dy, dw, db, partial, partial_bytes, err, batch, st
 #define SEEDRL_WGTC_CASE(CI, CO_, MODE)                                                          \
   if (cin == CI && cout == CO_ && in_mode == MODE) {                                             \
     int rc = kWgTryNext;                                                                         \

@@ -63,6 +63,15 @@ __host__ __device__ __forceinline__ int out_pixel(const ConvGeom& g, int p) {
   return (n * g.H + h) * g.W + c;
 }
 
+// Job tables: one launch packs every layer's weights / reduces every layer's weight-gradient
+// partials (passed to the kernels by value as __grid_constant__ parameters).
+constexpr int kMaxPackJobs = 32, kMaxReduceJobs = 16;
+struct PackJob { const float* w; void* wq; int ck, cout, cin_src, flip; };
+struct PackTable { PackJob jobs[kMaxPackJobs]; int n; };
+struct ReduceJob { const float* partial; float* dw; float* db; int nparts, nw, nb; };
+struct ReduceTable { ReduceJob jobs[kMaxReduceJobs]; };
+struct WgradBatch { float* buf; size_t cap_floats, used; int n; ReduceJob jobs[kMaxReduceJobs]; };
+
 // conv_tc_kernels.cu (tcgen05 tensor-core path)
 bool conv3x3_tc_supported(int cin, int cout, int in_mode);
 int conv3x3_tc_pack_weights(int cin, int cout, int flip, int split, const float* w, void* wq,
@@ -71,7 +80,9 @@ bool conv3x3_wgrad_tc_supported(int cin, int cout, int in_mode);
 void conv3x3_wgrad_tc_set_chunk(int kc);   // upper bound: 512 (default), 256 or 128
 int conv3x3_wgrad_tc(int cin, int cout, int in_mode, int split, int N, int H, int W, const void* x,
                      const float* dy, float* dw, float* db, float* partial, size_t partial_bytes,
-                     int* err, cudaStream_t st);
+                     int* err, WgradBatch* batch, cudaStream_t st);
+int wgrad_reduce_batch(WgradBatch* b, cudaStream_t st);
+int conv3x3_tc_pack_weights_batch(const PackTable& t, int split, cudaStream_t st);
 void conv3x3_tc_set_tile(int mt);           // upper bound: 512 (default), 256 or 128
 int conv3x3_tc_forward(int cin, int cout, int in_mode, int split, int N, int H, int W, const void* in,
                        const void* wq, const float* bias, const float* mask, const float* res,

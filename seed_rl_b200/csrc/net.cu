@@ -90,13 +90,18 @@ struct Bump {
 
 struct StackBufs { size_t a0, p, idx, c0, o0, c1, o1; };
 
+// packed-weight slot: (hi + lo) x 9 x 32 x 32 bf16; deferred weight-gradient partials of all
+// 15 convs: 148 CTAs x 97 680 floats (57.8 MB) rounded up
+constexpr size_t kPackSlotBytes = 2 * 9 * 32 * 32 * 2;
+constexpr size_t kPartialAllBytes = (size_t)64 << 20;
+
 struct Plan {
   int N;                       // T1 * B frames
   std::vector<StackBufs> st;
   size_t sh_a1, sh_a2;         // shallow conv outputs (post-relu)
   size_t xc, z, hp, cs, hs, c0buf;
   // backward scratch
-  size_t dhs, dz, dhrec, dc0, dc1, dd, gA, gB, gC, gFull, wt, partial, wq, tcerr, counter, gemm_ws;
+  size_t dhs, dz, dhrec, dc0, dc1, dd, gA, gB, gC, gFull, wt, partial, wq, tcerr, counter, gemm_ws, wq_all, partial_all;
   size_t total;
 };
 
@@ -148,6 +153,8 @@ static Plan make_plan(const seedrl_net* n, int T1, int B) {
   p.wt = b.take(64 * 1024 * 4);
   p.wq = b.take(2 * 64 * 1024 * 2);
   p.gemm_ws = b.take(gemm_tc_workspace_bytes());
+  p.wq_all = b.take((size_t)kMaxPackJobs * kPackSlotBytes);
+  p.partial_all = b.take(kPartialAllBytes);
   p.tcerr = b.take(256);
   p.counter = b.take(256);
   p.partial = b.take(conv3x3_wgrad_partial_bytes());
@@ -183,6 +190,46 @@ static int run_gemm(const seedrl_net* n, void* ws, const Plan& pl, bool ta, bool
   return sgemm(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, e, st);
 }
 
+// Per-call context of the tensor-core path (thread-local: forward/backward of different nets
+// may run on different host threads): where the pre-packed weights of this call live and the
+// deferred weight-gradient reductions.
+struct StepCtx {
+  PackTable packed;
+  WgradBatch wb;
+};
+static thread_local StepCtx* t_ctx = nullptr;
+
+// Packs the weights of every conv of the deep torso with one launch: forward forms, or the
+// flipped/transposed forms of the data-gradient convolutions (all but the first layer).
+static int pack_all_weights(const seedrl_net* n, const float* prm, void* ws, const Plan& pl, int flip,
+                            StepCtx* ctx, cudaStream_t st) {
+  ctx->packed.n = 0;
+  if (n->conv_mode < 1 || n->cfg.net != SEEDRL_NET_DEEP) return SEEDRL_OK;
+  char* base = W<char>(ws, pl.wq_all);
+  for (size_t s = 0; s < n->stacks.size(); ++s) {
+    const Stack& k = n->stacks[s];
+    const ConvLayer* ls[5] = {&k.conv, &k.r00, &k.r01, &k.r10, &k.r11};
+    for (int i = 0; i < 5; ++i) {
+      const ConvLayer& l = *ls[i];
+      if (flip && s == 0 && i == 0) continue;          // no data gradient into the frames
+      const int cin = flip ? l.cout : l.cin, cout = flip ? l.cin : l.cout;
+      if (ctx->packed.n >= kMaxPackJobs) return SEEDRL_OK;
+      PackJob j;
+      j.w = P(n, prm, l.w);
+      j.wq = base + (size_t)ctx->packed.n * kPackSlotBytes;
+      j.ck = cin < 16 ? 16 : cin; j.cout = cout; j.cin_src = cin; j.flip = flip;
+      ctx->packed.jobs[ctx->packed.n++] = j;
+    }
+  }
+  return conv3x3_tc_pack_weights_batch(ctx->packed, n->conv_mode == 2, st);
+}
+static const void* find_packed(const float* w, int flip) {
+  if (!t_ctx) return nullptr;
+  for (int i = 0; i < t_ctx->packed.n; ++i)
+    if (t_ctx->packed.jobs[i].w == w && t_ctx->packed.jobs[i].flip == flip) return t_ctx->packed.jobs[i].wq;
+  return nullptr;
+}
+
 // One 3x3 'same' convolution of the schedule.  flip != 0: data-gradient (weights flipped and
 // transposed; cin/cout are those of the *gradient* convolution).  Dispatches to the tcgen05
 // kernel when the net runs in tensor-core mode and the shape is supported, else fp32 SIMT.
@@ -190,9 +237,13 @@ static int run_conv(const seedrl_net* n, void* ws, const Plan& pl, int cin, int 
                     int N, int H, int Wd, const void* in, const float* w, const float* bias,
                     const float* mask, const float* res, float* out, int flip, cudaStream_t st) {
   if (n->conv_mode >= 1 && conv3x3_tc_supported(cin, cout, in_mode)) {
-    void* wq = W<void>(ws, pl.wq);
     const int split = n->conv_mode == 2;
-    SEEDRL_TRY(conv3x3_tc_pack_weights(cin, cout, flip, split, w, wq, st));
+    const void* wq = find_packed(w, flip);
+    if (!wq) {
+      void* scratch = W<void>(ws, pl.wq);
+      SEEDRL_TRY(conv3x3_tc_pack_weights(cin, cout, flip, split, w, scratch, st));
+      wq = scratch;
+    }
     return conv3x3_tc_forward(cin, cout, in_mode, split, N, H, Wd, in, wq, bias, mask, res, out, 0,
                               W<int>(ws, pl.tcerr), st);
   }
@@ -367,7 +418,13 @@ extern "C" int seedrl_net_forward(const seedrl_net* n, const float* prm, int T1,
   const float* flat_src;
   int flat_relu;
   if (n->cfg.net == SEEDRL_NET_DEEP) {
-    SEEDRL_TRY(torso_forward_deep(n, prm, pl, observation, ws, st));
+    StepCtx ctx;
+    ctx.wb = WgradBatch{nullptr, 0, 0, 0, {}};
+    SEEDRL_TRY(pack_all_weights(n, prm, ws, pl, 0, &ctx, st));
+    t_ctx = &ctx;
+    const int rc_t = torso_forward_deep(n, prm, pl, observation, ws, st);
+    t_ctx = nullptr;
+    SEEDRL_TRY(rc_t);
     flat_src = W<float>(ws, pl.st.back().o1);
     flat_relu = 1;                         // tf.nn.relu before Flatten, networks.py:105
   } else {
@@ -437,7 +494,8 @@ static int conv_bwd(const seedrl_net* n, const float* prm, float* grd, const Con
   if (n->conv_mode >= 1 && conv3x3_wgrad_tc_supported(l.cin, l.cout, x_mode)) {
     SEEDRL_TRY(conv3x3_wgrad_tc(l.cin, l.cout, x_mode, n->conv_mode == 2, N, H, Wd, x, dy,
                                 G(n, grd, l.w), G(n, grd, l.b), W<float>(ws, pl.partial),
-                                conv3x3_wgrad_partial_bytes(), W<int>(ws, pl.tcerr), st));
+                                conv3x3_wgrad_partial_bytes(), W<int>(ws, pl.tcerr),
+                                t_ctx ? &t_ctx->wb : nullptr, st));
   } else {
     SEEDRL_TRY(conv3x3_wgrad(l.cin, l.cout, x_mode, N, H, Wd, x, dy, G(n, grd, l.w), G(n, grd, l.b),
                              W<float>(ws, pl.partial), conv3x3_wgrad_partial_bytes(), st));
@@ -565,7 +623,16 @@ extern "C" int seedrl_net_backward(const seedrl_net* n, const float* prm, int T1
   ef.mask = flat_src; ef.ldm = n->flat;
   SEEDRL_TRY(run_gemm(n, ws, pl, false, true, N, n->flat, kHidden, dd, kHidden, P(n, prm, n->p_dense_w), kHidden,
                    W<float>(ws, pl.gA), n->flat, ef, st));
-  if (n->cfg.net == SEEDRL_NET_DEEP) return torso_backward_deep(n, prm, grd, pl, observation, ws, st);
+  if (n->cfg.net == SEEDRL_NET_DEEP) {
+    StepCtx ctx;
+    ctx.wb = WgradBatch{W<float>(ws, pl.partial_all), kPartialAllBytes / sizeof(float), 0, 0, {}};
+    SEEDRL_TRY(pack_all_weights(n, prm, ws, pl, 1, &ctx, st));
+    t_ctx = &ctx;
+    int rc_t = torso_backward_deep(n, prm, grd, pl, observation, ws, st);
+    t_ctx = nullptr;
+    if (rc_t == SEEDRL_OK) rc_t = wgrad_reduce_batch(&ctx.wb, st);
+    return rc_t;
+  }
   return torso_backward_shallow(n, prm, grd, pl, observation, ws, st);
 }
 
@@ -642,7 +709,7 @@ extern "C" int seedrl_debug_conv3x3_wgrad_tc(int cin, int cout, int in_mode, int
                                              seedrl_stream_t stream) {
   SEEDRL_CHECK_ARG(conv3x3_wgrad_tc_supported(cin, cout, in_mode), "unsupported (cin,cout,mode)");
   return conv3x3_wgrad_tc(cin, cout, in_mode, split, N, H, W, x, dy, dw, db, partial, partial_bytes,
-                          error_flag, (cudaStream_t)stream);
+                          error_flag, nullptr, (cudaStream_t)stream);
 }
 // Bench knob: output positions per tile of the tensor-core forward / data-gradient kernel
 // (the largest of 512/256/128 not above `mt` that keeps >= 2 CTAs per SM is used; default 512).
