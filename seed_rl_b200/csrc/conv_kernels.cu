@@ -451,43 +451,70 @@ __global__ void maxpool3s2_fwd_kernel(int N, int H, int W, int C, int Ho, int Wo
 }
 
 // dx[n,h,w,c] = sum over the <=4 windows containing (h,w) whose argmax is (h,w).
-// One CTA per input row (n, h); the (at most two) output rows whose windows cover h are
-// resolved once per CTA.
+// A thread owns a 2x2 block of input pixels (padded coordinates hp in {2a, 2a+1}, wp in
+// {2b, 2b+1}) x 4 channels: the block is covered by exactly the four windows (a-1..a, b-1..b),
+// each loaded once (argmax byte + gradient) and scattered to the <= 9 (pixel, tap) pairs it
+// owns inside the block -- 2 loads per output instead of up to 8.  One CTA per row pair.
 __global__ void maxpool3s2_bwd_kernel(int N, int H, int W, int C, int Ho, int Wo, int pt, int pl,
                                       const float* __restrict__ dy, const uint8_t* __restrict__ idx,
                                       float* __restrict__ dx) {
   const int C4 = C >> 2;
-  const int row = blockIdx.x;                 // n * H + h
-  const int n = row / H, h = row - n * H;
-  const int j = blockIdx.y * blockDim.x + threadIdx.x;   // w * C4 + c4
-  if (j >= W * C4) return;
-  const int w = (C4 & (C4 - 1)) == 0 ? j >> (31 - __clz(C4)) : j / C4, c4 = j - w * C4;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  // windows: ho with ho*2 - pt <= h <= ho*2 - pt + 2
-  const int hp = h + pt, wp = w + pl;
+  const int npairs = (H + pt + 1) >> 1;
+  const int row = blockIdx.x;                 // n * npairs + a
+  const int n = row / npairs, a = row - n * npairs;
+  const int j = blockIdx.y * blockDim.x + threadIdx.x;   // b * C4 + c4
+  const int nbw = (W + pl + 1) >> 1;
+  if (j >= nbw * C4) return;
+  const int b = (C4 & (C4 - 1)) == 0 ? j >> (31 - __clz(C4)) : j / C4, c4 = j - b * C4;
   const float4* dyn = reinterpret_cast<const float4*>(dy) + (size_t)n * Ho * Wo * C4;
   const uchar4* idn = reinterpret_cast<const uchar4*>(idx) + (size_t)n * Ho * Wo * C4;
+  // acc[r][s]: pixel (hp = 2a + r, wp = 2b + s)
+  float4 acc[2][2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int q = 0; q < 2; ++q) acc[r][q] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int dh = 0; dh < 2; ++dh) {
-    const int ho = ((hp - 1) >> 1) + dh;
-    const int kh = hp - ho * 2;
-    if (ho < 0 || ho >= Ho || kh < 0 || kh > 2 || (dh == 1 && ho > (hp >> 1))) continue;
+    const int ho = a - 1 + dh;
+    if (ho < 0 || ho >= Ho) continue;
 #pragma unroll
     for (int dw = 0; dw < 2; ++dw) {
-      const int wo = ((wp - 1) >> 1) + dw;
-      const int kw = wp - wo * 2;
-      if (wo < 0 || wo >= Wo || kw < 0 || kw > 2 || (dw == 1 && wo > (wp >> 1))) continue;
+      const int wo = b - 1 + dw;
+      if (wo < 0 || wo >= Wo) continue;
       const int o = (ho * Wo + wo) * C4 + c4;
-      const uchar4 a = __ldg(idn + o);
+      const uchar4 t = __ldg(idn + o);
       const float4 g = __ldg(dyn + o);
-      const unsigned char t = (unsigned char)(kh * 3 + kw);
-      if (a.x == t) acc.x += g.x;
-      if (a.y == t) acc.y += g.y;
-      if (a.z == t) acc.z += g.z;
-      if (a.w == t) acc.w += g.w;
+      // window (ho, wo) covers hp = 2ho..2ho+2: inside the block that is kh = 2 (row 0) for
+      // ho = a-1, kh = 0 (row 0) and 1 (row 1) for ho = a; same along w.
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int kh = dh == 0 ? (r == 0 ? 2 : -1) : r;
+        if (kh < 0) continue;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int kw = dw == 0 ? (q == 0 ? 2 : -1) : q;
+          if (kw < 0) continue;
+          const unsigned char tap = (unsigned char)(kh * 3 + kw);
+          if (t.x == tap) acc[r][q].x += g.x;
+          if (t.y == tap) acc[r][q].y += g.y;
+          if (t.z == tap) acc[r][q].z += g.z;
+          if (t.w == tap) acc[r][q].w += g.w;
+        }
+      }
     }
   }
-  reinterpret_cast<float4*>(dx)[(size_t)row * W * C4 + j] = acc;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int h = 2 * a + r - pt;
+    if (h < 0 || h >= H) continue;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int w = 2 * b + q - pl;
+      if (w < 0 || w >= W) continue;
+      reinterpret_cast<float4*>(dx)[((size_t)(n * H + h) * W + w) * C4 + c4] = acc[r][q];
+    }
+  }
 }
 
 static void same_pad(int n, int k, int s, int* out, int* before) {
@@ -520,9 +547,10 @@ int maxpool3s2_backward(int N, int H, int W, int C, const float* dy, const uint8
   same_pad(W, 3, 2, &Wo, &pl);
   const long long total = (long long)N * H * W * (C / 4);
   (void)total;
-  const int per_row = W * (C / 4);
+  const int per_row = ((W + pl + 1) / 2) * (C / 4);
   const int threads = per_row >= 256 ? 256 : ((per_row + 31) / 32) * 32;
-  maxpool3s2_bwd_kernel<<<dim3((unsigned)(N * H), (unsigned)ceil_div(per_row, threads)), threads, 0, st>>>(
+  const int npairs = (H + pt + 1) / 2;
+  maxpool3s2_bwd_kernel<<<dim3((unsigned)(N * npairs), (unsigned)ceil_div(per_row, threads)), threads, 0, st>>>(
       N, H, W, C, Ho, Wo, pt, pl, dy, idx, dx);
   count_launch(PC_POOL, st);
   SEEDRL_CHECK_LAUNCH();
