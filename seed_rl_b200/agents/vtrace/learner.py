@@ -231,3 +231,52 @@ class LearnerStep(object):
     loss, logs = self.compute_gradients(unroll)
     self.apply_gradients()
     return loss, logs
+
+
+class DeviceFeeder(object):
+  """Double-buffered host -> device feed of training batches (the role tf.data prefetching
+  onto the accelerator plays for the reference's `minimize(it)`, learner.py:457-466).
+
+  `put(pinned)` enqueues the H2D copies of one batch (a dict of pinned host tensors) on a
+  private copy stream into the slot the learner is not using; `get()` returns the dict of
+  device tensors of the oldest pending batch and makes the current (compute) stream wait for
+  its copies.  While step i trains from one slot, batch i+1 streams into the other, so the
+  upload is hidden behind the step instead of serialised in front of it."""
+
+  def __init__(self, example, device='cuda', slots=2):
+    self._slots = [{k: torch.empty_like(v, device=device) for k, v in example.items()} for _ in range(slots)]
+    self._copied = [torch.cuda.Event() for _ in range(slots)]
+    self._consumed = [None] * slots
+    self._stream = torch.cuda.Stream(device=device)
+    self._put = 0
+    self._get = 0
+
+  @property
+  def slots(self):
+    return self._slots
+
+  def put(self, pinned):
+    if self._put - self._get >= len(self._slots):
+      raise RuntimeError('DeviceFeeder: every slot holds an unconsumed batch')
+    s = self._put % len(self._slots)
+    with torch.cuda.stream(self._stream):
+      if self._consumed[s] is not None:
+        self._stream.wait_event(self._consumed[s])     # the step that read this slot has finished
+      for k, v in pinned.items():
+        self._slots[s][k].copy_(v, non_blocking=True)
+      self._copied[s].record(self._stream)
+    self._put += 1
+
+  def get(self):
+    if self._get >= self._put:
+      raise RuntimeError('DeviceFeeder: no batch pending')
+    s = self._get % len(self._slots)
+    torch.cuda.current_stream().wait_event(self._copied[s])
+    self._get += 1
+    return s, self._slots[s]
+
+  def done_with(self, slot):
+    """Call after the step that consumed `slot` has been enqueued on the compute stream."""
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream())
+    self._consumed[slot] = ev

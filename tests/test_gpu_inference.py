@@ -178,3 +178,25 @@ def test_served_through_rpc_and_batcher(tmp_path):
   for out in results.values():
     assert all(o.shape == (2,) and o.dtype == np.int64 for o in out)
   assert host.unroll_queue.size() == num_envs      # every env completed one unroll
+
+
+def test_device_feeder_double_buffering():
+  """learner.DeviceFeeder: batches come out in order with the uploaded contents; a third put
+  without a get is refused; a slot is only overwritten after its consumer was marked done."""
+  from seed_rl_b200.agents.vtrace import learner
+  mk = lambda v: {'a': torch.full((1 << 20,), float(v)).pin_memory(), 'b': torch.full((3, 5), v, dtype=torch.int64).pin_memory()}
+  f = learner.DeviceFeeder(mk(0))
+  f.put(mk(1)); f.put(mk(2))
+  with pytest.raises(RuntimeError):
+    f.put(mk(3))
+  seen = []
+  for nxt in (3, 4, 5, None, None):
+    slot, d = f.get()
+    acc = d['a'].sum() / d['a'].numel() + d['b'].float().mean()     # consume on the compute stream
+    f.done_with(slot)
+    if nxt is not None:
+      f.put(mk(nxt))
+    seen.append(float(acc))
+  assert seen == [2.0, 4.0, 6.0, 8.0, 10.0]
+  with pytest.raises(RuntimeError):
+    f.get()
