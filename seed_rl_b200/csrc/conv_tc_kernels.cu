@@ -88,6 +88,11 @@ int conv3x3_tc_pack_weights_batch(const PackTable& t, int split, cudaStream_t st
 
 constexpr int kTcThreads = 256;
 constexpr int kTcM = 128;
+#ifndef SEEDRL_TC_MIN_BLOCKS
+#define SEEDRL_TC_MIN_BLOCKS 4
+#endif
+constexpr int kTcMinBlocks = SEEDRL_TC_MIN_BLOCKS;   // resident CTAs per SM the register budget targets
+                                                     // (one fewer for 32 input channels: measured)
 
 // One tile = MT consecutive output positions (MT / 128 UMMA row blocks, one TMEM accumulator
 // each); the staged input covers MT + 2*PW + 2 positions, so the halo re-read and the
@@ -100,7 +105,7 @@ constexpr int kTcM = 128;
 // K-group re-reads it (LBO = 0) against zero weights; exact in bf16 (no lo plane); the 1/255
 // scale is applied to the accumulator.
 template <int CIN, int COUT, int IN_MODE, bool SPLIT, int MT>
-__global__ void __launch_bounds__(kTcThreads, COUT <= 16 ? 4 : 3)
+__global__ void __launch_bounds__(kTcThreads, CIN >= 32 ? kTcMinBlocks - 1 : kTcMinBlocks)
 conv3x3_tc_kernel(ConvGeom g, const void* __restrict__ in_, const uint4* __restrict__ wq,
                   const float* __restrict__ bias, const float* __restrict__ mask,
                   const float* __restrict__ res, float* __restrict__ out, int variant,
@@ -254,29 +259,32 @@ conv3x3_tc_kernel(ConvGeom g, const void* __restrict__ in_, const uint4* __restr
     }
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
-    // ---- epilogue: TMEM lane (= position) -> registers -> fp32 NHWC -----------------------
+    // ---- epilogue: TMEM lane (= position) -> registers -> fp32 NHWC, 16 channels at a time ---
     for (int m = warp >> 2; m < NSUB; m += kTcThreads / 128) {
       const int q = warp & 3;
-      float acc[COUT];
-      tmem_ld<COUT>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * COUT), acc);
       const int pix = out_pixel(g, q0 + m * kTcM + q * 32 + lane);
-      if (pix >= 0) {
-        const size_t o = (size_t)pix * COUT;
 #pragma unroll
-        for (int c4 = 0; c4 < COUT / 4; ++c4) {
-          const float4 bq = reinterpret_cast<const float4*>(s_bias)[c4];     // broadcast read
-          float4 v = make_float4(fmaf(acc[c4 * 4 + 0], oscale, bq.x), fmaf(acc[c4 * 4 + 1], oscale, bq.y),
-                                 fmaf(acc[c4 * 4 + 2], oscale, bq.z), fmaf(acc[c4 * 4 + 3], oscale, bq.w));
-          if (mask) {
-            const float4 mk = __ldg(reinterpret_cast<const float4*>(mask + o) + c4);
-            v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f;
-            v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
+      for (int hc = 0; hc < COUT / 16; ++hc) {
+        float acc[16];
+        tmem_ld<16>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * COUT + hc * 16), acc);
+        if (pix >= 0) {
+          const size_t o = (size_t)pix * COUT + hc * 16;
+#pragma unroll
+          for (int c4 = 0; c4 < 4; ++c4) {
+            const float4 bq = reinterpret_cast<const float4*>(s_bias)[hc * 4 + c4];     // broadcast read
+            float4 v = make_float4(fmaf(acc[c4 * 4 + 0], oscale, bq.x), fmaf(acc[c4 * 4 + 1], oscale, bq.y),
+                                   fmaf(acc[c4 * 4 + 2], oscale, bq.z), fmaf(acc[c4 * 4 + 3], oscale, bq.w));
+            if (mask) {
+              const float4 mk = __ldg(reinterpret_cast<const float4*>(mask + o) + c4);
+              v.x = mk.x > 0.f ? v.x : 0.f; v.y = mk.y > 0.f ? v.y : 0.f;
+              v.z = mk.z > 0.f ? v.z : 0.f; v.w = mk.w > 0.f ? v.w : 0.f;
+            }
+            if (res) {
+              const float4 r = __ldg(reinterpret_cast<const float4*>(res + o) + c4);
+              v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+            }
+            reinterpret_cast<float4*>(out + o)[c4] = v;
           }
-          if (res) {
-            const float4 r = __ldg(reinterpret_cast<const float4*>(res + o) + c4);
-            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
-          }
-          reinterpret_cast<float4*>(out + o)[c4] = v;
         }
       }
     }
