@@ -88,6 +88,12 @@ int conv3x3_tc_pack_weights_batch(const PackTable& t, int split, cudaStream_t st
 
 constexpr int kTcThreads = 256;
 constexpr int kTcM = 128;
+#ifndef SEEDRL_TC_ITEMS_U8
+#define SEEDRL_TC_ITEMS_U8 4
+#endif
+#ifndef SEEDRL_TC_ITEMS_G2
+#define SEEDRL_TC_ITEMS_G2 4
+#endif
 #ifndef SEEDRL_TC_MIN_BLOCKS
 #define SEEDRL_TC_MIN_BLOCKS 4
 #endif
@@ -117,6 +123,7 @@ conv3x3_tc_kernel(ConvGeom g, const void* __restrict__ in_, const uint4* __restr
   constexpr int SA = ASPLIT ? 2 : 1, SB = SPLIT ? 2 : 1;
   constexpr int NSUB = MT / kTcM;
   constexpr int TCOLS = NSUB * COUT <= 32 ? 32 : (NSUB * COUT <= 64 ? 64 : 128);
+  constexpr int IT = IN_MODE == IN_U8 ? SEEDRL_TC_ITEMS_U8 : (G == 2 ? SEEDRL_TC_ITEMS_G2 : 4);
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int PW = g.PW;
   const int L = MT + 2 * PW + 2;      // staged input positions
@@ -160,44 +167,47 @@ conv3x3_tc_kernel(ConvGeom g, const void* __restrict__ in_, const uint4* __restr
   for (int ch = blockIdx.x; ch < nchunks; ch += gridDim.x) {
     const int q0 = ch * MT;
     // ---- stage the input tile: NHWC -> bf16 channel-group planes ---------------------------
-    // 4 items per thread per round: all loads of a round are issued before any is consumed
-    for (int i0 = tid; i0 < L * G; i0 += 4 * kTcThreads) {
-      float4 va[4], vb[4];
-      uint32_t vw[4];
+    // IT items per thread per round: all loads of a round are issued before any is consumed
+    // (measured: 3, 4, 5 or 8 items per round give the same time -- with 3-4 CTAs per SM the
+    // round latency is hidden by the other CTAs)
+    for (int i0 = tid; i0 < L * G; i0 += IT * kTcThreads) {
+      float4 va[IN_MODE == IN_U8 ? 1 : IT], vb[IN_MODE == IN_U8 ? 1 : IT];
+      uint32_t vw[IN_MODE == IN_U8 ? IT : 1];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < IT; ++k) {
         const int i = i0 + k * kTcThreads;
-        va[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        vb[k] = va[k];
-        vw[k] = 0u;
+        constexpr bool U8 = IN_MODE == IN_U8;
+        va[U8 ? 0 : k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        vb[U8 ? 0 : k] = va[U8 ? 0 : k];
+        vw[U8 ? k : 0] = 0u;
         if (i < L * G) {
           const int s = i / G, gch = i - s * G;
           const int pix = in_pixel(g, q0 + s);
           if (pix >= 0) {
             if (IN_MODE == IN_U8) {
-              vw[k] = __ldg(inu + pix);
+              vw[IN_MODE == IN_U8 ? k : 0] = __ldg(inu + pix);
             } else {
               const float4* src = reinterpret_cast<const float4*>(inf + (size_t)pix * CIN + gch * 8);
-              va[k] = __ldg(src);
-              vb[k] = __ldg(src + 1);
+              va[IN_MODE == IN_U8 ? 0 : k] = __ldg(src);
+              vb[IN_MODE == IN_U8 ? 0 : k] = __ldg(src + 1);
             }
           }
         }
       }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < IT; ++k) {
         const int i = i0 + k * kTcThreads;
         if (i < L * G) {
           const int s = i / G, gch = i - s * G;
           if (IN_MODE == IN_U8) {
-            const uint32_t w = vw[k];     // byte k -> float without I2F: 0x4B0000kk is 2^23 + kk
+            const uint32_t w = vw[IN_MODE == IN_U8 ? k : 0];     // byte k -> float without I2F: 0x4B0000kk is 2^23 + kk
             s_a[s] = pack8_bf16(make_float4(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)) - 8388608.0f,
                                             __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541)) - 8388608.0f,
                                             __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7542)) - 8388608.0f,
                                             __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7543)) - 8388608.0f),
                                 make_float4(0.f, 0.f, 0.f, 0.f));
           } else {
-            float4 a = va[k], b = vb[k];
+            float4 a = va[IN_MODE == IN_U8 ? 0 : k], b = vb[IN_MODE == IN_U8 ? 0 : k];
             if (IN_MODE == IN_RELU) {
               a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f);
               b.x = fmaxf(b.x, 0.f); b.y = fmaxf(b.y, 0.f); b.z = fmaxf(b.z, 0.f); b.w = fmaxf(b.w, 0.f);
