@@ -132,7 +132,7 @@ class ClockSampler(object):
     self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
     try:
       self.p = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
-                                 '-lms', '100', '-i', str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                 '-lms', '20', '-i', str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
     except Exception:
       self.p = None
 

@@ -18,6 +18,8 @@
 // Epilogue: tcgen05.ld (thread = one row, 16 columns at a time) -> bias / relu / mask /
 // accumulate -> C, or -> the split-K workspace, reduced in slice order by
 // gemm_tc_reduce_kernel (deterministic).
+#include <cstdlib>
+
 #include "kernels.h"
 #include "tc_common.cuh"
 
@@ -241,19 +243,37 @@ gemm_tc_kernel(const GemmTcParams p) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tcols));
 }
 
-// C = epilogue(sum_z ws[z]) in slice order.
+// C = epilogue(sum_z ws[z]) in slice order.  VEC: four columns per thread (N % 4 == 0; the
+// partial planes are then 16-byte aligned), all `splits` loads of a thread independent.
+template <bool VEC>
 __global__ void gemm_tc_reduce_kernel(int M, int N, int splits, const float* __restrict__ ws,
                                       float* __restrict__ C, int ldc, GemmEpi e) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int W = VEC ? 4 : 1;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) * W;
   if (i >= M * N) return;
   const int m = i / N, n = i - m * N;
-  float x = 0.f;
-  for (int z = 0; z < splits; ++z) x += ws[(size_t)z * M * N + i];
-  if (e.bias) x += __ldg(e.bias + n);
-  if (e.relu) x = fmaxf(x, 0.f);
-  if (e.mask) x = __ldg(e.mask + (size_t)m * e.ldm + n) > 0.f ? x : 0.f;
-  float* c = C + (size_t)m * ldc + n;
-  *c = e.accumulate ? *c + x : x;
+  float x[W];
+#pragma unroll
+  for (int j = 0; j < W; ++j) x[j] = 0.f;
+  const size_t plane = (size_t)M * N;
+#pragma unroll 4
+  for (int z = 0; z < splits; ++z) {
+    if (VEC) {
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(ws + (size_t)z * plane + i));
+      x[0] += v.x; x[W > 1 ? 1 : 0] += v.y; x[W > 2 ? 2 : 0] += v.z; x[W > 3 ? 3 : 0] += v.w;
+    } else {
+      x[0] += __ldcs(ws + (size_t)z * plane + i);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < W; ++j) {
+    float v = x[j];
+    if (e.bias) v += __ldg(e.bias + n + j);
+    if (e.relu) v = fmaxf(v, 0.f);
+    if (e.mask) v = __ldg(e.mask + (size_t)m * e.ldm + n + j) > 0.f ? v : 0.f;
+    float* c = C + (size_t)m * ldc + n + j;
+    *c = e.accumulate ? *c + v : v;
+  }
 }
 
 bool gemm_tc_supported(int M, int N, int K) { return M >= 64 && N >= 16 && K >= 32; }
@@ -282,7 +302,8 @@ int gemm_tc(bool ta, bool tb, int split, int M, int N, int K, const float* A, in
   // split-K until the grid covers the SMs, keeping >= 4 K-blocks per slice and the
   // partials inside the workspace
   int splits = 1;
-  while (tiles * splits < 2 * kNumSMs && nkb / (splits * 2) >= 2 &&
+  static const int waves = getenv("SEEDRL_GEMM_WAVES") ? atoi(getenv("SEEDRL_GEMM_WAVES")) : 1;   // tuning knob
+  while (tiles * splits < waves * kNumSMs && nkb / (splits * 2) >= 2 &&
          (size_t)(splits * 2) * M * N * sizeof(float) <= ws_bytes && ws)
     splits *= 2;
   p.kblocks_per_split = ceil_div(nkb, splits);
@@ -318,7 +339,10 @@ int gemm_tc(bool ta, bool tb, int split, int M, int N, int K, const float* A, in
   count_launch(PC_GEMM, st);
   SEEDRL_CHECK_LAUNCH();
   if (splits > 1) {
-    gemm_tc_reduce_kernel<<<ceil_div(M * N, 256), 256, 0, st>>>(M, N, splits, ws, C, ldc, e);
+    if ((N & 3) == 0)
+      gemm_tc_reduce_kernel<true><<<ceil_div(M * N / 4, 256), 256, 0, st>>>(M, N, splits, ws, C, ldc, e);
+    else
+      gemm_tc_reduce_kernel<false><<<ceil_div(M * N, 256), 256, 0, st>>>(M, N, splits, ws, C, ldc, e);
     count_launch(PC_GEMM, st);
     SEEDRL_CHECK_LAUNCH();
   }
