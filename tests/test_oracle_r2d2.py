@@ -1,0 +1,80 @@
+"""CPU: the R2D2 oracle (test infrastructure for the next round's CUDA
+path) against (i) the known-answer cases of the reference's own tests
+(agents/r2d2/learner_test.py:60-70, 114-198) and (ii) tests/golden/r2d2_golden.npz = outputs
+of the unmodified reference functions executed over the numpy shim."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import r2d2_oracle as R
+
+G = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'r2d2_golden.npz'))
+col = lambda *v: np.array([v], np.float32).T
+
+
+def test_value_function_rescaling_reference_cases():          # learner_test.py:114-140
+  for x in np.linspace(-100., 100.):
+    np.testing.assert_allclose(R.inverse_value_function_rescaling(R.value_function_rescaling(x)), x,
+                               rtol=1e-6 * 100, atol=2e-4)
+  assert R.value_function_rescaling(0.) == 0 and R.inverse_value_function_rescaling(0.) == 0
+  assert R.value_function_rescaling(1000.) > 10. and R.value_function_rescaling(-1000.) < -10.
+  np.testing.assert_allclose(R.value_function_rescaling([0., 3., -3.]), [0., 1 + 3e-3, -1 - 3e-3], rtol=1e-6)
+  np.testing.assert_allclose(R.inverse_value_function_rescaling([0., 1 + 3e-3, -1 - 3e-3]), [0., 3, -3], atol=2e-4)
+
+
+def test_value_function_rescaling_golden():
+  np.testing.assert_array_equal(R.value_function_rescaling(G['resc_x']), G['resc_h'])
+  np.testing.assert_allclose(R.inverse_value_function_rescaling(G['resc_x']), G['resc_hinv'], rtol=1e-6, atol=1e-6)
+
+
+def test_n_step_bellman_target_reference_cases():             # learner_test.py:142-198
+  t = R.n_step_bellman_target(col(1., 2., 3.), col(0, 0, 0) > 0, col(100, 200, 300), 0.9, 1)
+  np.testing.assert_allclose(t, col(1 + 0.9 * 100, 2 + 0.9 * 200, 3 + 0.9 * 300), rtol=1e-6)
+  t = R.n_step_bellman_target(col(1., 2., 3.), col(0, 1, 0) > 0, col(100, 200, 300), 0.9, 1)
+  np.testing.assert_allclose(t, col(1 + 0.9 * 100, 2, 3 + 0.9 * 300), rtol=1e-6)
+  t = R.n_step_bellman_target(col(1., 2., 3.), col(0, 0, 0) > 0, col(100, 200, 300), 0.9, 2)
+  np.testing.assert_allclose(t, col(1 + 0.9 * 2 + 0.9 ** 2 * 200, 2 + 0.9 * 3 + 0.9 ** 2 * 300, 3 + 0.9 * 300),
+                             rtol=1e-6)
+  t = R.n_step_bellman_target(col(1., 2., 3., 4., 5., 6., 7.), col(0, 0, 0, 1, 0, 0, 0) > 0,
+                              col(100, 200, 300, 400, 500, 600, 700), 0.9, 3)
+  np.testing.assert_allclose(t, col(
+      1 + 0.9 * 2 + 0.9 ** 2 * 3 + 0.9 ** 3 * 300, 2 + 0.9 * 3 + 0.9 ** 2 * 4, 3 + 0.9 * 4, 4,
+      5 + 0.9 * 6 + 0.9 ** 2 * 7 + 0.9 ** 3 * 700, 6 + 0.9 * 7 + 0.9 ** 2 * 700, 7 + 0.9 * 700), rtol=1e-6)
+
+
+@pytest.mark.parametrize('name', ['a', 'b', 'c', 'd'])
+def test_n_step_bellman_target_golden(name):
+  r, d, q = G['nstep_%s_in' % name]
+  n, gamma = G['nstep_%s_cfg' % name]
+  got = R.n_step_bellman_target(r, d > 0, q, float(gamma), int(n))
+  np.testing.assert_allclose(got, G['nstep_%s_out' % name], rtol=2e-6, atol=1e-6)
+
+
+def test_loss_and_priorities_golden():
+  loss, prio, abs_td = R.loss_and_priorities(G['loss_train_q'], G['loss_train_action'], G['loss_target_q'],
+                                             G['loss_replay_action'], G['loss_reward'], G['loss_done'], 0.997)
+  np.testing.assert_allclose(loss, G['loss_out'], rtol=1e-5)
+  np.testing.assert_allclose(prio, G['loss_priorities'], rtol=1e-5)
+  assert abs_td.shape == (15, 6)
+
+
+def test_get_envs_epsilon():                                   # learner_test.py:60-70
+  e = R.get_envs_epsilon(np.arange(20), 10, 10, 1e-3)
+  np.testing.assert_allclose(e[10:], [1e-3] * 10, rtol=1e-6)
+  np.testing.assert_allclose(e[0], 0.4, rtol=1e-6)
+  np.testing.assert_allclose(e[9], 0.4 ** 8, rtol=1e-5)
+  np.testing.assert_allclose(e, G['eps_out'], rtol=1e-6)
+
+
+def test_prioritized_replay_probabilities_and_weights():       # common/utils.py:327-352
+  prio = np.array([1., 2., 4., 0., 0.], np.float32)            # ring of 5, three inserted
+  p = R.replay_probabilities(prio, 3, 0.5)
+  np.testing.assert_allclose(p, np.sqrt([1., 2., 4.]) / np.sqrt([1., 2., 4.]).sum(), rtol=1e-6)
+  w = R.replay_importance_weights(p, [0, 2, 2, 1], 0.6)
+  raw = ((1. / 3) / p[[0, 2, 2, 1]]) ** 0.6
+  np.testing.assert_allclose(w, raw / raw.max(), rtol=1e-6)
+  assert w.max() == 1.0
+  np.testing.assert_array_equal(R.replay_insert_indices(3, 4, 5), [3, 4, 0, 1])
+  # full ring: every slot counts
+  assert len(R.replay_probabilities(np.ones(5, np.float32), 9, 1.0)) == 5
