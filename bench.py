@@ -449,6 +449,43 @@ def main():
       line['cpu_baseline'] = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
                               'sample': r['sample'], 'ms_per_step': r['ms_per_step']}
 
+    if rank == 0 and world == 1 and args.net == 'deep' and args.conv != 'simt':
+      # ---- the single most time-consuming kernel instance of the step, alone: the 16->16
+      # conv @42x42 on all T1*B frames (8 launches/step as forward + data gradient).  Launch
+      # time measured live with CUDA events (10 back-to-back launches, working set 289 MB >> L2);
+      # `traffic` is the DRAM byte count of the same kernel from the committed ncu capture.
+      # Runs LAST and guarded: a failure here must never cost the bench line.
+      try:
+        Nf, Hh, Cc = T1 * B, 42, 16
+        xk = torch.randn(Nf, Hh, Hh, Cc, device='cuda'); wk = torch.randn(3, 3, Cc, Cc, device='cuda') * 0.1
+        bk = torch.zeros(Cc, device='cuda'); ok = torch.empty(Nf, Hh, Hh, Cc, device='cuda')
+        wqk = torch.empty(2 * 9 * 16 * Cc * 2, dtype=torch.uint8, device='cuda')
+        errk = torch.zeros(1, dtype=torch.int32, device='cuda')
+        splitk = 1 if args.conv == 'tc3' else 0
+
+        def conv_once():
+          _lib.check(L.seedrl_debug_conv3x3_tc(Cc, Cc, 1, splitk, Nf, Hh, Hh, _lib.ptr(xk), _lib.ptr(wk),
+                                               _lib.ptr(bk), None, None, _lib.ptr(ok), 0, 0, _lib.ptr(wqk),
+                                               _lib.ptr(errk), _lib.stream_ptr()))
+        for _ in range(3):
+          conv_once()
+        ms_k = timed(conv_once, 10)
+        alg = 2.0 * Nf * Hh * Hh * Cc * 4
+        line['roofline_dominant_kernel'] = {
+            'kernel': 'conv3x3_tc_kernel<16,16,relu-in,%s,512> N=%d 42x42 (+ its 3 us weight-pack launch)' %
+                      ('bf16x3' if splitk else 'bf16', Nf),
+            'bound': 'hbm', 'algorithmic_bytes_per_launch': alg, 'avg_launch_ms': ms_k,
+            'achieved': alg / (ms_k * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
+            'frac': alg / (ms_k * 1e-3) / 1e9 / hbm_peak,
+            'traffic': 254415104 if not splitk else None,
+            'traffic_source': 'profiles/r01_ncu_conv_fwd_16_16.txt: dram read 151.78 MB + write 102.63 MB '
+                              '(the rest of the 144.5 MB output was still in L2 when the kernel ended)',
+            'launches_per_step': 8, 'ok': int(errk.item()) == 0}
+        del xk, ok
+      except Exception as exc:        # pylint: disable=broad-except
+        line['roofline_dominant_kernel'] = {'unavailable': repr(exc)[:200]}
+
+
   if rank == 0:
     emit(line)
   if world > 1:
