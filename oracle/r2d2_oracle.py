@@ -9,8 +9,9 @@ Follows the reference line by line (paths relative to the reference repository):
   compute_loss_and_priorities_from_agent_outputs   agents/r2d2/learner.py:258-330
   get_envs_epsilon                       agents/r2d2/learner.py:129-152
   PrioritizedReplay probabilities / importance weights   common/utils.py:327-352
+  stack_frames (bit-packed frame stacking)               atari/networks.py:33-173
 Pinned (tests/test_oracle_r2d2.py) against the known-answer cases of
-agents/r2d2/learner_test.py:60-70,114-198 and against tests/golden/r2d2_golden.npz, produced
+agents/r2d2/learner_test.py:60-70,114-198, atari/networks_test.py:176-247 and against tests/golden/r2d2_golden.npz, produced
 by executing the UNMODIFIED reference functions over tests/golden/tf_numpy_shim.py
 (tests/golden/make_golden_r2d2.py).  What stays unpinned: tf.random.categorical's Philox
 stream (sampling is statistical in the reference's own tests too).
@@ -98,3 +99,49 @@ def replay_importance_weights(prob, indices, importance_sampling_exponent):
 def replay_insert_indices(num_inserted, append_size, size):
   """common/utils.py:296-303: FIFO ring insertion indices."""
   return np.arange(num_inserted, num_inserted + append_size) % size
+
+
+def stack_frames(frames, frame_stacking_state, done, stack_size):
+  """atari/networks.py:57-173.  frames f32 [T,B,...obs,1] in [0,255]; state int32
+  [B, prod(obs)] bit-packed (LSB byte = oldest of the stack_size-1 kept frames); done bool
+  [T,B].  Returns (stacked f32 [T,B,...obs,stack_size], newest first, frames across an
+  episode boundary zeroed; new int32 state [B, prod(obs)]).  Byte/integer work: bit-exact."""
+  frames = np.asarray(frames, F); done = np.asarray(done, bool)
+  if frames.shape[0:2] != done.shape[0:2]:
+    raise ValueError('Expected same first 2 dims for frames and dones. Got {} vs {}.'.format(
+        frames.shape[0:2], done.shape[0:2]))
+  if stack_size > 4:
+    raise ValueError('Only up to stack size 4 is supported due to bit-packing.')
+  if stack_size > 1 and frames.shape[-1] != 1:
+    raise ValueError('Due to frame stacking, we require last observation dimension to be 1. Got {}'.format(
+        frames.shape[-1]))
+  if stack_size == 1:
+    return frames, ()
+  T, B = frames.shape[:2]
+  obs_shape = frames.shape[2:-1]
+  state = np.asarray(frame_stacking_state)
+  if state.dtype != np.int32:
+    raise ValueError('Expected dtype int32 got {}'.format(state.dtype))
+  state = state.reshape((B,) + obs_shape)
+  # unpacked previous frames, oldest first (:113-119)
+  prev = [((state >> (8 * i)) & 0xFF).astype(F) for i in range(stack_size - 1)]
+  ext = np.concatenate([p.reshape((1,) + p.shape + (1,)) for p in prev] + [frames], axis=0)   # :124-128
+  stacked = np.concatenate([ext[stack_size - 1 - i: ext.shape[0] - i] for i in range(stack_size)], axis=-1)  # :135-138
+  # masks of frames that cross an episode boundary (:143-168)
+  row = done.reshape(done.shape + (1,) * (frames.ndim - 2))
+  masks = [np.zeros_like(row), row]
+  while len(masks) < stack_size:
+    p = masks[-1]
+    masks.append(p | np.concatenate([np.zeros_like(p[:1]), p[:-1]], axis=0))
+  stacked = np.where(np.concatenate(masks, axis=-1), F(0), stacked).astype(F)
+  # new bit-packed state from the zeroed stack: MSB byte = newest (:175-183)
+  shifts = np.array([8 * i for i in range(stack_size - 2, -1, -1)], np.int32)
+  new_state = (stacked[-1, ..., :-1].astype(np.int32) << shifts).sum(axis=-1, dtype=np.int32)
+  return stacked, new_state.reshape(B, int(np.prod(obs_shape)))
+
+
+def initial_frame_stacking_state(stack_size, batch_size, observation_shape):
+  """atari/networks.py:33-54."""
+  if stack_size == 1:
+    return ()
+  return np.zeros([batch_size, int(np.prod(observation_shape))], np.int32)

@@ -37,7 +37,38 @@ def extend(tf):
   tf.linspace = lambda a, b, num: T(np.linspace(a, b, num, dtype=f32))
   tf.constant = lambda v, dtype=None: T(np.asarray(v, f32 if dtype is None else dtype))
   tf.gather = lambda p, i: T(np.asarray(raw(p))[np.asarray(raw(i))])
-  # scalar-with-Tensor arithmetic the reference writes as `1. - tensor`, `eps * x`, ...
+  # ---- ops of atari/networks.py:57-173 (stack_frames) ----
+  class _Sh(list):                      # TensorShape-like: list with rank / num_elements
+    @property
+    def rank(self): return len(self)
+    def num_elements(self): return int(np.prod(self)) if len(self) else 1
+    def __getitem__(self, i):
+      r = list.__getitem__(self, i)
+      return _Sh(r) if isinstance(i, slice) else r
+    def __add__(self, o): return _Sh(list(self) + list(o))
+    def __radd__(self, o): return _Sh(list(o) + list(self))
+  class T2(T):
+    @property
+    def shape(self): return _Sh(self.a.shape)
+    def __getitem__(self, idx): return T2(self.a[idx])
+  tf._T2 = T2
+  tf.reshape = lambda x, shape: T2(np.reshape(raw(x), [int(v) for v in shape]))
+  tf.bitwise = types.ModuleType('bitwise')
+  tf.bitwise.right_shift = lambda x, n: T2(np.right_shift(raw(x), n))
+  tf.bitwise.left_shift = lambda x, n: T2(np.left_shift(raw(x), np.asarray(n, np.int32)))
+  tf.bitwise.bitwise_and = lambda x, m: T2(np.bitwise_and(raw(x), m))
+  tf.zeros = lambda shape, dtype=np.float32: T2(np.zeros([int(v) for v in shape], dtype))
+  tf.math.logical_or = lambda a, b: T2(np.logical_or(raw(a), raw(b)))
+  tf.pad = lambda x, pads: T2(np.pad(raw(x), pads))
+  tf.where = lambda c, a, b: T2(np.where(raw(c), raw(a), raw(b)))
+  _old_concat = tf.concat
+  tf.concat = lambda values, axis, name=None: T2(np.concatenate([np.asarray(raw(v)) for v in values], axis=axis))
+  tf.zeros_like = lambda x, dtype=None, name=None: T2(np.zeros_like(raw(x), dtype=dtype))
+  _old_cast = tf.cast
+  tf.cast = lambda x, dtype, name=None: T2(np.asarray(raw(x)).astype(dtype))
+  tf.reduce_sum = lambda x, axis=None: T2(np.sum(raw(x), axis=axis, dtype=np.asarray(raw(x)).dtype))
+  tf.reduce_max = lambda x, axis=None: T2(np.max(raw(x), axis=axis))
+  tf.reduce_mean = lambda x, axis=None: T2(np.mean(raw(x), axis=axis, dtype=np.float32))
   return tf
 
 
@@ -80,6 +111,19 @@ def main():
              loss_done=d, loss_out=loss.a, loss_priorities=prio.a)
 
   out['eps_out'] = ns['get_envs_epsilon'](T(np.arange(20)), 10, 10, 1e-3).a
+
+  # ---- stack_frames (atari/networks.py:57-173): bit-packed frame stacking -----------------
+  ns2 = {'tf': tf, 'STACKING_STATE_DTYPE': np.int32}
+  stack = _extract_function(os.path.join(REF, 'atari/networks.py'), 'stack_frames', ns2)
+  T2 = tf._T2
+  for name, (Tn, B, H, W, S) in {'a': (6, 2, 3, 4, 4), 'b': (9, 3, 5, 2, 3), 'c': (4, 1, 2, 2, 2)}.items():
+    fr = rng.integers(0, 256, (Tn, B, H, W, 1)).astype(f32)
+    dn = rng.random((Tn, B)) < 0.3
+    st = rng.integers(0, 1 << (8 * (S - 1)), (B, H * W)).astype(np.int32)
+    stacked, new_state = stack(T2(fr), T2(st), T2(dn), S)
+    out['stack_%s_frames' % name] = fr; out['stack_%s_done' % name] = dn; out['stack_%s_state' % name] = st
+    out['stack_%s_size' % name] = np.asarray(S)
+    out['stack_%s_out' % name] = stacked.a; out['stack_%s_new_state' % name] = new_state.a
   np.savez_compressed(os.path.join(HERE, 'r2d2_golden.npz'), **out)
   print('wrote r2d2_golden.npz:', sorted(out))
 

@@ -78,3 +78,45 @@ def test_prioritized_replay_probabilities_and_weights():       # common/utils.py
   np.testing.assert_array_equal(R.replay_insert_indices(3, 4, 5), [3, 4, 0, 1])
   # full ring: every slot counts
   assert len(R.replay_probabilities(np.ones(5, np.float32), 9, 1.0)) == 5
+
+
+def _stack(frames, state, done, S=4):
+  return R.stack_frames(np.asarray(frames, np.float32), state, np.asarray(done), S)
+
+
+def test_stack_frames_reference_cases():                       # atari/networks_test.py:176-247
+  zero = R.initial_frame_stacking_state(4, 1, [1])
+  assert zero.dtype == np.int32 and zero.shape == (1, 1)
+  out, st = _stack([[[1]]], zero, [[False]])
+  np.testing.assert_array_equal(out, [[[1, 0, 0, 0]]])
+  out, st = _stack([[[2]]], st, [[False]])
+  np.testing.assert_array_equal(out, [[[2, 1, 0, 0]]])
+  out, st = _stack([[[3]], [[4]], [[5]], [[6]], [[7]], [[8]]], st, [[False]] * 6)
+  assert out.shape[0] == 6
+  np.testing.assert_array_equal(out[0], [[3, 2, 1, 0]])
+  np.testing.assert_array_equal(out[5], [[8, 7, 6, 5]])
+  # done resets the stack
+  out, st = _stack([[[1]]], zero, [[False]])
+  out, st = _stack([[[2]]], st, [[True]])
+  np.testing.assert_array_equal(out, [[[2, 0, 0, 0]]])
+  out, st = _stack([[[3]], [[4]], [[5]], [[6]], [[7]], [[8]]], st,
+                   [[False], [False], [False], [False], [True], [False]])
+  np.testing.assert_array_equal(out[0], [[3, 2, 0, 0]])
+  np.testing.assert_array_equal(out[5], [[8, 7, 0, 0]])
+  # stack_size 1 is the identity with an empty state; errors as in the reference
+  f = np.zeros((2, 1, 3, 3, 1), np.float32)
+  o, s = R.stack_frames(f, (), np.zeros((2, 1), bool), 1)
+  assert o is not None and s == ()
+  with pytest.raises(ValueError):
+    R.stack_frames(f, zero, np.zeros((3, 1), bool), 4)
+  with pytest.raises(ValueError):
+    R.stack_frames(f, zero, np.zeros((2, 1), bool), 5)
+
+
+@pytest.mark.parametrize('name', ['a', 'b', 'c'])
+def test_stack_frames_golden_bit_exact(name):
+  out, st = R.stack_frames(G['stack_%s_frames' % name], G['stack_%s_state' % name], G['stack_%s_done' % name],
+                           int(G['stack_%s_size' % name]))
+  np.testing.assert_array_equal(out, G['stack_%s_out' % name])
+  np.testing.assert_array_equal(st, G['stack_%s_new_state' % name])
+  assert st.dtype == np.int32
