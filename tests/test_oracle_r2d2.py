@@ -120,3 +120,33 @@ def test_stack_frames_golden_bit_exact(name):
   np.testing.assert_array_equal(out, G['stack_%s_out' % name])
   np.testing.assert_array_equal(st, G['stack_%s_new_state' % name])
   assert st.dtype == np.int32
+
+
+def test_dueling_lstm_dqn_net_structure():
+  """atari/networks_test.py:78-117: unrolls run with and without frame stacking, the torso sees
+  stack_size channels, the core input is 512 + num_actions + 1 wide; plus the invariants the
+  code states (dueling advantages are mean-free, greedy action, state reset on done)."""
+  import torch
+  from oracle import net_oracle, r2d2_net_oracle as N
+  rng = np.random.default_rng(0)
+  OBS, A, T, B = [84, 84, 1], 37, 5, 2
+  for S in (4, 1):
+    specs = dict(N.param_specs(A, OBS, S))
+    assert specs['body/conv0/kernel'] == (8, 8, S if S > 1 else 1, 32)
+    assert specs['core/kernel'] == (512 + A + 1, 4 * 512)                    # networks_test.py:115-117
+    assert specs['body/dense/kernel'][0] == 7 * 7 * 64 and 'advantage/head/bias' not in specs
+    p = net_oracle.to_torch(N.init_params(A, OBS, S, seed=1))
+    obs = rng.integers(0, 256, [T, B] + OBS, dtype=np.uint8)
+    done = rng.random((T, B)) < 0.3
+    st = N.initial_state(B, OBS, S)
+    out, st2 = N.unroll(p, rng.integers(0, A, (T, B)), rng.normal(size=(T, B)), done, obs, st, A, S)
+    assert tuple(out.q_values.shape) == (T, B, A) and tuple(out.action.shape) == (T, B)
+    assert torch.equal(out.action.long(), out.q_values.argmax(-1))
+    assert isinstance(st2.frame_stacking_state, tuple) == (S == 1)
+    # splitting the unroll at any step and carrying the state gives the same outputs
+    _pa = rng.integers(0, A, (T, B)); _rw = rng.normal(size=(T, B))
+    out_a, mid = N.unroll(p, _pa[:2], _rw[:2], done[:2], obs[:2], st, A, S)
+    out_b, _ = N.unroll(p, _pa[2:], _rw[2:], done[2:], obs[2:], mid, A, S)
+    full, _ = N.unroll(p, _pa, _rw, done, obs, st, A, S)
+    np.testing.assert_allclose(torch.cat([out_a.q_values, out_b.q_values]).detach().numpy(),
+                               full.q_values.detach().numpy(), rtol=1e-5, atol=1e-6)
