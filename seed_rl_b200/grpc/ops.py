@@ -177,32 +177,78 @@ def decode_structure(buf):
   return None
 
 
-def _encode_call_request(fn_name, tensors):
-  return _ld(1, fn_name.encode()) + b''.join(_ld(2, encode_tensor(t)) for t in tensors)
+# ---- seed_rl.TensorService envelope (grpc/service.proto:28-57) ---------------------------
+# The *_raw functions work on already-serialised payloads (TensorProto / StructuredValue
+# bytes) and are pinned against the reference's compiled descriptor (tests/test_rpc.py,
+# tests/golden/rpc_golden.json).  proto3: default values (0, '') are not emitted.
+def _encode_call_request_raw(fn_name, tensor_bytes):
+  out = _ld(1, fn_name.encode('utf-8')) if fn_name else b''
+  return out + b''.join(_ld(2, t) for t in tensor_bytes)
 
 
-def _decode_call_request(buf):
+def _decode_call_request_raw(buf):
   name, tensors = '', []
   for f, wt, v in _parse(buf):
-    if f == 1: name = v.decode()
-    elif f == 2: tensors.append(decode_tensor(v))
+    if f == 1: name = v.decode('utf-8')
+    elif f == 2: tensors.append(bytes(v))
   return name, tensors
 
 
-def _encode_call_response(tensors, code=0, msg=''):
-  out = b''.join(_ld(1, encode_tensor(t)) for t in tensors)
+def _encode_call_response_raw(tensor_bytes, code=0, msg=''):
+  out = b''.join(_ld(1, t) for t in tensor_bytes)
   if code:
-    out += _key(2, 0) + _varint(code) + _ld(3, msg.encode())
+    out += _key(2, 0) + _varint(code)
+  if msg:
+    out += _ld(3, msg.encode('utf-8'))
   return out
 
 
-def _decode_call_response(buf):
+def _decode_call_response_raw(buf):
   tensors, code, msg = [], 0, ''
   for f, wt, v in _parse(buf):
-    if f == 1: tensors.append(decode_tensor(v))
+    if f == 1: tensors.append(bytes(v))
     elif f == 2: code = v
-    elif f == 3: msg = v.decode()
+    elif f == 3: msg = v.decode('utf-8')
   return tensors, code, msg
+
+
+def _encode_init_response_raw(signatures):
+  """signatures: [(name, output_specs bytes)] -> InitResponse."""
+  body = b''
+  for name, spec in signatures:
+    sig = (_ld(1, name.encode('utf-8')) if name else b'') + (_ld(2, spec) if spec else b'')
+    body += _ld(1, sig)
+  return body
+
+
+def _decode_init_response_raw(buf):
+  sigs = []
+  for f, _, v in _parse(buf):
+    if f == 1:
+      name, spec = '', b''
+      for f2, _, v2 in _parse(v):
+        if f2 == 1: name = v2.decode('utf-8')
+        elif f2 == 2: spec = bytes(v2)
+      sigs.append((name, spec))
+  return sigs
+
+
+def _encode_call_request(fn_name, tensors):
+  return _encode_call_request_raw(fn_name, [encode_tensor(t) for t in tensors])
+
+
+def _decode_call_request(buf):
+  name, raw = _decode_call_request_raw(buf)
+  return name, [decode_tensor(t) for t in raw]
+
+
+def _encode_call_response(tensors, code=0, msg=''):
+  return _encode_call_response_raw([encode_tensor(t) for t in tensors], code, msg)
+
+
+def _decode_call_response(buf):
+  raw, code, msg = _decode_call_response_raw(buf)
+  return [decode_tensor(t) for t in raw], code, msg
 
 
 # ---- tf.function stand-in -------------------------------------------------------------
@@ -396,15 +442,14 @@ class Server(object):
       L.seedrl_batcher_release(b.batcher, slab)
 
   def _init_rpc(self, request, context):
-    body = b''
+    sigs = []
     for b in self._fns.values():
       unbatched = None
       if b.out_structure is not None:
         unbatched = utils.map_structure(lambda s: TensorSpec(list(s.shape[1:]), s.dtype, s.name),
                                         b.out_structure)
-      sig = _ld(1, b.name.encode()) + _ld(2, encode_structure(unbatched))
-      body += _ld(1, sig)
-    return body
+      sigs.append((b.name, encode_structure(unbatched)))
+    return _encode_init_response_raw(sigs)
 
   def _call_rpc(self, request_iterator, context):
     for req in request_iterator:
@@ -436,13 +481,8 @@ class Client(object):
     self._lock = threading.Lock()        # one in-flight call per stream (grpc.cc:1064)
     self._requests = _Feeder()
     self._responses = None
-    for f, _, v in _parse(init(b'', wait_for_ready=True)):
-      if f == 1:
-        name, specs = '', None
-        for f2, _, v2 in _parse(v):
-          if f2 == 1: name = v2.decode()
-          elif f2 == 2: specs = decode_structure(v2)
-        self._add_method(name, specs)
+    for name, spec in _decode_init_response_raw(init(b'', wait_for_ready=True)):
+      self._add_method(name, decode_structure(spec) if spec else None)
 
   def _add_method(self, name, output_specs):
     def call(*inputs):
