@@ -108,7 +108,8 @@ def _parse(buf):
 
 
 def _shape_proto(shape):
-  return b''.join(_ld(2, _key(1, 0) + _varint(int(d))) for d in shape)
+  # proto3: a zero size is the default and is not written
+  return b''.join(_ld(2, (_key(1, 0) + _varint(int(d))) if int(d) else b'') for d in shape)
 
 
 def _parse_shape(buf):
@@ -130,7 +131,9 @@ def _contig(a):
 
 def encode_tensor(a):
   a = _contig(a)
-  return _key(1, 0) + _varint(_DT[a.dtype]) + _ld(2, _shape_proto(a.shape)) + _ld(4, a.tobytes())
+  content = a.tobytes()
+  return (_key(1, 0) + _varint(_DT[a.dtype]) + _ld(2, _shape_proto(a.shape)) +
+          (_ld(4, content) if content else b''))
 
 
 def decode_tensor(buf):

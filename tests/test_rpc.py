@@ -179,3 +179,43 @@ def test_service_envelope_matches_the_reference_descriptor():
     elif c['kind'] == 'InitRequest':
       assert want == b''                   # what Client sends to /Init
   assert seen == {'CallRequest', 'CallResponse', 'InitResponse', 'InitRequest'}
+
+
+def test_tensorproto_and_structuredvalue_match_tf_schemas():
+  """encode_tensor / encode_structure against bytes produced by the protobuf runtime from
+  protoc-compiled copies of TensorFlow's tensor.proto / struct.proto
+  (tests/golden/make_golden_tfproto.py), both directions."""
+  import json, os
+  from seed_rl_b200.common.utils import TensorSpec
+  from seed_rl_b200.grpc import ops
+  g = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'tfproto_golden.json')))
+  assert g['enum'] == {'float32': 1, 'int32': 3, 'uint8': 4, 'int64': 9, 'bool': 10}   # SURVEY 8(f)
+  for t in g['tensors']:
+    a = np.frombuffer(bytes.fromhex(t['content']), dtype=t['dtype']).reshape(t['shape'])
+    want = bytes.fromhex(t['hex'])
+    got = ops.encode_tensor(a)
+    back = ops.decode_tensor(want)
+    assert back.dtype == a.dtype and back.shape == a.shape and np.array_equal(back, a)
+    assert got == want, (t['dtype'], t['shape'])          # byte-identical, proto3 default omission included
+
+  def build(j):
+    if j is None:
+      return None
+    if 'tuple' in j:
+      return tuple(build(x) for x in j['tuple'])
+    if 'list' in j:
+      return [build(x) for x in j['list']]
+    return TensorSpec(j['shape'], j['dtype'], j['name'])
+
+  def same(a, b):
+    if a is None or b is None:
+      return a is None and b is None
+    if isinstance(a, TensorSpec):
+      return (isinstance(b, TensorSpec) and list(a.shape) == list(b.shape) and np.dtype(a.dtype) == np.dtype(b.dtype)
+              and (a.name or None) == (b.name or None))
+    return type(a) is type(b) and len(a) == len(b) and all(same(x, y) for x, y in zip(a, b))
+  for s in g['structures']:
+    spec = build(s['spec'])
+    want = bytes.fromhex(s['hex'])
+    assert same(ops.decode_structure(want), spec), s['spec']
+    assert ops.encode_structure(spec) == want, s['spec']    # byte-identical
