@@ -284,6 +284,43 @@ int seedrl_profile_begin(seedrl_stream_t stream);
 int seedrl_profile_end(double* ms_per_category, uint64_t* launches_per_category);
 
 /* ------------------------------------------------------------------------
+ * R2D2 post-network pieces.  Written and compiled in round 1, not yet
+ * executed on hardware; nothing on the V-trace path calls them.
+ *
+ * seedrl_r2d2_stack_frames <- atari/networks.py:57-173 (stack_frames): frames uint8 [T,B,P]
+ *   (P = prod(observation_shape), one channel), state int32 [B,P] bit-packed (LSB byte =
+ *   oldest of the stack_size-1 kept frames), done [T,B].  stacked uint8 [T,B,P,stack_size],
+ *   newest first, channels that cross an episode boundary zeroed (the reference returns the
+ *   same values as float32; /255 is folded into the first convolution here).  Errors: the
+ *   reference's "Only up to stack size 4 is supported due to bit-packing." */
+int seedrl_r2d2_stack_frames(int T, int B, int P, int stack_size, const uint8_t* frames,
+                             const int32_t* state_in, const uint8_t* done, uint8_t* stacked,
+                             int32_t* state_out, seedrl_stream_t stream);
+/* <- agents/r2d2/learner.py:258-330 (compute_loss_and_priorities_from_agent_outputs) with
+ *   value_function_rescaling / inverse (:180-192) and n_step_bellman_target (:195-255), plus the
+ *   gradient of mean_b(importance_weight_b * loss_b) (:604) w.r.t. q_train.  The greedy action
+ *   of the online network is re-derived as argmax_a q_train (first maximum, like tf.argmax).
+ *   loss, priorities: [B]; dq: [T,B,A]; scratch: seedrl_r2d2_loss_scratch_bytes. */
+size_t seedrl_r2d2_loss_scratch_bytes(int T, int B, int n_steps);
+int seedrl_r2d2_loss_fwd_bwd(int T, int B, int A, const float* q_train, const float* q_target,
+                             const int64_t* replay_action, const float* reward, const uint8_t* done,
+                             const float* importance_weights, float gamma, int n_steps, float eta,
+                             float value_rescaling_eps, float* loss, float* priorities, float* dq,
+                             void* scratch, seedrl_stream_t stream);
+/* <- common/utils.py:327-352 (PrioritizedReplay.sample, priority_exp != 0): prob_i =
+ *   prio_i^alpha / sum over the first `limit` slots; index_j = inverse CDF of uniforms[j] in
+ *   [0,1) (the reference draws with tf.random.categorical: same distribution, different
+ *   stream); weights_j = ((1/limit)/prob_{index_j})^beta / max_j.  probs_out may be NULL. */
+int seedrl_replay_sample(int limit, const float* priorities, float priority_exp,
+                         float importance_sampling_exp, int num_samples, const float* uniforms,
+                         int64_t* indices, float* weights, float* probs_out, seedrl_stream_t stream);
+/* <- tf.clip_by_global_norm (agents/r2d2/learner.py:608, clip_norm = 40) over the flat gradient
+ *   arena: g *= clip_norm / max(||g||_2, clip_norm); *norm_out = ||g||_2 (may be NULL). */
+size_t seedrl_clip_scratch_bytes(void);
+int seedrl_clip_by_global_norm(size_t n, float* grads, float clip_norm, float* norm_out,
+                               void* scratch, seedrl_stream_t stream);
+
+/* ------------------------------------------------------------------------
  * Single-kernel test hooks: let the GPU parity tests localise a failure to one
  * kernel of the network schedule.  Not part of the drop-in surface.
  * in_mode: 0 fp32 input, 1 relu(input), 2 uint8 input / 255. */

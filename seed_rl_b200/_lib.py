@@ -92,6 +92,13 @@ SIGNATURES = {
     'seedrl_batcher_next_full': (c_int, [P, c_int, ctypes.POINTER(c_int)]),
     'seedrl_batcher_publish': (c_int, [P, c_int, c_int]),
     'seedrl_batcher_shutdown': (c_int, [P]),
+    'seedrl_r2d2_stack_frames': (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
+    'seedrl_r2d2_loss_scratch_bytes': (c_size_t, [c_int, c_int, c_int]),
+    'seedrl_r2d2_loss_fwd_bwd': (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, c_float, c_int, c_float, c_float,
+                                         P, P, P, P, P]),
+    'seedrl_replay_sample': (c_int, [c_int, P, c_float, c_float, c_int, P, P, P, P, P]),
+    'seedrl_clip_scratch_bytes': (c_size_t, []),
+    'seedrl_clip_by_global_norm': (c_int, [c_size_t, P, c_float, P, P, P]),
     'seedrl_profile_num_categories': (c_int, []),
     'seedrl_profile_category_name': (ctypes.c_char_p, [c_int]),
     'seedrl_profile_begin': (c_int, [P]),

@@ -1,0 +1,304 @@
+// R2D2 post-network kernels for sm_100a:
+//
+//   r2d2_stack_frames_kernel   atari/networks.py:57-173   bit-packed frame stacking (uint8/int32)
+//   r2d2_loss_kernel           agents/r2d2/learner.py:180-330  h / h^-1, n-step double-DQN
+//                              targets, per-sequence loss, priorities and d loss / d q
+//   replay_sample_kernel       common/utils.py:327-352    p_i ~ prio_i^alpha, inverse-CDF draw,
+//                              importance weights normalised by their max
+//   global-norm clip           tf.clip_by_global_norm, learner.py:608 (clip_norm = 40)
+//
+// STATUS (round 1): written against oracle/r2d2_oracle.py, compiled for sm_100a, exported through
+// the C-ABI, NOT yet executed on hardware (the round's GPU budget was spent before this row);
+// its GPU tests are gated (tests/test_gpu_r2d2.py).  Nothing on the V-trace path calls it.
+//
+// All of it is HBM-/latency-bound byte and elementwise work: coalesced accesses across the
+// pixel or batch axis, sequential walks along time in registers.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace seedrl {
+
+// ---------------------------------------------------------------------------------------
+// One thread per (b, pixel): walks t = 0..T-1 with the last S frames in registers.
+//   stacked[t,b,p,i] = ext[t + S-1-i], ext = (S-1 unpacked state frames, oldest first) ++ frames,
+//   zeroed when an episode boundary lies in (t-i, t]  <=>  i > a_t, a_t = steps since the most
+//   recent done[.] = true at or before t inside this unroll (infinite if none).
+//   new_state byte j (LSB = oldest) = masked stacked[T-1,b,p,S-2-j].
+template <int S>
+__global__ void r2d2_stack_frames_kernel(int T, int B, int P, const uint8_t* __restrict__ frames,
+                                         const int32_t* __restrict__ state_in,
+                                         const uint8_t* __restrict__ done,
+                                         uint8_t* __restrict__ stacked, int32_t* __restrict__ state_out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (p >= P) return;
+  const uint32_t st = (uint32_t)state_in[(size_t)b * P + p];
+  // w[i], i >= 1: the frame i steps before the one about to arrive; the newest kept frame is
+  // byte S-2 of the packed state (LSB byte = oldest)
+  uint32_t w[S], last[S];
+  w[0] = 0;
+#pragma unroll
+  for (int i = 1; i < S; ++i) w[i] = (st >> (8 * (S - 1 - i))) & 0xFFu;
+#pragma unroll
+  for (int i = 0; i < S; ++i) last[i] = 0;
+  int age = 1 << 20;                                  // no done seen yet: nothing is masked
+  for (int t = 0; t < T; ++t) {
+    const uint32_t f = frames[((size_t)t * B + b) * P + p];
+    age = done[(size_t)t * B + b] ? 0 : age + 1;
+    uint8_t* o = stacked + (((size_t)t * B + b) * P + p) * S;
+    o[0] = (uint8_t)f;
+    last[0] = f;
+#pragma unroll
+    for (int i = 1; i < S; ++i) {
+      const uint32_t v = (i <= age) ? w[i] : 0u;     // masking never feeds back into the window
+      o[i] = (uint8_t)v;
+      last[i] = v;
+    }
+#pragma unroll
+    for (int i = S - 1; i >= 2; --i) w[i] = w[i - 1];
+    w[1] = f;
+  }
+  uint32_t ns = 0;
+#pragma unroll
+  for (int j = 0; j < S - 1; ++j) ns |= last[S - 2 - j] << (8 * j);
+  if (T == 0) ns = st;
+  state_out[(size_t)b * P + p] = (int32_t)ns;
+}
+
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float vf_rescale(float x, float eps) {              // learner.py:180-183
+  const float s = (x > 0.f) - (x < 0.f);
+  return s * (sqrtf(fabsf(x) + 1.f) - 1.f) + eps * x;
+}
+__device__ __forceinline__ float vf_rescale_inv(float x, float eps) {          // learner.py:186-192
+  const float s = (x > 0.f) - (x < 0.f);
+  const float inner = (sqrtf(1.f + 4.f * eps * (fabsf(x) + 1.f + eps)) - 1.f) / (2.f * eps);
+  return s * (inner * inner - 1.f);
+}
+
+struct R2d2LossParams {
+  int T, B, A, n_steps;
+  const float* q_train;     // [T,B,A]
+  const float* q_target;    // [T,B,A]
+  const int64_t* replay_action;   // [T,B]
+  const float* reward;      // [T,B]
+  const uint8_t* done;      // [T,B]
+  const float* is_weights;  // [B] or null (= 1)
+  float gamma, eta, eps;
+  float gamma_pow[8];       // fp32(gamma ** k): the reference DIVIDES the padded targets by it
+  float* loss;              // [B]
+  float* priorities;        // [B]
+  float* dq;                // [T,B,A]  d mean_b(w_b loss_b) / d q_train
+  float* scratch;           // [B][T + n_steps] Bellman-target work array
+};
+
+// One thread per sequence b (B ~ 64, T ~ 100: negligible next to the two network unrolls).
+// Follows n_step_bellman_target literally (padded arrays, n_steps in-place passes) so that the
+// fp32 rounding order is the oracle's.
+__global__ void r2d2_loss_kernel(const R2d2LossParams p) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= p.B) return;
+  const int T = p.T, B = p.B, A = p.A, n = p.n_steps;
+  float* bt = p.scratch + (size_t)b * (T + n);
+  // bellman_target = [0, qmax_0 .. qmax_{T-1}, qmax_{T-1}/gamma^1 .. /gamma^{n-1}]   (:241-246)
+  bt[0] = 0.f;
+  float qlast = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float* qt = p.q_train + ((size_t)t * B + b) * A;
+    int best = 0;
+    float bv = qt[0];
+    for (int a = 1; a < A; ++a)
+      if (qt[a] > bv) { bv = qt[a]; best = a; }                                  // argmax, first max
+    qlast = vf_rescale_inv(p.q_target[((size_t)t * B + b) * A + best], p.eps);   // :303-305
+    bt[1 + t] = qlast;
+  }
+  for (int k = 1; k < n; ++k) bt[T + k] = qlast / p.gamma_pow[k];
+  // n passes of  target = r + gamma (1 - done) target[1:]  over the zero-padded r / done (:250-253)
+  for (int j = 1; j <= n; ++j) {
+    const int len = T + n - j;                       // length after dropping j padded rows
+    for (int i = 0; i < len; ++i) {
+      const float r = i < T ? p.reward[(size_t)i * B + b] : 0.f;
+      const float nd = (i < T && p.done[(size_t)i * B + b]) ? 0.f : 1.f;
+      bt[i] = r + p.gamma * nd * bt[i + 1];
+    }
+  }
+  // td_t = h(target[t+1]) - Q(s_t, a_t), t < T-1  (:316-322)
+  const float w = (p.is_weights ? p.is_weights[b] : 1.f) / (float)B;             // d mean_b(w_b loss_b)
+  float mx = 0.f, sum = 0.f, sq = 0.f;
+  for (int t = 0; t < T; ++t) {
+    float* dq = p.dq + ((size_t)t * B + b) * A;
+    for (int a = 0; a < A; ++a) dq[a] = 0.f;
+    if (t + 1 < T) {
+      int64_t a = p.replay_action[(size_t)t * B + b];
+      a = a < 0 ? 0 : (a >= A ? A - 1 : a);
+      const float rq = p.q_train[((size_t)t * B + b) * A + a];
+      const float tgt = vf_rescale(bt[t + 1], p.eps);
+      const float td = tgt - rq;
+      const float ad = fabsf(td);
+      mx = fmaxf(mx, ad); sum += ad; sq += ad * ad;
+      dq[a] = -w * td;                               // d(0.5 td^2)/d rq = -(tgt - rq), target is stop-gradient
+    }
+  }
+  const int Tm = T - 1 > 0 ? T - 1 : 1;
+  p.priorities[b] = p.eta * mx + (1.f - p.eta) * (sum / (float)Tm);             // :325-326
+  p.loss[b] = 0.5f * sq;                                                         // :329
+}
+
+// ---------------------------------------------------------------------------------------
+// Single CTA (the replay holds ~100 unrolls): prob = prio^alpha / sum; inclusive CDF in shared
+// memory; sample j = first i with cdf[i] > u_j * total; weights = ((1/limit)/prob_i)^beta / max.
+constexpr int kReplayMax = 8192;
+__global__ void __launch_bounds__(1024)
+replay_sample_kernel(int limit, const float* __restrict__ priorities, float priority_exp, float is_exp,
+                     int num_samples, const float* __restrict__ uniforms, int64_t* __restrict__ indices,
+                     float* __restrict__ weights, float* __restrict__ probs_out) {
+  __shared__ float s_cdf[kReplayMax];
+  __shared__ float s_red[32];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < limit; i += blockDim.x) s_cdf[i] = powf(priorities[i], priority_exp);
+  __syncthreads();
+  // serial prefix by one thread in index order: deterministic, and 100..8192 adds are nothing
+  if (tid == 0) {
+    float acc = 0.f;
+    for (int i = 0; i < limit; ++i) { acc += s_cdf[i]; s_cdf[i] = acc; }
+    s_red[0] = acc;
+  }
+  __syncthreads();
+  const float total = s_red[0];
+  if (probs_out)
+    for (int i = tid; i < limit; i += blockDim.x)
+      probs_out[i] = (s_cdf[i] - (i ? s_cdf[i - 1] : 0.f)) / total;
+  float wmax = 0.f;
+  for (int j = tid; j < num_samples; j += blockDim.x) {
+    const float u = uniforms[j] * total;
+    int lo = 0, hi = limit - 1;
+    while (lo < hi) {                                 // first i with cdf[i] > u
+      const int mid = (lo + hi) >> 1;
+      if (s_cdf[mid] > u) hi = mid; else lo = mid + 1;
+    }
+    const float pi = (s_cdf[lo] - (lo ? s_cdf[lo - 1] : 0.f)) / total;
+    const float wj = powf((1.f / (float)limit) / pi, is_exp);
+    indices[j] = lo;
+    weights[j] = wj;
+    wmax = fmaxf(wmax, wj);
+  }
+  // max over the CTA, then normalise
+  for (int o = 16; o; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
+  __syncthreads();
+  if ((tid & 31) == 0) s_red[tid >> 5] = wmax;
+  __syncthreads();
+  float m = 0.f;
+  for (int k = 0; k < (int)(blockDim.x >> 5); ++k) m = fmaxf(m, s_red[k]);
+  for (int j = tid; j < num_samples; j += blockDim.x) weights[j] /= m;
+}
+
+// ---------------------------------------------------------------------------------------
+// tf.clip_by_global_norm: g *= clip / max(||g||_2, clip).  Deterministic two-stage reduction.
+__global__ void sumsq_partial_kernel(size_t n, const float* __restrict__ g, float* __restrict__ partial) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    s = fmaf(g[i], g[i], s);
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += red[k];
+    partial[blockIdx.x] = t;
+  }
+}
+__global__ void clip_scale_kernel(size_t n, float* __restrict__ g, const float* __restrict__ partial, int nparts,
+                                  float clip_norm, float* __restrict__ norm_out) {
+  __shared__ float s_scale;
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int k = 0; k < nparts; ++k) t += partial[k];        // fixed order
+    const float norm = sqrtf(t);
+    s_scale = clip_norm / fmaxf(norm, clip_norm);
+    if (norm_out && blockIdx.x == 0) *norm_out = norm;
+  }
+  __syncthreads();
+  const float sc = s_scale;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    g[i] *= sc;
+}
+
+}  // namespace seedrl
+
+using namespace seedrl;
+
+extern "C" int seedrl_r2d2_stack_frames(int T, int B, int P, int stack_size, const uint8_t* frames,
+                                        const int32_t* state_in, const uint8_t* done, uint8_t* stacked,
+                                        int32_t* state_out, seedrl_stream_t stream) {
+  SEEDRL_CHECK_ARG(T >= 0 && B >= 1 && P >= 1, "bad T/B/P");
+  SEEDRL_CHECK_ARG(stack_size >= 2 && stack_size <= 4,
+                   "Only up to stack size 4 is supported due to bit-packing.");   // networks.py:98-99
+  SEEDRL_CHECK_ARG(frames && state_in && done && stacked && state_out, "null pointer");
+  const dim3 grid(ceil_div(P, 256), B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (stack_size == 4) r2d2_stack_frames_kernel<4><<<grid, 256, 0, st>>>(T, B, P, frames, state_in, done, stacked, state_out);
+  else if (stack_size == 3) r2d2_stack_frames_kernel<3><<<grid, 256, 0, st>>>(T, B, P, frames, state_in, done, stacked, state_out);
+  else r2d2_stack_frames_kernel<2><<<grid, 256, 0, st>>>(T, B, P, frames, state_in, done, stacked, state_out);
+  count_launch(PC_MISC, st);
+  SEEDRL_CHECK_LAUNCH();
+  return SEEDRL_OK;
+}
+
+extern "C" size_t seedrl_r2d2_loss_scratch_bytes(int T, int B, int n_steps) {
+  return (size_t)B * (size_t)(T + n_steps) * sizeof(float);
+}
+
+extern "C" int seedrl_r2d2_loss_fwd_bwd(int T, int B, int A, const float* q_train, const float* q_target,
+                                        const int64_t* replay_action, const float* reward, const uint8_t* done,
+                                        const float* importance_weights, float gamma, int n_steps, float eta,
+                                        float value_rescaling_eps, float* loss, float* priorities, float* dq,
+                                        void* scratch, seedrl_stream_t stream) {
+  SEEDRL_CHECK_ARG(T >= 2 && B >= 1 && A >= 1, "need T>=2, B>=1, A>=1");
+  SEEDRL_CHECK_ARG(n_steps >= 1 && n_steps <= 8, "n_steps must be in [1, 8]");
+  SEEDRL_CHECK_ARG(q_train && q_target && replay_action && reward && done && loss && priorities && dq && scratch,
+                   "null pointer");
+  R2d2LossParams p;
+  p.T = T; p.B = B; p.A = A; p.n_steps = n_steps;
+  p.q_train = q_train; p.q_target = q_target; p.replay_action = replay_action; p.reward = reward;
+  p.done = done; p.is_weights = importance_weights; p.gamma = gamma; p.eta = eta; p.eps = value_rescaling_eps;
+  for (int k = 0; k < 8; ++k) p.gamma_pow[k] = (float)pow((double)gamma, (double)k);   // fp32(gamma ** k)
+  p.loss = loss; p.priorities = priorities; p.dq = dq; p.scratch = reinterpret_cast<float*>(scratch);
+  r2d2_loss_kernel<<<ceil_div(B, 64), 64, 0, (cudaStream_t)stream>>>(p);
+  count_launch(PC_LOSS, (cudaStream_t)stream);
+  SEEDRL_CHECK_LAUNCH();
+  return SEEDRL_OK;
+}
+
+extern "C" int seedrl_replay_sample(int limit, const float* priorities, float priority_exp,
+                                    float importance_sampling_exp, int num_samples, const float* uniforms,
+                                    int64_t* indices, float* weights, float* probs_out,
+                                    seedrl_stream_t stream) {
+  SEEDRL_CHECK_ARG(limit >= 1 && limit <= kReplayMax, "replay limit must be in [1, 8192]");
+  SEEDRL_CHECK_ARG(num_samples >= 1 && priorities && uniforms && indices && weights, "bad arguments");
+  replay_sample_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(limit, priorities, priority_exp,
+                                                            importance_sampling_exp, num_samples, uniforms,
+                                                            indices, weights, probs_out);
+  count_launch(PC_MISC, (cudaStream_t)stream);
+  SEEDRL_CHECK_LAUNCH();
+  return SEEDRL_OK;
+}
+
+extern "C" size_t seedrl_clip_scratch_bytes(void) { return 1024 * sizeof(float); }
+
+extern "C" int seedrl_clip_by_global_norm(size_t n, float* grads, float clip_norm, float* norm_out,
+                                          void* scratch, seedrl_stream_t stream) {
+  SEEDRL_CHECK_ARG(grads && scratch && clip_norm > 0.f, "bad arguments");
+  if (n == 0) return SEEDRL_OK;
+  const int parts = 592;                                 // 148 SMs x 4
+  float* partial = reinterpret_cast<float*>(scratch);
+  cudaStream_t st = (cudaStream_t)stream;
+  sumsq_partial_kernel<<<parts, 256, 0, st>>>(n, grads, partial);
+  count_launch(PC_ADAM, st);
+  SEEDRL_CHECK_LAUNCH();
+  clip_scale_kernel<<<parts, 256, 0, st>>>(n, grads, partial, parts, clip_norm, norm_out);
+  count_launch(PC_ADAM, st);
+  SEEDRL_CHECK_LAUNCH();
+  return SEEDRL_OK;
+}
