@@ -114,7 +114,10 @@ extern "C" int seedrl_batcher_claim(seedrl_batcher* b, int k, int* slab, int* ro
   for (;;) {
     if (b->shutdown) return fail(SEEDRL_ERR_CANCELLED, "Server shutdown.");
     Slab& s = b->slabs[b->cur];
-    if (s.state == FILLING) {
+    // A slab whose rows are all claimed but not yet all committed (a caller was descheduled
+    // between claim and commit) is still FILLING: when the other callers lap the ring and come
+    // back to it, it is busy -- wait for it like for any slab in flight.
+    if (s.state == FILLING && s.claimed < b->batch_size) {
       if (s.claimed + k > b->batch_size)   // grpc.cc:653 (CHECK-fails there)
         return fail(SEEDRL_ERR_OUT_OF_RANGE,
                     "seedrl_batcher_claim: call would straddle two batches (batch size must be a "

@@ -246,3 +246,19 @@ def test_conv_position_maps_on_host():
           ok = (r < H) & (c < W) & (n < N)
           want = np.where(ok, (n * H + r) * W + c, -1)
         np.testing.assert_array_equal(out, want)
+
+
+def test_batcher_native_thread_stress(tmp_path):
+  """Native threads lap the slab ring while one caller sits between claim and commit
+  (tests/host_emulation/batcher_stress.cc).  Regression test: seedrl_batcher_claim reported a
+  spurious 'would straddle two batches' for a fully claimed, not yet fully committed slab,
+  which killed callers (1 run in ~40 of the Python stress test above stalled)."""
+  import subprocess
+  exe = str(tmp_path / 'batcher_stress')
+  libdir = os.path.join(ROOT, 'seed_rl_b200')
+  subprocess.check_call(['g++', '-O2', '-std=c++17', '-o', exe,
+                         os.path.join(ROOT, 'tests', 'host_emulation', 'batcher_stress.cc'),
+                         '-L' + libdir, '-lseedrl_b200', '-Wl,-rpath,' + libdir, '-lpthread'])
+  r = subprocess.run([exe, '300'], capture_output=True, text=True, timeout=300)
+  assert r.returncode == 0, r.stdout + r.stderr
+  assert r.stdout.strip() == 'stalls=0 bad=0 claim_errors=0'
