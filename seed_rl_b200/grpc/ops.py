@@ -72,39 +72,50 @@ def _ld(field, payload):
   return _key(field, 2) + _varint(len(payload)) + payload
 
 
+class MalformedProto(ValueError):
+  """A byte string that is not a well-formed protobuf message of the expected schema."""
+
+
+def _read_varint(buf, i, n):
+  v = 0; shift = 0
+  while True:
+    if i >= n or shift > 63:
+      raise MalformedProto('truncated or over-long varint')
+    b = buf[i]; i += 1
+    v |= (b & 0x7F) << shift; shift += 7
+    if not b & 0x80:
+      return v & ((1 << 64) - 1), i
+
+
 def _parse(buf):
-  """Yields (field, wire_type, value) -- value is int for varint, bytes for len-delimited."""
+  """Yields (field, wire_type, value) -- value is int for varint, bytes for len-delimited.
+  Malformed input raises MalformedProto (a ValueError), never anything else."""
   i, n = 0, len(buf)
   while i < n:
-    k = 0; shift = 0
-    while True:
-      b = buf[i]; i += 1
-      k |= (b & 0x7F) << shift; shift += 7
-      if not b & 0x80:
-        break
+    k, i = _read_varint(buf, i, n)
     field, wt = k >> 3, k & 7
+    if field == 0:
+      raise MalformedProto('field number 0')
     if wt == 0:
-      v = 0; shift = 0
-      while True:
-        b = buf[i]; i += 1
-        v |= (b & 0x7F) << shift; shift += 7
-        if not b & 0x80:
-          break
+      v, i = _read_varint(buf, i, n)
       yield field, wt, v
     elif wt == 2:
-      ln = 0; shift = 0
-      while True:
-        b = buf[i]; i += 1
-        ln |= (b & 0x7F) << shift; shift += 7
-        if not b & 0x80:
-          break
+      ln, i = _read_varint(buf, i, n)
+      if ln > n - i:
+        raise MalformedProto('length-delimited field runs past the end of the message')
       yield field, wt, bytes(buf[i:i + ln]); i += ln
-    elif wt == 5:
-      yield field, wt, bytes(buf[i:i + 4]); i += 4
-    elif wt == 1:
-      yield field, wt, bytes(buf[i:i + 8]); i += 8
+    elif wt in (5, 1):
+      w = 4 if wt == 5 else 8
+      if w > n - i:
+        raise MalformedProto('fixed-width field runs past the end of the message')
+      yield field, wt, bytes(buf[i:i + w]); i += w
     else:
-      raise ValueError('unsupported wire type %d' % wt)
+      raise MalformedProto('unsupported wire type %d' % wt)
+
+
+def _expect(wt, want, what):
+  if wt != want:
+    raise MalformedProto('%s has wire type %d, expected %d' % (what, wt, want))
 
 
 def _shape_proto(shape):
@@ -116,12 +127,21 @@ def _parse_shape(buf):
   dims = []
   for f, wt, v in _parse(buf):
     if f == 2:
+      _expect(wt, 2, 'TensorShapeProto.dim')
       size = 0
-      for f2, _, v2 in _parse(v):
+      for f2, wt2, v2 in _parse(v):
         if f2 == 1:
+          _expect(wt2, 0, 'Dim.size')
           size = v2 if v2 < (1 << 63) else v2 - (1 << 64)
       dims.append(size)
   return dims
+
+
+def _utf8(v):
+  try:
+    return v.decode('utf-8')
+  except UnicodeDecodeError:
+    raise MalformedProto('string field is not valid UTF-8')
 
 
 def _contig(a):
@@ -140,11 +160,26 @@ def decode_tensor(buf):
   dtype, shape, content = None, [], b''
   for f, wt, v in _parse(buf):
     if f == 1:
+      _expect(wt, 0, 'TensorProto.dtype')
+      if v not in _DT_INV:
+        raise MalformedProto('unsupported TensorProto dtype %d' % v)
       dtype = _DT_INV[v]
     elif f == 2:
+      _expect(wt, 2, 'TensorProto.tensor_shape')
       shape = _parse_shape(v)
     elif f == 4:
+      _expect(wt, 2, 'TensorProto.tensor_content')
       content = v
+  if dtype is None:
+    raise MalformedProto('TensorProto without dtype')
+  n = 1
+  for d in shape:
+    if d < 0:
+      raise MalformedProto('negative dimension')
+    n *= d
+  if n * np.dtype(dtype).itemsize != len(content):
+    raise MalformedProto('tensor_content has %d bytes, shape %s of %s needs %d' %
+                         (len(content), shape, np.dtype(dtype).name, n * np.dtype(dtype).itemsize))
   return np.frombuffer(content, dtype=dtype).reshape(shape)
 
 
@@ -168,14 +203,25 @@ def decode_structure(buf):
     if f == 1:
       return None
     if f == 33:
+      _expect(wt, 2, 'StructuredValue.tensor_spec_value')
       name, shape, dt = None, [], 1
-      for f2, _, v2 in _parse(v):
-        if f2 == 1: name = v2.decode()
-        elif f2 == 2: shape = _parse_shape(v2)
-        elif f2 == 3: dt = v2
+      for f2, wt2, v2 in _parse(v):
+        if f2 == 1:
+          _expect(wt2, 2, 'TensorSpecProto.name'); name = _utf8(v2)
+        elif f2 == 2:
+          _expect(wt2, 2, 'TensorSpecProto.shape'); shape = _parse_shape(v2)
+        elif f2 == 3:
+          _expect(wt2, 0, 'TensorSpecProto.dtype'); dt = v2
+      if dt not in _DT_INV:
+        raise MalformedProto('unsupported TensorSpecProto dtype %d' % dt)
       return TensorSpec(shape, _DT_INV[dt].name, name)
     if f in (51, 52):
-      items = [decode_structure(v2) for f2, _, v2 in _parse(v) if f2 == 1]
+      _expect(wt, 2, 'StructuredValue.list_value / tuple_value')
+      items = []
+      for f2, wt2, v2 in _parse(v):
+        if f2 == 1:
+          _expect(wt2, 2, 'ListValue.values')
+          items.append(decode_structure(v2))
       return tuple(items) if f == 52 else items
   return None
 
@@ -192,8 +238,10 @@ def _encode_call_request_raw(fn_name, tensor_bytes):
 def _decode_call_request_raw(buf):
   name, tensors = '', []
   for f, wt, v in _parse(buf):
-    if f == 1: name = v.decode('utf-8')
-    elif f == 2: tensors.append(bytes(v))
+    if f == 1:
+      _expect(wt, 2, 'CallRequest.function'); name = _utf8(v)
+    elif f == 2:
+      _expect(wt, 2, 'CallRequest.tensor'); tensors.append(bytes(v))
   return name, tensors
 
 
@@ -209,9 +257,12 @@ def _encode_call_response_raw(tensor_bytes, code=0, msg=''):
 def _decode_call_response_raw(buf):
   tensors, code, msg = [], 0, ''
   for f, wt, v in _parse(buf):
-    if f == 1: tensors.append(bytes(v))
-    elif f == 2: code = v
-    elif f == 3: msg = v.decode('utf-8')
+    if f == 1:
+      _expect(wt, 2, 'CallResponse.tensor'); tensors.append(bytes(v))
+    elif f == 2:
+      _expect(wt, 0, 'CallResponse.status_code'); code = v if v < (1 << 31) else v - (1 << 64)
+    elif f == 3:
+      _expect(wt, 2, 'CallResponse.status_error_message'); msg = _utf8(v)
   return tensors, code, msg
 
 
@@ -226,12 +277,15 @@ def _encode_init_response_raw(signatures):
 
 def _decode_init_response_raw(buf):
   sigs = []
-  for f, _, v in _parse(buf):
+  for f, wt, v in _parse(buf):
     if f == 1:
+      _expect(wt, 2, 'InitResponse.method_output_signature')
       name, spec = '', b''
-      for f2, _, v2 in _parse(v):
-        if f2 == 1: name = v2.decode('utf-8')
-        elif f2 == 2: spec = bytes(v2)
+      for f2, wt2, v2 in _parse(v):
+        if f2 == 1:
+          _expect(wt2, 2, 'MethodOutputSignature.name'); name = _utf8(v2)
+        elif f2 == 2:
+          _expect(wt2, 2, 'MethodOutputSignature.output_specs'); spec = bytes(v2)
       sigs.append((name, spec))
   return sigs
 
@@ -457,7 +511,10 @@ class Server(object):
   def _call_rpc(self, request_iterator, context):
     for req in request_iterator:
       try:
-        name, tensors = _decode_call_request(req)
+        try:
+          name, tensors = _decode_call_request(req)
+        except MalformedProto as e:       # what a failed ParseFromString is in grpc.cc
+          raise InvalidArgumentError(INVALID_ARGUMENT, 'Malformed CallRequest: %s' % e)
         outs = self.call_local(name, tensors)
         yield _encode_call_response(outs)
       except RpcError as e:

@@ -219,3 +219,49 @@ def test_tensorproto_and_structuredvalue_match_tf_schemas():
     want = bytes.fromhex(s['hex'])
     assert same(ops.decode_structure(want), spec), s['spec']
     assert ops.encode_structure(spec) == want, s['spec']    # byte-identical
+
+
+def test_decoders_reject_malformed_bytes_cleanly():
+  """Random bytes, truncations and bit flips of valid messages either decode or raise
+  ops.MalformedProto (a ValueError) -- never IndexError / MemoryError / a hang; a malformed
+  CallRequest on the wire comes back as InvalidArgument, like a failed ParseFromString."""
+  from seed_rl_b200.grpc import ops
+  rng = np.random.default_rng(0)
+  decoders = (ops.decode_tensor, ops.decode_structure, ops._decode_call_request_raw,
+              ops._decode_call_response_raw, ops._decode_init_response_raw, ops._decode_call_request)
+  valid = [ops.encode_tensor(rng.normal(size=(3, 4)).astype(np.float32)),
+           ops.encode_structure((TS([2, 3], 'float32', 'x'), [TS([], 'int64', None)])),
+           ops._encode_call_request('inference', [np.arange(5, dtype=np.int32), np.zeros((2, 2), np.uint8)]),
+           ops._encode_call_response([np.ones(3, np.float32)], 3, 'bad'),
+           ops._encode_init_response_raw([('inference', bytes([0x9a, 0x02, 0x00]))])]
+  cases = [bytes(rng.integers(0, 256, int(rng.integers(0, 48)), dtype=np.uint8)) for _ in range(4000)]
+  for v in valid:
+    for _ in range(300):
+      b = bytearray(v)
+      op = rng.integers(0, 3)
+      if op == 0 and len(b) > 1:
+        b = b[:int(rng.integers(0, len(b)))]
+      elif op == 1:
+        b[int(rng.integers(0, len(b)))] ^= 1 << int(rng.integers(0, 8))
+      else:
+        i = int(rng.integers(0, len(b) + 1)); b[i:i] = bytes(rng.integers(0, 256, 3, dtype=np.uint8))
+      cases.append(bytes(b))
+  outcomes = set()
+  for c in cases:
+    for d in decoders:
+      try:
+        d(c); outcomes.add('ok')
+      except ops.MalformedProto:
+        outcomes.add('malformed')
+  assert outcomes == {'ok', 'malformed'}
+
+
+def test_malformed_call_request_is_invalid_argument_on_the_stream(server_client):
+  from seed_rl_b200.grpc import ops
+  @ops.function((TS([4], 'int32', 'x'),), TS([4], 'int32', 'y'))
+  def foo(x):
+    return x + 1
+  server, _ = server_client(foo)
+  resp = list(server._call_rpc(iter([bytes([0x0a, 0xff, 0xff, 0xff, 0xff, 0x0f])]), None))     # length runs past the end
+  tensors, code, msg = ops._decode_call_response_raw(resp[0])
+  assert tensors == [] and code == ops.INVALID_ARGUMENT and msg.startswith('Malformed CallRequest')
