@@ -49,33 +49,18 @@ replay_sample_kernel(int limit, const float* __restrict__ priorities, float prio
   __shared__ float s_cdf[kReplayMax];
   __shared__ float s_red[32];
   const int tid = threadIdx.x;
-  for (int i = tid; i < limit; i += blockDim.x) s_cdf[i] = powf(priorities[i], priority_exp);
+  for (int i = tid; i < limit; i += blockDim.x) replay_pow_thread(i, priorities, priority_exp, s_cdf);
   __syncthreads();
   // serial prefix by one thread in index order: deterministic, and 100..8192 adds are nothing
-  if (tid == 0) {
-    float acc = 0.f;
-    for (int i = 0; i < limit; ++i) { acc += s_cdf[i]; s_cdf[i] = acc; }
-    s_red[0] = acc;
-  }
+  if (tid == 0) s_red[0] = replay_prefix_serial(limit, s_cdf);
   __syncthreads();
   const float total = s_red[0];
   if (probs_out)
     for (int i = tid; i < limit; i += blockDim.x)
       probs_out[i] = (s_cdf[i] - (i ? s_cdf[i - 1] : 0.f)) / total;
   float wmax = 0.f;
-  for (int j = tid; j < num_samples; j += blockDim.x) {
-    const float u = uniforms[j] * total;
-    int lo = 0, hi = limit - 1;
-    while (lo < hi) {                                 // first i with cdf[i] > u
-      const int mid = (lo + hi) >> 1;
-      if (s_cdf[mid] > u) hi = mid; else lo = mid + 1;
-    }
-    const float pi = (s_cdf[lo] - (lo ? s_cdf[lo - 1] : 0.f)) / total;
-    const float wj = powf((1.f / (float)limit) / pi, is_exp);
-    indices[j] = lo;
-    weights[j] = wj;
-    wmax = fmaxf(wmax, wj);
-  }
+  for (int j = tid; j < num_samples; j += blockDim.x)
+    wmax = fmaxf(wmax, replay_sample_thread(j, limit, s_cdf, total, is_exp, uniforms, indices, weights));
   // max over the CTA, then normalise
   for (int o = 16; o; o >>= 1) wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, o));
   __syncthreads();

@@ -127,4 +127,31 @@ SEEDRL_HD void r2d2_loss_thread(const R2d2LossParams& p, int b) {
   p.loss[b] = 0.5f * sq;                                                         // :329
 }
 
+// ---- prioritized replay sampling (common/utils.py:327-352), phase bodies ---------------------
+// phase 1 (thread i): s_cdf[i] = prio_i ^ alpha
+SEEDRL_HD void replay_pow_thread(int i, const float* priorities, float priority_exp, float* s_cdf) {
+  s_cdf[i] = powf(priorities[i], priority_exp);
+}
+// phase 2 (one thread): inclusive prefix in index order (deterministic); returns the total
+SEEDRL_HD float replay_prefix_serial(int limit, float* s_cdf) {
+  float acc = 0.f;
+  for (int i = 0; i < limit; ++i) { acc += s_cdf[i]; s_cdf[i] = acc; }
+  return acc;
+}
+// phase 3 (thread j): index = first i with cdf[i] > u_j * total; un-normalised importance weight
+SEEDRL_HD float replay_sample_thread(int j, int limit, const float* s_cdf, float total, float is_exp,
+                                     const float* uniforms, int64_t* indices, float* weights) {
+  const float u = uniforms[j] * total;
+  int lo = 0, hi = limit - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (s_cdf[mid] > u) hi = mid; else lo = mid + 1;
+  }
+  const float pi = (s_cdf[lo] - (lo ? s_cdf[lo - 1] : 0.f)) / total;
+  const float wj = powf((1.f / (float)limit) / pi, is_exp);
+  indices[j] = lo;
+  weights[j] = wj;
+  return wj;
+}
+
 }  // namespace seedrl

@@ -33,3 +33,20 @@ extern "C" int emu_r2d2_loss(int T, int B, int A, const float* q_train, const fl
   for (int b = 0; b < B; ++b) seedrl::r2d2_loss_thread(p, b);
   return 0;
 }
+
+// replay_sample_kernel's phases in the order the kernel runs them (one CTA)
+extern "C" int emu_replay_sample(int limit, const float* priorities, float priority_exp, float is_exp,
+                                 int num_samples, const float* uniforms, int64_t* indices, float* weights,
+                                 float* probs_out) {
+  float* cdf = new float[limit];
+  for (int i = 0; i < limit; ++i) seedrl::replay_pow_thread(i, priorities, priority_exp, cdf);
+  const float total = seedrl::replay_prefix_serial(limit, cdf);
+  if (probs_out)
+    for (int i = 0; i < limit; ++i) probs_out[i] = (cdf[i] - (i ? cdf[i - 1] : 0.f)) / total;
+  float wmax = 0.f;
+  for (int j = 0; j < num_samples; ++j)
+    wmax = fmaxf(wmax, seedrl::replay_sample_thread(j, limit, cdf, total, is_exp, uniforms, indices, weights));
+  for (int j = 0; j < num_samples; ++j) weights[j] /= wmax;
+  delete[] cdf;
+  return 0;
+}

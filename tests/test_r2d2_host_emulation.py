@@ -86,3 +86,22 @@ def test_loss_thread_body_vs_oracle(emu, T, B, A, n):
   # through the scratch array instead (scratch[b, 1:T] = targets[1:] before rescaling)
   for b in range(B):
     np.testing.assert_allclose(scratch[b, :T], R.n_step_bellman_target(r, d, qmax, gamma, n)[:, b], rtol=2e-6, atol=1e-6)
+
+
+def test_replay_sample_phase_bodies(emu):                       # common/utils.py:327-352
+  rng = np.random.default_rng(0)
+  prio = (rng.random(100) + 0.01).astype(np.float32); limit = 70
+  u = rng.random(4096).astype(np.float32)
+  idx = np.zeros(4096, np.int64); w = np.zeros(4096, np.float32); probs = np.zeros(limit, np.float32)
+  f = ctypes.c_float
+  assert emu.emu_replay_sample(limit, ptr(prio), f(0.9), f(0.6), 4096, ptr(u), ptr(idx), ptr(w), ptr(probs)) == 0
+  p = R.replay_probabilities(prio, limit, 0.9)
+  np.testing.assert_allclose(probs, p, rtol=2e-5)
+  assert idx.min() >= 0 and idx.max() < limit and w.max() == 1.0
+  np.testing.assert_allclose(w, R.replay_importance_weights(p, idx, 0.6), rtol=2e-4)
+  freq = np.bincount(idx, minlength=limit) / len(idx)
+  assert np.abs(freq - p).max() < 0.02                         # statistical, like tests/utils_test.py:353-365
+  # the draw is the inverse CDF of the given uniforms
+  cdf = np.cumsum(np.power(prio[:limit], np.float32(0.9)).astype(np.float32), dtype=np.float32)
+  want = np.minimum(np.searchsorted(cdf, u * cdf[-1], side='right'), limit - 1)
+  assert (idx == want).mean() > 0.999                          # (equal up to fp32 prefix rounding at bin edges)
