@@ -3,10 +3,13 @@
 after the network unroll) with autograd standing in for tf.GradientTape
 (learner.py:261-264).
 
-Parity status: the reference has NO test of compute_loss for V-trace
-(SURVEY 4): this file is "parity unpinned" except through its V-trace core,
-which is pinned (see vtrace_oracle.py) and the categorical log_prob
-(pinned by reference tests/vtrace_test.py:88-115).
+Parity status: the reference has NO test of compute_loss for V-trace.  The
+FORWARD composition (row slicing, reward clip, discounts, the five loss terms and the 11
+logged scalars with their names) is pinned against the UNMODIFIED reference compute_loss
+executed over tests/golden/tf_numpy_shim.py (tests/golden/make_golden_loss.py ->
+loss_golden.npz, tests/test_oracle_golden.py); its V-trace core is pinned separately
+(vtrace_oracle.py) and the categorical log_prob by reference tests/vtrace_test.py:88-115.
+The gradient (tf.GradientTape) stays "parity unpinned": torch autograd of this forward.
 """
 import collections
 

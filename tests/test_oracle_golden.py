@@ -185,3 +185,24 @@ def test_aggregator_oracle():
   assert a.read([0, 1, 2, 3])[0].tolist() == [0, 43, 0, 0]
   a.replace([0, 2], [np.array([1, 2])])
   assert a.read([0, 1, 2, 3])[0].tolist() == [1, 43, 2, 0]
+
+
+@pytest.mark.parametrize('case', ['a', 'b', 'c'])
+def test_compute_loss_composition_against_reference_source(case):
+  """oracle/loss_oracle.py against tests/golden/loss_golden.npz = the UNMODIFIED reference
+  compute_loss (agents/vtrace/learner.py:73-159) and common/vtrace.py executed over the numpy
+  shim (tests/golden/make_golden_loss.py): total loss and every logged scalar, by name."""
+  import os
+  from oracle import loss_oracle
+  g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'loss_golden.npz'))
+  d, lam, bc, ec, kc, mar, te = (float(x) for x in g[case + '_cfg'])
+  cfg = loss_oracle.default_config(discounting=d, lambda_=lam, baseline_cost=bc, entropy_cost=ec, kl_cost=kc,
+                                   max_abs_reward=mar, target_entropy=te or None)
+  total, logs, _ = loss_oracle.compute_loss_from_outputs(
+      cfg, g[case + '_ll'], g[case + '_lb'], g[case + '_bl'], g[case + '_act'], g[case + '_rew'], g[case + '_done'])
+  np.testing.assert_allclose(float(total), float(g[case + '_total']), rtol=2e-5, atol=2e-6)
+  keys = [k[len(case) + 5:].replace('__', '/') for k in g.files if k.startswith(case + '_log_')]
+  assert sorted(keys) == sorted(logs)                     # same scalar names as the reference logs
+  for k in keys:
+    np.testing.assert_allclose(float(logs[k]), float(g['%s_log_%s' % (case, k.replace('/', '__'))]),
+                               rtol=2e-5, atol=2e-6, err_msg=k)
