@@ -9,8 +9,11 @@ the policy networks on the hot path:
 Keras layer arithmetic (TF 2.4.1 Conv2D / MaxPool2D(padding='same') / Dense /
 LSTMCell, not vendored under /root/reference) is restated from its published
 semantics; the reference's tests pin only shapes/variable counts
-(tests/agents_test.py:45 -> 39 trainable tensors) => NUMERICS PARITY UNPINNED
-for the network; pinned structure: variable count, shapes, gate order.
+(tests/agents_test.py:45 -> 39 trainable tensors) => the layer NUMERICS are parity-unpinned
+(cross-checked against an independent numpy-loop restatement,
+tests/test_oracle_layers_independent.py).  The WIRING of ImpalaDeep is pinned: the unmodified
+reference classes run over a Keras-layer shim (tests/golden/make_golden_net.py) reproduce
+this file's outputs for the same weights (tests/test_oracle_golden.py).
 
 Weights use the Keras layouts: conv kernel HWIO [kh,kw,cin,cout], dense
 [in,out], LSTM kernel [in,4H] / recurrent [H,4H] with gate order i,f,c,o.

@@ -206,3 +206,27 @@ def test_compute_loss_composition_against_reference_source(case):
   for k in keys:
     np.testing.assert_allclose(float(logs[k]), float(g['%s_log_%s' % (case, k.replace('/', '__'))]),
                                rtol=2e-5, atol=2e-6, err_msg=k)
+
+
+def test_impala_deep_wiring_against_reference_source():
+  """oracle/net_oracle.py against tests/golden/net_golden.npz = the UNMODIFIED reference
+  dmlab/networks.py (_Stack, ImpalaDeep) + common/utils.batch_apply executed over a Keras-layer
+  shim (tests/golden/make_golden_net.py): same weights, same inputs -> same logits, baseline,
+  final LSTM state, for a 5-step unroll with done-resets and for a single inference step."""
+  import os, sys
+  import torch
+  from oracle import net_oracle
+  sys.path.insert(0, os.path.join(os.path.dirname(__file__), 'golden'))
+  import net_golden_params as G
+  g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'net_golden.npz'))
+  p = G.make_params(); i = G.make_inputs()
+  t = torch.as_tensor
+  with torch.no_grad():
+    logits, baseline, (h, c) = net_oracle.unroll('deep', p, t(i['prev']), t(i['rew']), t(i['done']), t(i['obs']),
+                                                 (t(i['h0']), t(i['c0'])), G.A)
+    l1, b1, (h1, _) = net_oracle.unroll('deep', p, t(i['prev'][:1]), t(i['rew'][:1]), t(i['done'][:1]), t(i['obs'][:1]),
+                                         (t(i['h0']), t(i['c0'])), G.A)
+  for got, want in ((logits, 'logits'), (baseline, 'baseline'), (h, 'h'), (c, 'c'), (l1[0], 'logits1'),
+                    (b1[0], 'baseline1'), (h1, 'h1')):
+    np.testing.assert_allclose(got.numpy(), g[want], rtol=1e-5, atol=1e-6, err_msg=want)
+  assert i['done'].any() and not i['done'].all()          # the reset path is exercised
