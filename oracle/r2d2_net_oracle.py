@@ -8,8 +8,10 @@ agent network, SURVEY 8(a) row a11:
 Keras layer arithmetic (TF 2.4.1 Conv2D(padding='valid') / Dense / LSTMCell) is restated from
 its published semantics; the reference's tests pin shapes only (atari/networks_test.py:78-117:
 unrolls run, the torso sees stack_size channels, the core input is 512 + num_actions + 1 wide)
-=> NUMERICS PARITY UNPINNED for the network; pinned: variable structure, shapes, gate order,
-reset-on-done semantics (through stack_frames / _unroll_cell known-answer cases).
+=> layer NUMERICS parity-unpinned; pinned: variable structure, shapes, and the WIRING -- the
+unmodified reference classes executed over a Keras-layer shim with these weights
+(tests/golden/make_golden_r2d2_net.py) reproduce this file's Q values, greedy actions, LSTM
+state and (bit for bit) packed frame state (tests/test_oracle_r2d2.py).
 
 Weights use the Keras layouts (conv HWIO, dense [in,out], LSTM [in,4H]/[H,4H], gates i,f,c,o).
 """

@@ -150,3 +150,26 @@ def test_dueling_lstm_dqn_net_structure():
     full, _ = N.unroll(p, _pa, _rw, done, obs, st, A, S)
     np.testing.assert_allclose(torch.cat([out_a.q_values, out_b.q_values]).detach().numpy(),
                                full.q_values.detach().numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_dueling_lstm_dqn_net_wiring_against_reference_source():
+  """oracle/r2d2_net_oracle.py against tests/golden/r2d2_net_golden.npz = the UNMODIFIED reference
+  atari/networks.py (stack_frames, _unroll_cell, DuelingLSTMDQNNet) + common/utils.batch_apply
+  executed over a Keras-layer shim (tests/golden/make_golden_r2d2_net.py): same weights and
+  inputs -> same Q values, greedy actions, final LSTM state and bit-identical packed frame state."""
+  import sys
+  import torch
+  from oracle import r2d2_net_oracle as N
+  sys.path.insert(0, os.path.join(os.path.dirname(__file__), 'golden'))
+  import make_golden_r2d2_net as GEN
+  g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'r2d2_net_golden.npz'))
+  p = GEN.make_params(); i = GEN.make_inputs()
+  with torch.no_grad():
+    out, st = N.unroll(p, i['prev'], i['rew'], i['done'], i['obs'],
+                       N.AgentState((torch.as_tensor(i['h0']), torch.as_tensor(i['c0'])), i['fstate']), GEN.A, GEN.S)
+  np.testing.assert_allclose(out.q_values.numpy(), g['q'], rtol=1e-5, atol=1e-6)
+  np.testing.assert_array_equal(out.action.numpy(), g['action'])
+  np.testing.assert_allclose(st.core_state[0].numpy(), g['h'], rtol=1e-5, atol=1e-6)
+  np.testing.assert_allclose(st.core_state[1].numpy(), g['c'], rtol=1e-5, atol=1e-6)
+  np.testing.assert_array_equal(st.frame_stacking_state, g['fstate'])
+  assert i['done'].any() and not i['done'].all()
