@@ -13,7 +13,9 @@ Follows the reference line by line (paths relative to the reference repository):
 Pinned (tests/test_oracle_r2d2.py) against the known-answer cases of
 agents/r2d2/learner_test.py:60-70,114-198, atari/networks_test.py:176-247 and against tests/golden/r2d2_golden.npz, produced
 by executing the UNMODIFIED reference functions over tests/golden/tf_numpy_shim.py
-(tests/golden/make_golden_r2d2.py).  What stays unpinned: tf.random.categorical's Philox
+(tests/golden/make_golden_r2d2.py); the replay functions additionally against the unmodified
+PrioritizedReplay class run over a tf.Variable stand-in (tests/golden/make_golden_replay.py).
+What stays unpinned: tf.random.categorical's Philox
 stream (sampling is statistical in the reference's own tests too).
 """
 import numpy as np

@@ -173,3 +173,31 @@ def test_dueling_lstm_dqn_net_wiring_against_reference_source():
   np.testing.assert_allclose(st.core_state[1].numpy(), g['c'], rtol=1e-5, atol=1e-6)
   np.testing.assert_array_equal(st.frame_stacking_state, g['fstate'])
   assert i['done'].any() and not i['done'].all()
+
+
+def test_prioritized_replay_against_reference_class():
+  """oracle replay functions against tests/golden/replay_golden.npz = the UNMODIFIED reference
+  PrioritizedReplay (common/utils.py:260-370) executed over a tf.Variable stand-in
+  (tests/golden/make_golden_replay.py): FIFO wrap-around insertion, probabilities over the
+  filled part of the ring, inverse-CDF draws from the recorded uniforms, importance weights,
+  priority updates."""
+  g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'replay_golden.npz'))
+  size, table, inserted = 7, np.zeros(7, np.float32), 0
+  store = np.zeros((7, 3), np.float32)
+  for s in range(3):
+    pr = g['ins%d_prio' % s]
+    idx = R.replay_insert_indices(inserted, len(pr), size)
+    np.testing.assert_array_equal(idx, g['ins%d_idx' % s])
+    table[idx] = pr; store[idx] = g['ins%d_vals' % s]; inserted += len(pr)
+    assert inserted == int(g['smp%d_num_inserted' % s])
+    np.testing.assert_array_equal(table, g['smp%d_prio_table' % s])
+    p = R.replay_probabilities(table, inserted, 0.9)
+    draw = np.minimum(np.searchsorted(np.cumsum(p.astype(np.float64)), g['smp%d_u' % s], side='right'), len(p) - 1)
+    np.testing.assert_array_equal(draw, g['smp%d_idx' % s])
+    np.testing.assert_allclose(R.replay_importance_weights(p, draw, 0.6), g['smp%d_w' % s], rtol=1e-5)
+    np.testing.assert_array_equal(store[draw], g['smp%d_vals' % s])
+    table[draw] = g['upd%d_prio' % s]                         # update_priorities
+    np.testing.assert_array_equal(table, g['upd%d_table' % s])
+  assert (g['ins2_idx'] < g['ins2_idx'][0]).any()             # the third insert wrapped around
+  np.testing.assert_array_equal(g['uni_w'], np.ones(4, np.float32))   # priority_exp == 0: unit weights
+  np.testing.assert_array_equal(g['uni_idx'], (g['uni_u'] * 7).astype(np.int64))
