@@ -35,19 +35,23 @@ OBS = (84, 84, 4)
 def parse_args():
   p = argparse.ArgumentParser()
   p.add_argument('--gpus', type=int, default=1)
-  p.add_argument('--steps', type=int, default=20)
-  p.add_argument('--warmup', type=int, default=5)
+  p.add_argument('--steps', type=int, default=50)
+  p.add_argument('--warmup', type=int, default=10)
   p.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   p.add_argument('--net', default='deep', choices=['deep', 'shallow'])
   p.add_argument('--batch', type=int, default=64, help='unrolls per GPU')
   p.add_argument('--unroll', type=int, default=20)
-  p.add_argument('--cpu-batch', type=int, default=8, help='unrolls per CPU-baseline step')
-  p.add_argument('--conv', default='tc', choices=['simt', 'tc', 'tc3'],
+  p.add_argument('--cpu-batch', type=int, default=0,
+                 help='unrolls per CPU-baseline step (0 = the same batch as the GPU arm)')
+  p.add_argument('--conv', default='tc3', choices=['simt', 'tc', 'tc3'],
                  help="contraction path of the convs and dense layers: fp32 SIMT, tcgen05 bf16, or "
                       "tcgen05 bf16x3 (fp32-faithful split operands; the parity mode)")
   p.add_argument('--no-extras', action='store_true',
                  help='skip the profiling pass, the loss-kernel sweep and the CPU baseline')
-  return p.parse_args()
+  a = p.parse_args()
+  if a.cpu_batch <= 0:
+    a.cpu_batch = a.batch
+  return a
 
 
 # ----------------------------------------------------------------------------------------
@@ -89,30 +93,32 @@ def run_reference(args):
   rank = int(os.environ.get('RANK', '0'))
   if rank != 0:
     return
-  r = cpu_learner_throughput(args.net, args.unroll, args.cpu_batch, args.steps, min(args.warmup, 2))
+  r = cpu_learner_throughput(args.net, args.unroll, args.cpu_batch, args.steps, args.warmup)
   line = {
       'impl': 'reference', 'metric': METRIC, 'value': r['value'], 'unit': UNIT,
-      'n_gpus': args.gpus, 'steps': args.steps, 'warmup': min(args.warmup, 2),
+      'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
       'ms_per_step': r['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak',
       'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-      'config': workload_config(args, 1, cpu=True),
+      'config': workload_config(args, max(args.gpus, 1)),
       'cpu_baseline': {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
                        'sample': r['sample']},
       'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
       'gpu_launches': 0,
+      'cpu_batch_per_step': args.cpu_batch,
       'note': 'TensorFlow 2.4.1 is not installable here (no network): this arm times the CPU '
               'oracle, a line-by-line torch-CPU restatement of the reference learner step.'}
   emit(line)
 
 
-def workload_config(args, n, cpu=False):
+def workload_config(args, n):
+  """Identical for both arms (the reference arm runs the same batch per step on the host)."""
   return {
       'workload': 'Impala%s learner step, T=%d, B=%d unrolls/GPU, synthetic 84x84x4 uint8 '
                   '(BASELINE configs[3]; per-GPU slice is the configs[1]/[2] shape)' %
                   ('Deep' if args.net == 'deep' else 'Shallow', args.unroll, args.batch),
       'net': 'ImpalaDeep (dmlab/networks.py:63-171)' if args.net == 'deep' else 'IMPALA shallow (paper)',
-      'unroll_length': args.unroll, 'batch_per_gpu': args.cpu_batch if cpu else args.batch,
-      'global_batch': (args.cpu_batch if cpu else args.batch * n), 'num_actions': A,
+      'unroll_length': args.unroll, 'batch_per_gpu': args.batch,
+      'global_batch': args.batch * n, 'num_actions': A,
       'num_action_repeats': 1,
       'optimizer': 'Adam lr=4.8e-4 beta1=0 eps=3.125e-7 (dmlab/vtrace_main.py:46-51)',
       'loss': 'gamma=0.99 lambda=1 baseline_cost=0.5 entropy_cost=2.5e-4 kl_cost=0',
@@ -269,17 +275,24 @@ def main():
       dist.barrier()
     torch.cuda.synchronize()
 
+  last_median = [None]
+
   def timed(fn, k):
+    """EXACTLY k calls between one pair of CUDA events (barrier + synchronize on both sides,
+    MAX over ranks); an event after every call also gives the per-step median (reported beside
+    the mean, never instead of it)."""
     barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(k):
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(k + 1)]
+    evs[0].record()
+    for i in range(k):
       fn()
-    e1.record()
+      evs[i + 1].record()
     barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device='cuda')
+    ms = torch.tensor([evs[0].elapsed_time(evs[k])], device='cuda')
     if world > 1:
       dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    per = sorted(evs[i].elapsed_time(evs[i + 1]) for i in range(k))
+    last_median[0] = per[len(per) // 2]
     return float(ms) / k
 
   # ---- kernel-only (inputs resident in HBM) --------------------------------------------
@@ -289,6 +302,8 @@ def main():
   n0 = _lib.launch_count()
   ms_step = timed(lambda: step.minimize(unroll), args.steps)
   launches = (_lib.launch_count() - n0) // args.steps
+  ms_step_median = last_median[0]
+  agent.check_errors()      # raises if any kernel of the timed steps timed out on a barrier
   clocks = sampler.stop() if sampler else None
   value = world * B * T / (ms_step * 1e-3)
 
@@ -328,11 +343,12 @@ def main():
 
   line = {
       'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-      'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'higher_is_better': True,
+      'warmup': max(args.warmup, 3), 'ms_per_step': ms_step, 'ms_per_step_median': ms_step_median,
+      'higher_is_better': True,
       'scaling': 'weak', 'vs_baseline': None,
       'dtype': {'tc': 'bf16', 'tc3': 'bf16x3 (fp32-faithful tensor-core contraction), f32 elsewhere',
                 'simt': 'f32'}[args.conv], 'data': 'synthetic',
-      'config': dict(workload_config(args, world), conv_path=args.conv), 'clocks': clocks,
+      'config': workload_config(args, world), 'conv_path': args.conv, 'clocks': clocks,
       'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e,
               'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes,
               'api': 'seed_rl_b200.agents.vtrace.learner.DeviceFeeder.put/get + LearnerStep.minimize(Unroll)',
@@ -445,7 +461,7 @@ def main():
         del ag, stp
       line['other_conv_paths'] = others
       # ---- CPU baseline beside it (bounded sample) ----------------------------------------
-      r = cpu_learner_throughput(args.net, T, args.cpu_batch, 3, 1)
+      r = cpu_learner_throughput(args.net, T, args.cpu_batch, 5, 2)
       line['cpu_baseline'] = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
                               'sample': r['sample'], 'ms_per_step': r['ms_per_step']}
 
@@ -477,9 +493,7 @@ def main():
             'bound': 'hbm', 'algorithmic_bytes_per_launch': alg, 'avg_launch_ms': ms_k,
             'achieved': alg / (ms_k * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
             'frac': alg / (ms_k * 1e-3) / 1e9 / hbm_peak,
-            'traffic': 254415104 if not splitk else None,
-            'traffic_source': 'profiles/r01_ncu_conv_fwd_16_16.txt: dram read 151.78 MB + write 102.63 MB '
-                              '(the rest of the 144.5 MB output was still in L2 when the kernel ended)',
+            'traffic': None,
             'launches_per_step': 8, 'ok': int(errk.item()) == 0}
         del xk, ok
       except Exception as exc:        # pylint: disable=broad-except

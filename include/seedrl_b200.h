@@ -170,7 +170,9 @@ size_t seedrl_net_arena_floats(const seedrl_net* net);
  * Dense / LSTM-projection / head GEMMs:
  * 0 = fp32 SIMT (bit-reproducible fp32 reference path), 1 = tcgen05 tensor cores, bf16
  * operands with fp32 accumulation, 2 = tcgen05 with bf16x3 split operands (hi*hi + lo*hi +
- * hi*lo: fp32-faithful to ~2^-16 relative). */
+ * hi*lo: fp32-faithful to ~2^-16 relative), 3 = the same bf16x3 arithmetic with the 16/32-channel
+ * activations and gradients kept in HBM as bf16 hi/lo channel-group planes (the UMMA operand
+ * format): TMA-fed, warp-specialised conv kernels (csrc/conv_planes.cu; deep net only). */
 int seedrl_net_set_conv_mode(seedrl_net* net, int mode);
 /* LSTM recurrence: 1 (default) = one persistent cooperative kernel for all T steps each way,
  * 0 = a GEMM + a pointwise kernel per time step. */
@@ -202,6 +204,14 @@ int seedrl_net_backward(const seedrl_net* net, const float* params, int T1, int 
                         const float* dlogits, const float* dbaseline,
                         float* grads, void* workspace, size_t workspace_bytes,
                         seedrl_stream_t stream);
+/* The tcgen05 / persistent kernels never spin forever: a barrier wait that expires sets an
+ * error flag in the workspace and the kernel bails out (its results are then garbage).
+ * seedrl_net_forward clears the flag; this call copies it back (synchronising `stream`) and
+ * returns SEEDRL_ERR_INTERNAL if any kernel of the last forward/backward on this workspace
+ * set it.  (No reference analogue: TF raises from the op; here the caller polls at a point
+ * that is synchronous anyway -- when it reads the loss.) */
+int seedrl_net_check_error(const seedrl_net* net, int T1, int B, void* workspace,
+                           size_t workspace_bytes, seedrl_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * (a7/a8) Per-environment state on the GPU.  Replaces
@@ -375,6 +385,23 @@ int seedrl_debug_sgemm(int ta, int tb, int M, int N, int K, const float* A, int 
                        const float* B, int ldb, float* C, int ldc, const float* bias,
                        const float* mask, int ldm, int relu, int accumulate, int a_relu,
                        seedrl_stream_t stream);
+
+/* ---- plane-tensor convolution path (conv_mode 3) test hooks: single kernels of
+ * csrc/conv_planes.cu, so the GPU parity tests can localise a failure.  Not on the product path. */
+size_t seedrl_debug_planes_bytes(int N, int H, int W, int C);
+int seedrl_debug_to_planes(int N, int H, int W, int C, int relu, const float* x, void* out,
+                           seedrl_stream_t stream);
+int seedrl_debug_from_planes(int N, int H, int W, int C, const void* in, float* y,
+                             seedrl_stream_t stream);
+int seedrl_debug_convp(int cin, int cout, int N, int H, int W, const void* in, const float* w,
+                       const float* bias, const void* mask, const void* res, int flip,
+                       void* out_raw, void* out_relu, float* out_nhwc, void* wq_scratch,
+                       int* error_flag, seedrl_stream_t stream);
+int seedrl_debug_wgradp(int cin, int cout, int N, int H, int W, const void* x, const void* dy,
+                        float* dw, float* db, float* partial, size_t partial_bytes,
+                        int* error_flag, seedrl_stream_t stream);
+int seedrl_debug_poolp(int backward, int N, int H, int W, int C, const void* in, void* out_raw,
+                       void* out_relu, float* out_nhwc, uint8_t* idx, seedrl_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -74,6 +74,7 @@ SIGNATURES = {
         (c_int, [P, P, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, c_size_t, P]),
     'seedrl_net_backward':
         (c_int, [P, P, c_int, c_int, P, P, P, P, P, P, P, P, c_size_t, P]),
+    'seedrl_net_check_error': (c_int, [P, c_int, c_int, P, c_size_t, P]),
     'seedrl_store_append_field': (c_int, [P, P, P, c_int, c_int, c_size_t, P, P]),
     'seedrl_store_advance': (c_int, [P, P, c_int, c_int, P, P, P]),
     'seedrl_store_gather_field': (c_int, [P, P, c_int, c_int, c_size_t, c_int, c_int, P, P]),
@@ -103,6 +104,12 @@ SIGNATURES = {
     'seedrl_profile_category_name': (ctypes.c_char_p, [c_int]),
     'seedrl_profile_begin': (c_int, [P]),
     'seedrl_profile_end': (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_u64)]),
+    'seedrl_debug_planes_bytes': (c_size_t, [c_int, c_int, c_int, c_int]),
+    'seedrl_debug_to_planes': (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P]),
+    'seedrl_debug_from_planes': (c_int, [c_int, c_int, c_int, c_int, P, P, P]),
+    'seedrl_debug_convp': (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, c_int, P, P, P, P, P, P]),
+    'seedrl_debug_wgradp': (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, c_size_t, P, P]),
+    'seedrl_debug_poolp': (c_int, [c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
     'seedrl_debug_conv3x3': (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P]),
     'seedrl_debug_conv3x3_flip': (c_int, [c_int, c_int, P, P, P]),
     'seedrl_debug_conv3x3_tc':

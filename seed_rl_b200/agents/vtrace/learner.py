@@ -192,8 +192,12 @@ class LearnerStep(object):
   """`minimize` of reference learner.py:255-280 for one replica (= one GPU/process)."""
 
   def __init__(self, agent, optimizer, parametric_action_distribution=None, settings=None,
-               logger=None, process_group=None, grad_reduce='sum'):
+               logger=None, process_group=None, grad_reduce='sum', check_errors_every=64):
     self.agent = agent
+    # the kernels' bounded-wait error flag is polled (one 4-byte D2H + stream sync) every
+    # `check_errors_every` steps; 0 = never (the caller polls agent.check_errors() itself)
+    self.check_errors_every = int(check_errors_every)
+    self._steps = 0
     self.optimizer = optimizer
     self.dist = parametric_action_distribution
     self.settings = settings or default_loss_settings()
@@ -230,6 +234,9 @@ class LearnerStep(object):
   def minimize(self, unroll):
     loss, logs = self.compute_gradients(unroll)
     self.apply_gradients()
+    self._steps += 1
+    if self.check_errors_every and (self._steps == 1 or self._steps % self.check_errors_every == 0):
+      self.agent.check_errors()
     return loss, logs
 
 

@@ -117,17 +117,22 @@ class InferenceHost(object):
       completed_ids, unrolls = self.store.append(env_ids, (prev_actions, env_dev, agent_outputs),
                                                  check_duplicates=True)
       n_done = int(completed_ids.numel())
+      pending = []
       if n_done:
         first = self.first_agent_states.read(completed_ids)
         flat = utils.flatten(unrolls)
         for i in range(n_done):     # one queue element per unroll, as in the reference
           u = utils.pack_sequence_as(self.store._specs, [f[:, i] for f in flat])
-          self.unroll_queue.enqueue(Unroll((first[0][i], first[1][i]), *u))
+          pending.append(Unroll((first[0][i], first[1][i]), *u))
         self.first_agent_states.replace(completed_ids, self.agent_states.read(completed_ids))
       # Update current state (:402-403) and return the actions (:405).
       self.agent_states.replace(ids_dev, curr_states)
       self.actions.replace(ids_dev, agent_outputs.action)
       out = agent_outputs.action.cpu()       # D2H + sync of this stream
+    # The unrolls were produced on self.stream, which the blocking copy above has drained: only
+    # now are they handed to the learner thread (which consumes them on another stream).
+    for u in pending:
+      self.unroll_queue.enqueue(u)
     return out.numpy()
 
 
@@ -135,6 +140,14 @@ def dequeue_batch(unroll_queue, batch_size):
   """reference learner.py:418-432: B unrolls -> one time-major batch.  Unrolls are already
   [T+1, ...] on the GPU; stacking along dim 1 IS the time-major layout."""
   items = [unroll_queue.dequeue() for _ in range(batch_size)]
+  if torch.cuda.is_available():
+    # the items were allocated on the inference stream: tell the caching allocator that this
+    # stream reads them, so their blocks are not recycled under the (asynchronous) stack below
+    cur = torch.cuda.current_stream()
+    for it in items:
+      for t in utils.flatten(it):
+        if isinstance(t, torch.Tensor) and t.is_cuda:
+          t.record_stream(cur)
   state = tuple(torch.stack([it.agent_state[k] for it in items]) for k in range(2))
   def stack(field):
     return utils.map_structure(lambda *xs: torch.stack(xs, dim=1),

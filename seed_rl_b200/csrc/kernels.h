@@ -88,6 +88,39 @@ int conv3x3_tc_forward(int cin, int cout, int in_mode, int split, int N, int H, 
                        const void* wq, const float* bias, const float* mask, const float* res,
                        float* out, int variant, int* err, cudaStream_t st);
 
+// conv_planes.cu ("planes" path: activations stored in HBM as bf16 hi/lo channel-group planes of
+// the padded tall image = the UMMA operand format; TMA-fed, warp-specialised kernels)
+constexpr int kPlanesTryNext = -12347;
+#define SEEDRL_TRY_RC(expr)             \
+  do {                                  \
+    const int rc__ = (expr);            \
+    if (rc__ != SEEDRL_OK) return rc__; \
+  } while (0)
+long long planes_positions(int N, int H, int W);          // storage positions per plane (Lp)
+size_t planes_bytes(int N, int H, int W, int C);          // 2 * C/8 planes x Lp x 16 B
+struct PlaneConv {
+  int N, H, W;
+  const void* in;        // plane tensor, CIN channels
+  const void* wq;        // packed weights (hi | lo), conv3x3_tc_pack_weights layout, split = 1
+  const float* bias;     // [COUT] or null
+  const void* mask;      // plane tensor (COUT ch) of the ReLU'd forward activation: out = 0 where it is 0
+  const void* res;       // plane tensor (COUT ch) added to the result, or null
+  void* out_raw;         // plane tensor, or null
+  void* out_relu;        // plane tensor holding relu(result), or null
+  float* out_nhwc;       // fp32 [N,H,W,COUT], or null
+  int* err;
+};
+bool convp_supported(int cin, int cout);
+int convp_forward(int cin, int cout, const PlaneConv& c, cudaStream_t st);
+int wgradp(int cin, int cout, int N, int H, int W, const void* x, const void* dy, float* dw, float* db,
+           int* err, WgradBatch* batch, cudaStream_t st);
+int to_planes(int N, int H, int W, int C, int relu, const float* x, void* out, cudaStream_t st);
+int from_planes(int N, int H, int W, int C, const void* in, float* y, cudaStream_t st);
+int poolp_forward(int N, int H, int W, int C, const float* x, void* out_raw, void* out_relu, uint8_t* idx,
+                  cudaStream_t st);
+int poolp_backward(int N, int H, int W, int C, const void* dy, const uint8_t* idx, void* dx_planes,
+                   float* dx_nhwc, cudaStream_t st);
+
 // conv_kernels.cu
 int conv3x3_forward(int cin, int cout, int in_mode, int N, int H, int W, const void* in,
                     const float* w, const float* bias, const float* mask, const float* res,

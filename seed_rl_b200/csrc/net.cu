@@ -88,7 +88,12 @@ struct Bump {
   }
 };
 
-struct StackBufs { size_t a0, p, idx, c0, o0, c1, o1; };
+struct StackBufs {
+  size_t a0, p, idx, c0, o0, c1, o1;
+  // conv_mode 3 (plane tensors, conv_planes.cu): raw / ReLU'd pooled activation, ReLU'd c0 / c1,
+  // raw / ReLU'd o0, raw o1 (the last stack's o1 stays fp32 NHWC for the Dense layer)
+  size_t praw, prelu, c0r, o0raw, o0relu, c1r, o1p;
+};
 
 // packed-weight slot: (hi + lo) x 9 x 32 x 32 bf16; deferred weight-gradient partials of all
 // 15 convs: 148 CTAs x 97 680 floats (57.8 MB) rounded up
@@ -102,6 +107,7 @@ struct Plan {
   size_t xc, z, hp, cs, hs, c0buf;
   // backward scratch
   size_t dhs, dz, dhrec, dc0, dc1, dd, gA, gB, gC, gFull, wt, partial, wq, tcerr, counter, gemm_ws, wq_all, partial_all;
+  size_t gP1, gP2, gP3, gFP;   // conv_mode 3: plane-tensor gradients (pooled resolution x3, full resolution)
   size_t total;
 };
 
@@ -110,18 +116,32 @@ static Plan make_plan(const seedrl_net* n, int T1, int B) {
   Bump b;
   const size_t N = (size_t)T1 * B;
   p.N = (int)N;
-  size_t pooled_max = 0, full_max = 0;
+  size_t pooled_max = 0, full_max = 0, pooled_planes_max = 0, full_planes_max = 0;
+  const bool planes = n->conv_mode == 3 && n->cfg.net == SEEDRL_NET_DEEP;
   if (n->cfg.net == SEEDRL_NET_DEEP) {
-    for (const Stack& s : n->stacks) {
-      StackBufs sb;
+    for (size_t si = 0; si < n->stacks.size(); ++si) {
+      const Stack& s = n->stacks[si];
+      StackBufs sb = StackBufs();
       const size_t full = N * s.hin * s.win * s.c, pooled = N * s.hout * s.wout * s.c;
       sb.a0 = b.take(full * 4);
-      sb.p = b.take(pooled * 4);
       sb.idx = b.take(pooled);
-      sb.c0 = b.take(pooled * 4);
-      sb.o0 = b.take(pooled * 4);
-      sb.c1 = b.take(pooled * 4);
-      sb.o1 = b.take(pooled * 4);
+      if (!planes) {
+        sb.p = b.take(pooled * 4);
+        sb.c0 = b.take(pooled * 4);
+        sb.o0 = b.take(pooled * 4);
+        sb.c1 = b.take(pooled * 4);
+        sb.o1 = b.take(pooled * 4);
+      } else {
+        const size_t pb = planes_bytes((int)N, s.hout, s.wout, s.c);
+        sb.praw = b.take(pb); sb.prelu = b.take(pb); sb.c0r = b.take(pb);
+        sb.o0raw = b.take(pb); sb.o0relu = b.take(pb); sb.c1r = b.take(pb);
+        if (si + 1 < n->stacks.size()) sb.o1p = b.take(pb); else sb.o1 = b.take(pooled * 4);
+        if (pb > pooled_planes_max) pooled_planes_max = pb;
+        if (si > 0) {
+          const size_t fb = planes_bytes((int)N, s.hin, s.win, s.c);
+          if (fb > full_planes_max) full_planes_max = fb;
+        }
+      }
       p.st.push_back(sb);
       if (pooled > pooled_max) pooled_max = pooled;
       if (full > full_max) full_max = full;
@@ -147,8 +167,16 @@ static Plan make_plan(const seedrl_net* n, int T1, int B) {
   p.dc1 = b.take((size_t)B * kHidden * 4);
   p.dd = b.take(N * kHidden * 4);
   p.gA = b.take(pooled_max * 4);
-  p.gB = b.take(pooled_max * 4);
-  p.gC = b.take(pooled_max * 4);
+  p.gB = p.gC = p.gP1 = p.gP2 = p.gP3 = p.gFP = 0;
+  if (!planes) {
+    p.gB = b.take(pooled_max * 4);
+    p.gC = b.take(pooled_max * 4);
+  } else {
+    p.gP1 = b.take(pooled_planes_max);
+    p.gP2 = b.take(pooled_planes_max);
+    p.gP3 = b.take(pooled_planes_max);
+    p.gFP = b.take(full_planes_max);
+  }
   p.gFull = b.take(full_max * 4);
   p.wt = b.take(64 * 1024 * 4);
   p.wq = b.take(2 * 64 * 1024 * 2);
@@ -185,7 +213,7 @@ static int run_gemm(const seedrl_net* n, void* ws, const Plan& pl, bool ta, bool
                     const float* A, int lda, const float* B, int ldb, float* C, int ldc, const GemmEpi& e,
                     cudaStream_t st) {
   if (n->conv_mode >= 1 && gemm_tc_supported(M, N, K))
-    return gemm_tc(ta, tb, n->conv_mode == 2, M, N, K, A, lda, B, ldb, C, ldc, e, W<float>(ws, pl.gemm_ws),
+    return gemm_tc(ta, tb, n->conv_mode >= 2, M, N, K, A, lda, B, ldb, C, ldc, e, W<float>(ws, pl.gemm_ws),
                    gemm_tc_workspace_bytes(), W<int>(ws, pl.tcerr), st);
   return sgemm(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, e, st);
 }
@@ -221,7 +249,7 @@ static int pack_all_weights(const seedrl_net* n, const float* prm, void* ws, con
       ctx->packed.jobs[ctx->packed.n++] = j;
     }
   }
-  return conv3x3_tc_pack_weights_batch(ctx->packed, n->conv_mode == 2, st);
+  return conv3x3_tc_pack_weights_batch(ctx->packed, n->conv_mode >= 2, st);
 }
 static const void* find_packed(const float* w, int flip) {
   if (!t_ctx) return nullptr;
@@ -237,7 +265,7 @@ static int run_conv(const seedrl_net* n, void* ws, const Plan& pl, int cin, int 
                     int N, int H, int Wd, const void* in, const float* w, const float* bias,
                     const float* mask, const float* res, float* out, int flip, cudaStream_t st) {
   if (n->conv_mode >= 1 && conv3x3_tc_supported(cin, cout, in_mode)) {
-    const int split = n->conv_mode == 2;
+    const int split = n->conv_mode >= 2;
     const void* wq = find_packed(w, flip);
     if (!wq) {
       void* scratch = W<void>(ws, pl.wq);
@@ -336,8 +364,9 @@ extern "C" int seedrl_net_set_lstm_mode(seedrl_net* net, int mode) {
   return SEEDRL_OK;
 }
 extern "C" int seedrl_net_set_conv_mode(seedrl_net* net, int mode) {
-  SEEDRL_CHECK_ARG(net && mode >= 0 && mode <= 2,
-                   "mode must be 0 (fp32 SIMT), 1 (tcgen05 bf16) or 2 (tcgen05 bf16x3)");
+  SEEDRL_CHECK_ARG(net && mode >= 0 && mode <= 3,
+                   "mode must be 0 (fp32 SIMT), 1 (tcgen05 bf16), 2 (tcgen05 bf16x3) or 3 (bf16x3 plane tensors)");
+  SEEDRL_CHECK_ARG(mode != 3 || net->cfg.net == SEEDRL_NET_DEEP, "mode 3 is built for the deep net");
   net->conv_mode = mode;
   return SEEDRL_OK;
 }
@@ -390,6 +419,61 @@ static int torso_forward_deep(const seedrl_net* n, const float* prm, const Plan&
   return SEEDRL_OK;
 }
 
+// conv_mode 3: the same _Stack schedule on plane tensors (conv_planes.cu).  The first conv reads the
+// uint8 frames with the staged tcgen05 kernel (bf16x3) and writes fp32 NHWC for the max-pool; from
+// there on every conv input is a TMA tile of an HBM-resident operand.
+static int planes_conv(const seedrl_net* n, void* ws, const Plan& pl, int cin, int cout, int N, int H, int Wd,
+                       const void* in, const float* w, int flip, const float* bias, const void* mask,
+                       const void* res, void* out_raw, void* out_relu, float* out_nhwc, cudaStream_t st) {
+  const void* wq = find_packed(w, flip);
+  if (!wq) {
+    void* scratch = W<void>(ws, pl.wq);
+    SEEDRL_TRY(conv3x3_tc_pack_weights(cin, cout, flip, 1, w, scratch, st));
+    wq = scratch;
+  }
+  PlaneConv c;
+  c.N = N; c.H = H; c.W = Wd; c.in = in; c.wq = wq; c.bias = bias; c.mask = mask; c.res = res;
+  c.out_raw = out_raw; c.out_relu = out_relu; c.out_nhwc = out_nhwc; c.err = W<int>(ws, pl.tcerr);
+  return convp_forward(cin, cout, c, st);
+}
+
+static int torso_forward_planes(const seedrl_net* n, const float* prm, const Plan& pl,
+                                const uint8_t* obs, void* ws, cudaStream_t st) {
+  const int N = pl.N;
+  const void* prev = nullptr;
+  const size_t ns = n->stacks.size();
+  for (size_t s = 0; s < ns; ++s) {
+    const Stack& k = n->stacks[s];
+    const StackBufs& b = pl.st[s];
+    float* a0 = W<float>(ws, b.a0);
+    void* praw = W<void>(ws, b.praw); void* prelu = W<void>(ws, b.prelu);
+    void* c0r = W<void>(ws, b.c0r); void* o0raw = W<void>(ws, b.o0raw);
+    void* o0relu = W<void>(ws, b.o0relu); void* c1r = W<void>(ws, b.c1r);
+    const bool last = s + 1 == ns;
+    if (s == 0)
+      SEEDRL_TRY(run_conv(n, ws, pl, k.cin, k.c, IN_U8, N, k.hin, k.win, obs, P(n, prm, k.conv.w),
+                          P(n, prm, k.conv.b), nullptr, nullptr, a0, 0, st));
+    else
+      SEEDRL_TRY(planes_conv(n, ws, pl, k.cin, k.c, N, k.hin, k.win, prev, P(n, prm, k.conv.w), 0,
+                             P(n, prm, k.conv.b), nullptr, nullptr, nullptr, nullptr, a0, st));
+    SEEDRL_TRY(poolp_forward(N, k.hin, k.win, k.c, a0, praw, prelu, W<uint8_t>(ws, b.idx), st));
+    const int H = k.hout, Wd = k.wout, C = k.c;
+    // res block 0: c0 = conv00(relu(p)); o0 = conv01(relu(c0)) + p        (networks.py:52-58)
+    SEEDRL_TRY(planes_conv(n, ws, pl, C, C, N, H, Wd, prelu, P(n, prm, k.r00.w), 0, P(n, prm, k.r00.b), nullptr,
+                           nullptr, nullptr, c0r, nullptr, st));
+    SEEDRL_TRY(planes_conv(n, ws, pl, C, C, N, H, Wd, c0r, P(n, prm, k.r01.w), 0, P(n, prm, k.r01.b), nullptr,
+                           praw, o0raw, o0relu, nullptr, st));
+    // res block 1: c1 = conv10(relu(o0)); o1 = conv11(relu(c1)) + o0
+    SEEDRL_TRY(planes_conv(n, ws, pl, C, C, N, H, Wd, o0relu, P(n, prm, k.r10.w), 0, P(n, prm, k.r10.b), nullptr,
+                           nullptr, nullptr, c1r, nullptr, st));
+    SEEDRL_TRY(planes_conv(n, ws, pl, C, C, N, H, Wd, c1r, P(n, prm, k.r11.w), 0, P(n, prm, k.r11.b), nullptr,
+                           o0raw, last ? nullptr : W<void>(ws, b.o1p), nullptr,
+                           last ? W<float>(ws, b.o1) : nullptr, st));
+    prev = W<void>(ws, b.o1p);
+  }
+  return SEEDRL_OK;
+}
+
 static int torso_forward_shallow(const seedrl_net* n, const float* prm, const Plan& pl,
                                  const uint8_t* obs, void* ws, cudaStream_t st) {
   const int N = pl.N;
@@ -415,6 +499,9 @@ extern "C" int seedrl_net_forward(const seedrl_net* n, const float* prm, int T1,
   SEEDRL_CHECK_ARG(ws_bytes >= pl.total, "workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   const int N = pl.N, A = n->cfg.num_actions, CI = n->core_in;
+  // bounded-wait error flag of the tcgen05 / persistent kernels: cleared here, set by any kernel of
+  // this forward or the matching backward, read back by seedrl_net_check_error
+  SEEDRL_CUDA(cudaMemsetAsync(W<int>(ws, pl.tcerr), 0, sizeof(int), st));
   const float* flat_src;
   int flat_relu;
   if (n->cfg.net == SEEDRL_NET_DEEP) {
@@ -422,7 +509,8 @@ extern "C" int seedrl_net_forward(const seedrl_net* n, const float* prm, int T1,
     ctx.wb = WgradBatch{nullptr, 0, 0, 0, {}};
     SEEDRL_TRY(pack_all_weights(n, prm, ws, pl, 0, &ctx, st));
     t_ctx = &ctx;
-    const int rc_t = torso_forward_deep(n, prm, pl, observation, ws, st);
+    const int rc_t = n->conv_mode == 3 ? torso_forward_planes(n, prm, pl, observation, ws, st)
+                                       : torso_forward_deep(n, prm, pl, observation, ws, st);
     t_ctx = nullptr;
     SEEDRL_TRY(rc_t);
     flat_src = W<float>(ws, pl.st.back().o1);
@@ -486,13 +574,31 @@ extern "C" int seedrl_net_forward(const seedrl_net* n, const float* prm, int T1,
   return SEEDRL_OK;
 }
 
+// Reads back the device-side error flag of the last forward/backward that used this workspace
+// (set when a bounded mbarrier / grid-barrier wait of a tcgen05 or persistent kernel expired, i.e.
+// the results are garbage).  Synchronises `stream`.
+extern "C" int seedrl_net_check_error(const seedrl_net* n, int T1, int B, void* ws, size_t ws_bytes,
+                                      seedrl_stream_t stream) {
+  SEEDRL_CHECK_ARG(n && ws && T1 >= 1 && B >= 1, "bad arguments");
+  const Plan pl = make_plan(n, T1, B);
+  SEEDRL_CHECK_ARG(ws_bytes >= pl.total, "workspace too small");
+  int flag = 0;
+  SEEDRL_CUDA(cudaMemcpyAsync(&flag, W<int>(ws, pl.tcerr), sizeof(int), cudaMemcpyDeviceToHost,
+                              (cudaStream_t)stream));
+  SEEDRL_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  if (flag != 0)
+    return set_error(SEEDRL_ERR_INTERNAL,
+                     "a tensor-core / persistent kernel timed out on a barrier: results of this step are invalid");
+  return SEEDRL_OK;
+}
+
 // ---- backward -------------------------------------------------------------------
 static int conv_bwd(const seedrl_net* n, const float* prm, float* grd, const ConvLayer& l, int N,
                     int H, int Wd, const void* x, int x_mode, const float* dy, const float* dmask,
                     const float* dres, float* dx, void* ws, const Plan& pl, cudaStream_t st) {
   // weight + bias gradient
   if (n->conv_mode >= 1 && conv3x3_wgrad_tc_supported(l.cin, l.cout, x_mode)) {
-    SEEDRL_TRY(conv3x3_wgrad_tc(l.cin, l.cout, x_mode, n->conv_mode == 2, N, H, Wd, x, dy,
+    SEEDRL_TRY(conv3x3_wgrad_tc(l.cin, l.cout, x_mode, n->conv_mode >= 2, N, H, Wd, x, dy,
                                 G(n, grd, l.w), G(n, grd, l.b), W<float>(ws, pl.partial),
                                 conv3x3_wgrad_partial_bytes(), W<int>(ws, pl.tcerr),
                                 t_ctx ? &t_ctx->wb : nullptr, st));
@@ -533,6 +639,58 @@ static int torso_backward_deep(const seedrl_net* n, const float* prm, float* grd
     const void* x = s == 0 ? (const void*)obs : (const void*)W<float>(ws, pl.st[s - 1].o1);
     SEEDRL_TRY(conv_bwd(n, prm, grd, k.conv, N, k.hin, k.win, x, s == 0 ? IN_U8 : IN_F32, gF, nullptr,
                         nullptr, s == 0 ? nullptr : gA, ws, pl, st));
+  }
+  return SEEDRL_OK;
+}
+
+// conv_mode 3 backward: every gradient between the Dense layer and the first conv is a plane tensor.
+static int planes_conv_bwd(const seedrl_net* n, const float* prm, float* grd, const ConvLayer& l, int N, int H,
+                           int Wd, const void* x, const void* dy, const void* dmask, const void* dres,
+                           void* dx, void* ws, const Plan& pl, cudaStream_t st) {
+  SEEDRL_TRY(wgradp(l.cin, l.cout, N, H, Wd, x, dy, G(n, grd, l.w), G(n, grd, l.b), W<int>(ws, pl.tcerr),
+                    t_ctx ? &t_ctx->wb : nullptr, st));
+  if (dx) {
+    g_conv_cat = PC_CONV_DGRAD;
+    const int rc = planes_conv(n, ws, pl, l.cout, l.cin, N, H, Wd, dy, P(n, prm, l.w), 1, nullptr, dmask, dres,
+                               dx, nullptr, nullptr, st);
+    g_conv_cat = PC_CONV_FWD;
+    SEEDRL_TRY(rc);
+  }
+  return SEEDRL_OK;
+}
+
+static int torso_backward_planes(const seedrl_net* n, const float* prm, float* grd, const Plan& pl,
+                                 const uint8_t* obs, void* ws, cudaStream_t st) {
+  // On entry gA (fp32 NHWC) holds d loss / d o1 of the last stack.
+  const int N = pl.N;
+  void* g1 = W<void>(ws, pl.gP1); void* g2 = W<void>(ws, pl.gP2); void* g3 = W<void>(ws, pl.gP3);
+  void* gfp = W<void>(ws, pl.gFP); float* gF = W<float>(ws, pl.gFull);
+  {
+    const Stack& k = n->stacks.back();
+    SEEDRL_TRY(to_planes(N, k.hout, k.wout, k.c, 0, W<float>(ws, pl.gA), g1, st));
+  }
+  for (int s = (int)n->stacks.size() - 1; s >= 0; --s) {
+    const Stack& k = n->stacks[s];
+    const StackBufs& b = pl.st[s];
+    const int H = k.hout, Wd = k.wout;
+    const void* prelu = W<void>(ws, b.prelu); const void* c0r = W<void>(ws, b.c0r);
+    const void* o0relu = W<void>(ws, b.o0relu); const void* c1r = W<void>(ws, b.c1r);
+    // block 1: o1 = conv11(relu(c1)) + o0 ; c1 = conv10(relu(o0))
+    SEEDRL_TRY(planes_conv_bwd(n, prm, grd, k.r11, N, H, Wd, c1r, g1, c1r, nullptr, g2, ws, pl, st));
+    SEEDRL_TRY(planes_conv_bwd(n, prm, grd, k.r10, N, H, Wd, o0relu, g2, o0relu, g1, g3, ws, pl, st));
+    // block 0: o0 = conv01(relu(c0)) + p ; c0 = conv00(relu(p))
+    SEEDRL_TRY(planes_conv_bwd(n, prm, grd, k.r01, N, H, Wd, c0r, g3, c0r, nullptr, g2, ws, pl, st));
+    SEEDRL_TRY(planes_conv_bwd(n, prm, grd, k.r00, N, H, Wd, prelu, g2, prelu, g3, g1, ws, pl, st));
+    // max-pool, then the stack's first conv
+    if (s == 0) {
+      SEEDRL_TRY(poolp_backward(N, k.hin, k.win, k.c, g1, W<uint8_t>(ws, b.idx), nullptr, gF, st));
+      SEEDRL_TRY(conv_bwd(n, prm, grd, k.conv, N, k.hin, k.win, obs, IN_U8, gF, nullptr, nullptr, nullptr, ws, pl,
+                          st));
+    } else {
+      SEEDRL_TRY(poolp_backward(N, k.hin, k.win, k.c, g1, W<uint8_t>(ws, b.idx), gfp, nullptr, st));
+      SEEDRL_TRY(planes_conv_bwd(n, prm, grd, k.conv, N, k.hin, k.win, W<void>(ws, pl.st[s - 1].o1p), gfp, nullptr,
+                                 nullptr, g1, ws, pl, st));
+    }
   }
   return SEEDRL_OK;
 }
@@ -628,7 +786,8 @@ extern "C" int seedrl_net_backward(const seedrl_net* n, const float* prm, int T1
     ctx.wb = WgradBatch{W<float>(ws, pl.partial_all), kPartialAllBytes / sizeof(float), 0, 0, {}};
     SEEDRL_TRY(pack_all_weights(n, prm, ws, pl, 1, &ctx, st));
     t_ctx = &ctx;
-    int rc_t = torso_backward_deep(n, prm, grd, pl, observation, ws, st);
+    int rc_t = n->conv_mode == 3 ? torso_backward_planes(n, prm, grd, pl, observation, ws, st)
+                                 : torso_backward_deep(n, prm, grd, pl, observation, ws, st);
     t_ctx = nullptr;
     if (rc_t == SEEDRL_OK) rc_t = wgrad_reduce_batch(&ctx.wb, st);
     return rc_t;
@@ -728,4 +887,51 @@ extern "C" int seedrl_debug_conv3x3_tc(int cin, int cout, int in_mode, int split
   SEEDRL_TRY(conv3x3_tc_pack_weights(cin, cout, flip, split, w, wq_scratch, (cudaStream_t)stream));
   return conv3x3_tc_forward(cin, cout, in_mode, split, N, H, W, in, wq_scratch, bias, mask, res, out,
                             variant, error_flag, (cudaStream_t)stream);
+}
+
+// ---- plane-tensor path test hooks (conv_planes.cu) ---------------------------------------------
+extern "C" size_t seedrl_debug_planes_bytes(int N, int H, int W, int C) {
+  if (N < 1 || H < 1 || W < 1 || C < 8 || C % 8) return 0;
+  return planes_bytes(N, H, W, C);
+}
+extern "C" int seedrl_debug_to_planes(int N, int H, int W, int C, int relu, const float* x, void* out,
+                                      seedrl_stream_t stream) {
+  SEEDRL_CHECK_ARG(N >= 1 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0 && x && out, "bad arguments");
+  return to_planes(N, H, W, C, relu, x, out, (cudaStream_t)stream);
+}
+extern "C" int seedrl_debug_from_planes(int N, int H, int W, int C, const void* in, float* y,
+                                        seedrl_stream_t stream) {
+  SEEDRL_CHECK_ARG(N >= 1 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0 && in && y, "bad arguments");
+  return from_planes(N, H, W, C, in, y, (cudaStream_t)stream);
+}
+// 3x3 'same' conv on plane tensors.  w: fp32 HWIO of the FORWARD layer; flip != 0 runs the data
+// gradient (cin/cout are those of the gradient convolution).  wq_scratch >= 2*9*cin*cout*2 bytes.
+extern "C" int seedrl_debug_convp(int cin, int cout, int N, int H, int W, const void* in, const float* w,
+                                  const float* bias, const void* mask, const void* res, int flip,
+                                  void* out_raw, void* out_relu, float* out_nhwc, void* wq_scratch,
+                                  int* error_flag, seedrl_stream_t stream) {
+  SEEDRL_CHECK_ARG(convp_supported(cin, cout) && in && w && wq_scratch, "unsupported (cin,cout) or null pointer");
+  SEEDRL_TRY(conv3x3_tc_pack_weights(cin, cout, flip, 1, w, wq_scratch, (cudaStream_t)stream));
+  PlaneConv c;
+  c.N = N; c.H = H; c.W = W; c.in = in; c.wq = wq_scratch; c.bias = bias; c.mask = mask; c.res = res;
+  c.out_raw = out_raw; c.out_relu = out_relu; c.out_nhwc = out_nhwc; c.err = error_flag;
+  return convp_forward(cin, cout, c, (cudaStream_t)stream);
+}
+extern "C" int seedrl_debug_wgradp(int cin, int cout, int N, int H, int W, const void* x, const void* dy,
+                                   float* dw, float* db, float* partial, size_t partial_bytes,
+                                   int* error_flag, seedrl_stream_t stream) {
+  SEEDRL_CHECK_ARG(x && dy && dw && db && partial, "null pointer");
+  WgradBatch wb{partial, partial_bytes / sizeof(float), 0, 0, {}};
+  SEEDRL_TRY(wgradp(cin, cout, N, H, W, x, dy, dw, db, error_flag, &wb, (cudaStream_t)stream));
+  return wgrad_reduce_batch(&wb, (cudaStream_t)stream);
+}
+// max-pool 3x3/2 'SAME' on the plane path.  forward: x fp32 NHWC -> out_raw / out_relu plane tensors
+// + idx; backward: dy plane tensor (pooled) + idx -> dx plane tensor (out_raw) or fp32 NHWC (out_nhwc).
+extern "C" int seedrl_debug_poolp(int backward, int N, int H, int W, int C, const void* in, void* out_raw,
+                                  void* out_relu, float* out_nhwc, uint8_t* idx, seedrl_stream_t stream) {
+  SEEDRL_CHECK_ARG(N >= 1 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0 && in && idx, "bad arguments");
+  if (backward) return poolp_backward(N, H, W, C, in, idx, out_raw, out_nhwc, (cudaStream_t)stream);
+  SEEDRL_CHECK_ARG(out_raw && out_relu, "null pointer");
+  return poolp_forward(N, H, W, C, reinterpret_cast<const float*>(in), out_raw, out_relu, idx,
+                       (cudaStream_t)stream);
 }

@@ -141,7 +141,12 @@ SEEDRL_HD float replay_prefix_serial(int limit, float* s_cdf) {
 // phase 3 (thread j): index = first i with cdf[i] > u_j * total; un-normalised importance weight
 SEEDRL_HD float replay_sample_thread(int j, int limit, const float* s_cdf, float total, float is_exp,
                                      const float* uniforms, int64_t* indices, float* weights) {
-  const float u = uniforms[j] * total;
+  // u < total strictly (uniforms[j] * total can round up to total): then the first i with
+  // cdf[i] > u exists and has cdf[i] > u >= cdf[i-1], i.e. positive mass -- like
+  // tf.random.categorical over log-probabilities, a zero-priority entry is never drawn.
+  float u = uniforms[j] * total;
+  const float below = total > 0.f ? total * (1.f - 5.9604645e-8f) : 0.f;
+  if (u > below) u = below;
   int lo = 0, hi = limit - 1;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;

@@ -16,6 +16,7 @@ IMPALA-paper shallow net (not in the reference), same protocol.
 import collections
 import ctypes
 import math
+import threading
 
 import numpy as np
 import torch
@@ -43,9 +44,12 @@ class _CudaAgent(object):
     h = ctypes.c_void_p()
     _lib.check(L.seedrl_net_create(ctypes.byref(cfg), ctypes.byref(h)))
     self._h = h
-    modes = {'simt': 0, 'tc': 1, 'tc3': 2}
+    modes = {'simt': 0, 'tc': 1, 'tc3': 2, 'tc3p': 3}
     if conv_mode not in modes:
-      raise ValueError("conv_mode must be 'simt', 'tc' (bf16) or 'tc3' (bf16x3, fp32-faithful)")
+      raise ValueError("conv_mode must be 'simt', 'tc' (bf16), 'tc3' (bf16x3, fp32-faithful) or "
+                       "'tc3p' (bf16x3 on HBM-resident operand planes, TMA-fed)")
+    if conv_mode == 'tc3p' and self._NET != _lib.NET_DEEP:
+      raise ValueError("conv_mode 'tc3p' is built for the deep net")
     self.conv_mode = conv_mode
     _lib.check(L.seedrl_net_set_conv_mode(h, modes[conv_mode]))
     if lstm_mode not in ('persistent', 'stepwise'):
@@ -69,8 +73,11 @@ class _CudaAgent(object):
     self.params = torch.zeros(self.arena_floats, dtype=torch.float32, device=self.device)
     self.grads = torch.zeros_like(self.params)
     self._init_parameters(seed)
-    self._ws = None
-    self._ws_key = None
+    # One activation workspace per (T1, B): the inference thread (T1=1, B=N, its own stream)
+    # and the learner thread (T1=T+1, B=batch) share this agent's parameters but never a
+    # workspace; backward() uses exactly the buffer its is_training forward filled.
+    self._workspaces = {}
+    self._lock = threading.Lock()
     self._rng_offset = 0
     self._seed = seed
     self._saved = None
@@ -151,13 +158,33 @@ class _CudaAgent(object):
     return (z, z.clone())
 
   def _workspace(self, T1, B):
-    key = (T1, B)
-    if self._ws_key != key:
-      nbytes = int(_lib.lib().seedrl_net_workspace_bytes(self._h, T1, B))
-      self._ws = None
-      self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-      self._ws_key = key
-    return self._ws
+    key = (T1, B, threading.get_ident())
+    with self._lock:
+      ws = self._workspaces.get(key)
+      if ws is None:
+        nbytes = int(_lib.lib().seedrl_net_workspace_bytes(self._h, T1, B))
+        # drop this thread's buffers of other shapes first (a learner that changes batch size
+        # must not keep several multi-GB workspaces alive)
+        for k in [k for k in self._workspaces if k[2] == key[2] and k != key]:
+          del self._workspaces[k]
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self._workspaces[key] = ws
+    return ws
+
+  def check_errors(self):
+    """Raises if a kernel of the last training forward/backward hit a bounded-wait timeout
+    (synchronises the current stream; call where the loss is read anyway)."""
+    if self._saved is None:
+      return
+    T1, B, ws = self._saved[0], self._saved[1], self._saved[-1]
+    _lib.check(_lib.lib().seedrl_net_check_error(self._h, T1, B, _lib.ptr(ws), ws.numel(),
+                                                 _lib.stream_ptr()))
+
+  def _next_rng_offset(self):
+    with self._lock:
+      o = self._rng_offset
+      self._rng_offset += 1
+    return o
 
   def get_action(self, *args, **kwargs):
     return self.__call__(*args, **kwargs)
@@ -194,12 +221,11 @@ class _CudaAgent(object):
     if gumbel_noise is not None:
       noise = _lib.require_cuda(gumbel_noise, torch.float32, 'gumbel_noise')
     _lib.check(L.seedrl_categorical_sample(
-        T1 * B, A, _lib.ptr(logits), _lib.ptr(noise), int(self._seed), int(self._rng_offset),
+        T1 * B, A, _lib.ptr(logits), _lib.ptr(noise), int(self._seed), int(self._next_rng_offset()),
         _lib.ptr(action), st))
-    self._rng_offset += 1
     action = action.view(T1, B)
     if is_training:
-      self._saved = (T1, B, prev_actions, reward, done, frame)
+      self._saved = (T1, B, prev_actions, reward, done, frame, ws)
     out = AgentOutput(action, logits, baseline)
     if not unroll:
       out = AgentOutput(*(t.squeeze(0) for t in out))
@@ -209,8 +235,7 @@ class _CudaAgent(object):
     """d loss / d parameters for the last is_training unroll -> self.grads (overwritten)."""
     if self._saved is None:
       raise RuntimeError('backward() needs a preceding __call__(..., unroll=True, is_training=True)')
-    T1, B, prev_actions, reward, done, frame = self._saved
-    ws = self._workspace(T1, B)
+    T1, B, prev_actions, reward, done, frame, ws = self._saved
     _lib.check(_lib.lib().seedrl_net_backward(
         self._h, _lib.ptr(self.params), T1, B, _lib.ptr(prev_actions), _lib.ptr(reward),
         _lib.ptr(done), _lib.ptr(frame), _lib.ptr(dlogits), _lib.ptr(dbaseline),

@@ -1,19 +1,11 @@
-"""GPU: R2D2 post-network kernels against oracle/r2d2_oracle.py.
-
-GATED: these kernels were written and compiled at the end of round 1, after the round's GPU
-budget was spent -- they have never run on hardware.  Set SEEDRL_RUN_UNVERIFIED=1 to run them;
-the gate comes off once they have passed on a B200."""
-import os
-
+"""GPU: R2D2 post-network kernels against oracle/r2d2_oracle.py."""
 import numpy as np
 import pytest
 import torch
 
 from oracle import r2d2_oracle as R
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('SEEDRL_RUN_UNVERIFIED') != '1',
-                                 reason='R2D2 kernels not yet verified on hardware (round 1)')]
+pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize('T,B,H,W,S', [(6, 2, 3, 4, 4), (9, 3, 5, 2, 3), (4, 1, 2, 2, 2), (20, 4, 84, 84, 4), (1, 2, 3, 3, 4)])
@@ -61,7 +53,7 @@ def test_loss_and_priorities_vs_oracle(T, B, A, n):
       r, d, R.inverse_value_function_rescaling(gq[np.arange(T)[:, None], np.arange(B)[None], tq.argmax(-1)]), 0.997, n)[1:])
   want = np.zeros((T, B, A), np.float32)
   want[tt, bb, ra[:-1]] = -(w[None] / B) * (target - tq[tt, bb, ra[:-1]])
-  np.testing.assert_allclose(dq.cpu().numpy(), want, rtol=2e-4, atol=1e-7)
+  np.testing.assert_allclose(dq.cpu().numpy(), want, rtol=2e-4, atol=1e-6)   # td ~ 0 cancels to ~1e-7 abs
 
 
 def test_replay_sample_and_clip():
@@ -71,10 +63,10 @@ def test_replay_sample_and_clip():
   u = rng.random(4096).astype(np.float32)
   idx, wts, probs = learner.replay_sample(torch.as_tensor(prio).cuda(), 70, 4096, 0.9, 0.6, uniforms=torch.as_tensor(u).cuda())
   p = R.replay_probabilities(prio, 70, 0.9)
-  np.testing.assert_allclose(probs.cpu().numpy(), p, rtol=1e-5)
+  np.testing.assert_allclose(probs.cpu().numpy(), p, rtol=5e-5)   # powf vs numpy power: 1.3e-5 seen
   i = idx.cpu().numpy()
   assert i.min() >= 0 and i.max() < 70
-  np.testing.assert_allclose(wts.cpu().numpy(), R.replay_importance_weights(p, i, 0.6), rtol=1e-5)
+  np.testing.assert_allclose(wts.cpu().numpy(), R.replay_importance_weights(p, i, 0.6), rtol=5e-5)
   # inverse-CDF draw: index = first i with cdf_i > u * total
   cdf = np.cumsum(np.power(prio[:70], np.float32(0.9), dtype=np.float32), dtype=np.float32)
   np.testing.assert_array_equal(i, np.minimum(np.searchsorted(cdf, u * cdf[-1], side='right'), 69))
