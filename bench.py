@@ -43,12 +43,15 @@ def parse_args():
   p.add_argument('--unroll', type=int, default=20)
   p.add_argument('--cpu-batch', type=int, default=0,
                  help='unrolls per CPU-baseline step (0 = the same batch as the GPU arm)')
-  p.add_argument('--conv', default='tc3', choices=['simt', 'tc', 'tc3'],
-                 help="contraction path of the convs and dense layers: fp32 SIMT, tcgen05 bf16, or "
-                      "tcgen05 bf16x3 (fp32-faithful split operands; the parity mode)")
+  p.add_argument('--conv', default='tc3p', choices=['simt', 'tc', 'tc3', 'tc3p'],
+                 help="contraction path of the convs and dense layers: fp32 SIMT, tcgen05 bf16, "
+                      "tcgen05 bf16x3 (fp32-faithful split operands), or tc3p = bf16x3 on HBM-resident "
+                      "operand planes with TMA-fed warp-specialised kernels (deep net; the default)")
   p.add_argument('--no-extras', action='store_true',
                  help='skip the profiling pass, the loss-kernel sweep and the CPU baseline')
   a = p.parse_args()
+  if a.net == 'shallow' and a.conv == 'tc3p':
+    a.conv = 'tc3'
   if a.cpu_batch <= 0:
     a.cpu_batch = a.batch
   return a
@@ -192,6 +195,39 @@ def conv_bytes_per_step(N, cat):
     elif cat == 'conv3x3_wgrad':
       tot += full_in + full_out + 4 * (2 * pooled)        # x and dy read once per conv
       launches += 10                                      # kernel + reduce per conv
+  return tot, launches
+
+
+def conv_bytes_per_step_planes(N, cat):
+  """Same accounting for conv_mode 'tc3p' (DESIGN 4.2): plane tensors hold hi+lo bf16 = 4 bytes per
+  element (padding positions not counted); which tensors each kernel reads / writes differs from
+  the fp32 layout: conv01 / conv11 write a raw and (conv01) a ReLU'd copy, the ReLU mask of a data
+  gradient is the hi plane only (2 bytes per element)."""
+  stacks = [(84, 84, 4, 16), (42, 42, 16, 32), (21, 21, 32, 32)]
+  tot, launches = 0, 0
+  for si, (h, w, cin, c) in enumerate(stacks):
+    ho, wo = (h + 1) // 2, (w + 1) // 2
+    full_in = N * h * w * cin * (1 if si == 0 else 4)
+    full_out = N * h * w * c * 4
+    pooled = N * ho * wo * c * 4
+    if cat == 'conv3x3_fwd':
+      tot += full_in + full_out               # stack conv: frames / plane tensor in, fp32 NHWC out
+      tot += 2 * pooled                       # conv00: relu(p) in, relu(c0) out
+      tot += 4 * pooled                       # conv01: relu(c0) + p in, o0 and relu(o0) out
+      tot += 2 * pooled                       # conv10
+      tot += 3 * pooled                       # conv11: relu(c1) + o0 in, o1 out
+      launches += 5
+    elif cat == 'conv3x3_dgrad':
+      tot += 4 * (2 * pooled) + 4 * (pooled // 2) + 2 * pooled   # dy in, dx out, hi-plane masks, 2 residuals
+      launches += 4
+      if si > 0:
+        tot += full_out + N * h * w * cin * 4
+        launches += 1
+    elif cat == 'conv3x3_wgrad':
+      tot += full_in + full_out + 4 * (2 * pooled)
+      launches += 5
+  if cat == 'conv3x3_wgrad':
+    launches += 1                             # one deferred reduce of all partials
   return tot, launches
 
 
@@ -347,6 +383,8 @@ def main():
       'higher_is_better': True,
       'scaling': 'weak', 'vs_baseline': None,
       'dtype': {'tc': 'bf16', 'tc3': 'bf16x3 (fp32-faithful tensor-core contraction), f32 elsewhere',
+                'tc3p': 'bf16x3 (fp32-faithful tensor-core contraction; activations stored as bf16 hi+lo '
+                        'pairs), f32 elsewhere',
                 'simt': 'f32'}[args.conv], 'data': 'synthetic',
       'config': workload_config(args, world), 'conv_path': args.conv, 'clocks': clocks,
       'e2e': {'value': e2e_value, 'unit': UNIT, 'ms_per_step': ms_e2e,
@@ -385,7 +423,7 @@ def main():
     if args.net == 'deep':
       conv_cats = [k for k in ('conv3x3_fwd', 'conv3x3_dgrad', 'conv3x3_wgrad')]
       dom = max(conv_cats, key=lambda k: cats[k][0])
-      nbytes, nl = conv_bytes_per_step(T1 * B, dom)
+      nbytes, nl = (conv_bytes_per_step_planes if args.conv == 'tc3p' else conv_bytes_per_step)(T1 * B, dom)
       ms_dom = cats[dom][0]
       ach = nbytes / (ms_dom * 1e-3) / 1e9
       line['roofline'] = {
@@ -394,9 +432,17 @@ def main():
           'algorithmic_bytes_per_launch': nbytes / max(cats[dom][1], 1),
           'avg_launch_ms': ms_dom / max(cats[dom][1], 1), 'launches_per_step': cats[dom][1],
           'share_of_step': ms_dom / tot if tot else None, 'peak_source': peak_src,
-          'note': 'category time from CUDA events around every launch of the timed steps; tcgen05 path: '
-                  'operands are converted fp32->bf16 on the way into shared memory, so the bound is the '
-                  'fp32 activation traffic (HBM), not tensor FLOPs'}
+          'per_category': {
+              k: {'ms': cats[k][0], 'algorithmic_bytes': (conv_bytes_per_step_planes if args.conv == 'tc3p'
+                                                          else conv_bytes_per_step)(T1 * B, k)[0]}
+              for k in conv_cats},
+          'note': 'category time from CUDA events around every launch of 3 profiled steps; algorithmic bytes = '
+                  'every operand read once + every result written once in the layout of this conv path '
+                  '(bench.py conv_bytes_per_step*); the convs are HBM-bound (AI ~ 36-70 FLOP/B), tensor FLOPs '
+                  'are not the limit'}
+      for k, v in line['roofline']['per_category'].items():
+        v['GBps'] = v['algorithmic_bytes'] / (v['ms'] * 1e-3) / 1e9 if v['ms'] else None
+        v['frac'] = v['GBps'] / hbm_peak if v['ms'] else None
 
     if rank == 0 and world == 1:
       # ---- the fused V-trace loss kernel: B sweep (north star: >= 60% HBM at streaming size)
@@ -448,7 +494,7 @@ def main():
           'sweep': sweep}
       # ---- the other contraction paths, same workload (5 steps each) ----------------------
       others = {}
-      for mode in ('simt', 'tc', 'tc3'):
+      for mode in ('simt', 'tc', 'tc3', 'tc3p'):
         if mode == args.conv:
           continue
         ag = cls(A, OBS, seed=0, conv_mode=mode)
@@ -466,39 +512,48 @@ def main():
                               'sample': r['sample'], 'ms_per_step': r['ms_per_step']}
 
     if rank == 0 and world == 1 and args.net == 'deep' and args.conv != 'simt':
-      # ---- the single most time-consuming kernel instance of the step, alone: the 16->16
-      # conv @42x42 on all T1*B frames (8 launches/step as forward + data gradient).  Launch
-      # time measured live with CUDA events (10 back-to-back launches, working set 289 MB >> L2);
-      # `traffic` is the DRAM byte count of the same kernel from the committed ncu capture.
+      # ---- the most time-consuming single kernel instance of the step, alone: the 16->16 conv
+      # @42x42 on all T1*B frames (8 launches/step as forward + data gradient).  Launch time
+      # measured live with CUDA events (10 back-to-back launches, working set ~300 MB >> L2).
       # Runs LAST and guarded: a failure here must never cost the bench line.
       try:
         Nf, Hh, Cc = T1 * B, 42, 16
         xk = torch.randn(Nf, Hh, Hh, Cc, device='cuda'); wk = torch.randn(3, 3, Cc, Cc, device='cuda') * 0.1
-        bk = torch.zeros(Cc, device='cuda'); ok = torch.empty(Nf, Hh, Hh, Cc, device='cuda')
+        bk = torch.zeros(Cc, device='cuda')
         wqk = torch.empty(2 * 9 * 16 * Cc * 2, dtype=torch.uint8, device='cuda')
         errk = torch.zeros(1, dtype=torch.int32, device='cuda')
-        splitk = 1 if args.conv == 'tc3' else 0
+        if args.conv == 'tc3p':
+          nb = int(L.seedrl_debug_planes_bytes(Nf, Hh, Hh, Cc))
+          xin = torch.empty(nb, dtype=torch.uint8, device='cuda'); ok = torch.empty(nb, dtype=torch.uint8, device='cuda')
+          _lib.check(L.seedrl_debug_to_planes(Nf, Hh, Hh, Cc, 1, _lib.ptr(xk), _lib.ptr(xin), _lib.stream_ptr()))
+          kname = 'convp_kernel<16,16,4> (TMA + tcgen05 bf16x3, plane tensors in/out) N=%d 42x42' % Nf
 
-        def conv_once():
-          _lib.check(L.seedrl_debug_conv3x3_tc(Cc, Cc, 1, splitk, Nf, Hh, Hh, _lib.ptr(xk), _lib.ptr(wk),
-                                               _lib.ptr(bk), None, None, _lib.ptr(ok), 0, 0, _lib.ptr(wqk),
-                                               _lib.ptr(errk), _lib.stream_ptr()))
+          def conv_once():
+            _lib.check(L.seedrl_debug_convp(Cc, Cc, Nf, Hh, Hh, _lib.ptr(xin), _lib.ptr(wk), _lib.ptr(bk), None, None,
+                                            0, None, _lib.ptr(ok), None, _lib.ptr(wqk), _lib.ptr(errk),
+                                            _lib.stream_ptr()))
+        else:
+          ok = torch.empty(Nf, Hh, Hh, Cc, device='cuda')
+          splitk = 1 if args.conv == 'tc3' else 0
+          kname = 'conv3x3_tc_kernel<16,16,relu-in,%s,512> N=%d 42x42' % ('bf16x3' if splitk else 'bf16', Nf)
+
+          def conv_once():
+            _lib.check(L.seedrl_debug_conv3x3_tc(Cc, Cc, 1, splitk, Nf, Hh, Hh, _lib.ptr(xk), _lib.ptr(wk),
+                                                 _lib.ptr(bk), None, None, _lib.ptr(ok), 0, 0, _lib.ptr(wqk),
+                                                 _lib.ptr(errk), _lib.stream_ptr()))
         for _ in range(3):
           conv_once()
         ms_k = timed(conv_once, 10)
         alg = 2.0 * Nf * Hh * Hh * Cc * 4
         line['roofline_dominant_kernel'] = {
-            'kernel': 'conv3x3_tc_kernel<16,16,relu-in,%s,512> N=%d 42x42 (+ its 3 us weight-pack launch)' %
-                      ('bf16x3' if splitk else 'bf16', Nf),
+            'kernel': kname + ' (+ its 3 us weight-pack launch)',
             'bound': 'hbm', 'algorithmic_bytes_per_launch': alg, 'avg_launch_ms': ms_k,
             'achieved': alg / (ms_k * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
-            'frac': alg / (ms_k * 1e-3) / 1e9 / hbm_peak,
-            'traffic': None,
+            'frac': alg / (ms_k * 1e-3) / 1e9 / hbm_peak, 'traffic': None,
             'launches_per_step': 8, 'ok': int(errk.item()) == 0}
         del xk, ok
       except Exception as exc:        # pylint: disable=broad-except
         line['roofline_dominant_kernel'] = {'unavailable': repr(exc)[:200]}
-
 
   if rank == 0:
     emit(line)

@@ -48,7 +48,7 @@ long long planes_positions(int N, int H, int W) {
   const long long Q = (long long)N * (H + 1) * (W + 2);
   // every storage position a consumer's TMA box can touch inside its declared extent is written
   // (zeros) by the producer: tiles read up to 2*PW+2 past Q, shifted maps drop up to 64 positions
-  return ((Q + 2 * (W + 2) + 2 + 128 + 63) / 64) * 64;
+  return ((Q + 2 * (W + 2) + 2 + 256 + 127) / 128) * 128;
 }
 size_t planes_bytes(int N, int H, int W, int C) {
   return (size_t)planes_positions(N, H, W) * 16 * 2 * (C / 8);
@@ -73,20 +73,33 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// 3-D view of a plane tensor starting `shift` positions in: {64 u32 = one 16-position chunk,
-// chunks, planes}; box = {64, box_chunks, box_planes}.  Out-of-extent chunks read as zeros.
+// Positions per TMA box row.  The TMA engine pays a fixed cost per box row, so rows are as long as
+// the 256-element box limit allows: 128 positions x 16 B = 256 x uint64 (measured: 16-position rows
+// made the conv kernels TMA-issue-bound at ~40 cycles per row).  Tiles start on multiples of it.
+static int g_chunk = 0;
+int planes_chunk() {
+  if (g_chunk == 0) {
+    const char* e = getenv("SEEDRL_PLANES_CHUNK");
+    g_chunk = e ? atoi(e) : 128;
+    if (g_chunk != 16 && g_chunk != 32 && g_chunk != 64 && g_chunk != 128) g_chunk = 128;
+  }
+  return g_chunk;
+}
+
+// 3-D view of a plane tensor starting `shift` positions in: {one chunk of CH positions as 2*CH
+// uint64, chunks, planes}; box = {2*CH, box_chunks, box_planes}.  Out-of-extent chunks read as zeros.
 static int make_plane_map(CUtensorMap* tm, const void* base, long long Lp, int planes, int shift,
-                          int box_chunks, int box_planes) {
+                          int CH, int box_chunks, int box_planes) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return set_error(SEEDRL_ERR_INTERNAL, "cuTensorMapEncodeTiled is not available");
   if (box_chunks < 1 || box_chunks > 256 || box_planes < 1 || box_planes > planes)
     return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "conv planes: TMA box out of range");
-  const cuuint64_t gdim[3] = {64, (cuuint64_t)((Lp - shift) / 16), (cuuint64_t)planes};
-  const cuuint64_t gstr[2] = {256, (cuuint64_t)Lp * 16};
-  const cuuint32_t box[3] = {64, (cuuint32_t)box_chunks, (cuuint32_t)box_planes};
+  const cuuint64_t gdim[3] = {(cuuint64_t)(2 * CH), (cuuint64_t)((Lp - shift) / CH), (cuuint64_t)planes};
+  const cuuint64_t gstr[2] = {(cuuint64_t)CH * 16, (cuuint64_t)Lp * 16};
+  const cuuint32_t box[3] = {(cuuint32_t)(2 * CH), (cuuint32_t)box_chunks, (cuuint32_t)box_planes};
   const cuuint32_t estr[3] = {1, 1, 1};
   void* addr = const_cast<char*>(reinterpret_cast<const char*>(base)) + (size_t)shift * 16;
-  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, addr, gdim, gstr, box, estr,
+  const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, addr, gdim, gstr, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -129,7 +142,8 @@ __device__ __forceinline__ float bf16hi(uint32_t w) { return __uint_as_float(w &
 struct ConvpArgs {
   ConvGeom g;
   int Lp;                      // storage positions per plane (input and output share the geometry)
-  int nch;                     // 16-position chunks per staged tile (box_chunks of the map)
+  int nch;                     // chunks per staged tile (box_chunks of the map)
+  int chunk;                   // positions per chunk
   int ntiles;
   const uint4* wq;             // packed weights [hi | lo], conv_tc_kernels.cu layout
   const float* bias;           // [COUT] or null
@@ -149,12 +163,15 @@ __global__ void __launch_bounds__(kCpThreads, 1)
 convp_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvpArgs a) {
   constexpr int G = CIN / 8, GO = COUT / 8, NS = CIN / 16;
   constexpr int MT = NSUB * kCpM;
-  constexpr int ACC_COLS = NSUB * COUT;                  // one accumulator set
-  constexpr int TCOLS = 2 * ACC_COLS <= 32 ? 32 : (2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128 : 256));
+  // one accumulator set: per M block 2*COUT columns [a*hi(w) + lo(a)*hi(w) | hi(a)*lo(w)]
+  constexpr int ACC_COLS = NSUB * 2 * COUT;
+  constexpr int TCOLS = 2 * ACC_COLS <= 32 ? 32 : (2 * ACC_COLS <= 64 ? 64 : (2 * ACC_COLS <= 128 ? 128
+                        : (2 * ACC_COLS <= 256 ? 256 : 512)));
+  static_assert(2 * ACC_COLS <= 512, "TMEM has 512 columns");
   constexpr int NEPI = NSUB >= 2 ? 8 : 4;                // epilogue warps that own an M block
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int PW = a.g.PW;
-  const uint32_t P = (uint32_t)a.nch * 256u;             // plane stride in a stage (bytes)
+  const uint32_t P = (uint32_t)(a.nch * a.chunk) * 16u;  // plane stride in a stage (bytes)
   const uint32_t stage_bytes = 2u * G * P;
   uint8_t* s_stage = smem_raw;                           // [2][hi G planes | lo G planes]
   uint4* s_b = reinterpret_cast<uint4*>(smem_raw + 2 * (size_t)stage_bytes);   // 2 * 9*CIN*COUT bf16
@@ -200,13 +217,18 @@ convp_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvpArgs a) {
         if (it >= 2 && !mbar_wait_bounded(s_empty + s, (uint32_t)(((it >> 1) - 1) & 1))) { timed_out = true; break; }
         const int tile = (int)blockIdx.x + it * (int)gridDim.x;
         mbar_expect_tx(s_full + s, stage_bytes);
-        tma_load_3d(s_stage + (size_t)s * stage_bytes, &tm_in, 0, tile * (MT / 16), 0, s_full + s);
+        tma_load_3d(s_stage + (size_t)s * stage_bytes, &tm_in, 0, tile * MT / a.chunk, 0, s_full + s);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ================================ MMA issuer ==============================================
-    constexpr uint32_t idesc = umma_idesc(kCpM, COUT);
+    // The tensor core reads its A tile (128 positions x 16 channels = 4 KB) from shared memory
+    // at ~128 B/clk for EVERY instruction -- that, not the FLOP rate, bounds small-N MMAs (measured:
+    // 39 clk per 128x16x16).  So the bf16x3 product is issued as TWO reads of the activations per
+    // (tap, slab): hi(a) x [hi(w) | lo(w)] as one N = 2*COUT instruction, lo(a) x hi(w) accumulated
+    // onto its first half; the epilogue adds the halves.
+    constexpr uint32_t idesc2 = umma_idesc(kCpM, 2 * COUT), idesc1 = umma_idesc(kCpM, COUT);
     const uint32_t b_base = smem_u32(s_b);
     for (int it = 0; it < my_tiles; ++it) {
       const int s = it & 1;
@@ -216,21 +238,24 @@ convp_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvpArgs a) {
       if (elect_one()) {
         const uint32_t a_base = smem_u32(s_stage + (size_t)s * stage_bytes);
         const uint32_t d_base = tmem_base + (uint32_t)(s * ACC_COLS);
+        // descriptors are advanced by adding to their address field (16-byte units)
+        const uint64_t da0 = umma_desc(a_base, P, 128u);
+        const uint64_t db0 = umma_desc(b_base, (uint32_t)(2 * GO) * 128u, 128u);
+        const uint64_t lo_off = (uint64_t)((G * P) >> 4), slab_off = (uint64_t)((2 * P) >> 4);
 #pragma unroll 1
         for (int m = 0; m < NSUB; ++m) {
           uint32_t acc = 0;
+          const uint32_t d = d_base + (uint32_t)(m * 2 * COUT);
 #pragma unroll
           for (int tap = 0; tap < 9; ++tap) {
-            const int off = m * kCpM + (tap / 3) * PW + (tap % 3);
+            const uint64_t off = (uint64_t)(m * kCpM + (tap / 3) * PW + (tap % 3));
 #pragma unroll
             for (int sl = 0; sl < NS; ++sl) {
-              const uint64_t da = umma_desc(a_base + (uint32_t)(sl * 2) * P + (uint32_t)off * 16u, P, 128u);
-              const uint64_t db = umma_desc(b_base + (uint32_t)(tap * NS + sl) * (COUT * 32u), (uint32_t)GO * 128u, 128u);
-              umma_f16(d_base + (uint32_t)(m * COUT), da, db, idesc, acc);
+              const uint64_t da = da0 + off + (uint64_t)sl * slab_off;
+              const uint64_t db = db0 + (uint64_t)((tap * NS + sl) * (COUT * 64 / 16));
+              umma_f16(d, da, db, idesc2, acc);
+              umma_f16(d, da + lo_off, db, idesc1, 1u);
               acc = 1;
-              // + lo(a)*hi(b) + hi(a)*lo(b); the descriptor address field counts 16-byte units
-              umma_f16(d_base + (uint32_t)(m * COUT), da + (uint64_t)((G * P) >> 4), db, idesc, 1u);
-              umma_f16(d_base + (uint32_t)(m * COUT), da, db + (uint64_t)(9 * CIN * COUT / 8), idesc, 1u);
             }
           }
         }
@@ -282,9 +307,14 @@ convp_kernel(const __grid_constant__ CUtensorMap tm_in, const ConvpArgs a) {
         }
         float v[COUT];
 #pragma unroll
-        for (int hc = 0; hc < COUT / 16; ++hc)
-          tmem_ld<16>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * ACC_COLS + m * COUT + hc * 16),
-                      v + hc * 16);
+        for (int hc = 0; hc < COUT / 16; ++hc) {
+          float v2[16];
+          const uint32_t col = (uint32_t)(as * ACC_COLS + m * 2 * COUT + hc * 16);
+          tmem_ld<16>(tmem_base + ((uint32_t)(q * 32) << 16) + col, v + hc * 16);
+          tmem_ld<16>(tmem_base + ((uint32_t)(q * 32) << 16) + col + COUT, v2);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[hc * 16 + e] += v2[e];
+        }
         if (bi == NB - 1) {          // accumulator set drained: hand it back to the MMA warp
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
@@ -351,12 +381,13 @@ static int launch_convp(const PlaneConv& c, cudaStream_t st) {
   if (Lp + MT + 4 * g.PW >= (1LL << 31))
     return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "convp: batch too large for 32-bit positions");
   const int L = MT + 2 * g.PW + 2;
-  const int nch = (L + 15) / 16;
-  const size_t stage = (size_t)2 * (CIN / 8) * nch * 256;
+  const int CH = planes_chunk();
+  const int nch = (L + CH - 1) / CH;
+  const size_t stage = (size_t)2 * (CIN / 8) * nch * CH * 16;
   const size_t smem = 2 * stage + (size_t)2 * 9 * CIN * COUT * 2 + COUT * 4 + 8 * 8 + 16;
   if (smem > 227 * 1024) return kPlanesTryNext;
   CUtensorMap tm;
-  SEEDRL_TRY_RC(make_plane_map(&tm, c.in, Lp, 2 * (CIN / 8), 0, nch, 2 * (CIN / 8)));
+  SEEDRL_TRY_RC(make_plane_map(&tm, c.in, Lp, 2 * (CIN / 8), 0, CH, nch, 2 * (CIN / 8)));
   static bool attr = false;
   if (!attr) {
     SEEDRL_CUDA(cudaFuncSetAttribute(convp_kernel<CIN, COUT, NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -364,7 +395,7 @@ static int launch_convp(const PlaneConv& c, cudaStream_t st) {
     attr = true;
   }
   ConvpArgs a;
-  a.g = g; a.Lp = (int)Lp; a.nch = nch;
+  a.g = g; a.Lp = (int)Lp; a.nch = nch; a.chunk = CH;
   a.ntiles = (int)((Lp - g.PW - 1 + MT - 1) / MT);       // every storage position >= PW + 1 is written
   a.wq = reinterpret_cast<const uint4*>(c.wq); a.bias = c.bias;
   a.mask = reinterpret_cast<const uint4*>(c.mask); a.res = reinterpret_cast<const uint4*>(c.res);
@@ -405,9 +436,22 @@ int convp_forward(int cin, int cout, const PlaneConv& c, cudaStream_t st) {
 
 // ------------------------------------------------------------------------------------------------
 // weight + bias gradient
+//   dW[kh][kw][ci][co] = sum_p x~[p + kh*PW + kw][ci] * dy[p][co]
+//                      = sum_j x~[j + PW + kw][ci] * dy[j + (1 - kh)*PW][co]        (j = p + (kh-1)*PW)
+// GEMM with K = positions j (chunks of KC), M = (kw, ci) rows, N = (kh, co) columns:
+//   A  = three kw-shifted TMA copies of the x planes (no halo) + one constant plane whose first
+//        channel is 1 (its accumulator row is the bias gradient);  MN-major, 128 rows
+//   B  = three kh-shifted TMA copies of the dy planes; MN-major, hi planes then lo planes
+// so the activation tile -- the operand whose shared-memory read (4 KB per instruction at
+// ~128 B/clk) bounds small-N MMAs -- is read TWICE per 16 positions:
+//   hi(x) x [hi(dy) kh=0..2 | lo(dy) kh=0..2]   N = 6*COUT   -> D[:, 0 : 6*COUT]
+//   lo(x) x  hi(dy) kh=0..2                     N = 3*COUT   -> accumulated onto D[:, 0 : 3*COUT]
+// (the first version kept kh as a start-address offset of the x planes: three accumulators, nine
+// instructions and nine reads of the x tile per 16 positions -- the tensor pipe was 92 % busy at 19 %
+// of HBM bandwidth).  Terms with j < 0 pair the zero row above the first image with dy and vanish.
 struct WgradpArgs {
-  int PW, nchx, nchd, nchunks, nb;     // chunks of 16 positions per x / dy box; K chunks; stages
-  long long Q;
+  int PW, nchx, nchunks, nb;            // TMA chunks per box (x and dy alike); K chunks; stages
+  int chunk;                            // positions per TMA chunk
   float* partial;                       // [grid][9*CIN*COUT + COUT]
   int* err;
 };
@@ -415,21 +459,21 @@ struct WgradpArgs {
 constexpr int kWpThreads = 192;
 constexpr int kWpMaxStages = 4;
 
+struct WgradMaps { CUtensorMap x[3], dy[3]; };
+
 template <int CP, int COUT, int KC>
 __global__ void __launch_bounds__(kWpThreads, 1)
-wgradp_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__ CUtensorMap tm_x1,
-              const __grid_constant__ CUtensorMap tm_x2, const __grid_constant__ CUtensorMap tm_dy,
-              const WgradpArgs a) {
+wgradp_kernel(const __grid_constant__ WgradMaps tm, const WgradpArgs a) {
   constexpr int G = CP / 8, GO = COUT / 8;
   constexpr int XG = 3 * G + 1;                          // M groups per half: (kw, g) planes + ones/zeros plane
-  constexpr int TCOLS = 3 * COUT <= 32 ? 32 : (3 * COUT <= 64 ? 64 : 128);
+  constexpr int TCOLS = 6 * COUT <= 128 ? 128 : 256;
   constexpr int NW = 9 * CP * COUT + COUT;
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  const int PW = a.PW, nb = a.nb;
-  const uint32_t Px = (uint32_t)a.nchx * 256u;           // x plane stride (bytes)
-  const uint32_t Pd = (uint32_t)a.nchd * 256u;           // dy plane stride
-  const uint32_t xh_bytes = (uint32_t)XG * Px;
-  const uint32_t stage_bytes = 2u * xh_bytes + 2u * GO * Pd;   // [x hi | x lo | dy hi | dy lo]
+  const int nb = a.nb;
+  const uint32_t Pk = (uint32_t)(a.nchx * a.chunk) * 16u;   // plane stride (bytes), x and dy alike
+  const uint32_t xh_bytes = (uint32_t)XG * Pk;
+  const uint32_t dh_bytes = (uint32_t)(3 * GO) * Pk;
+  const uint32_t stage_bytes = 2u * xh_bytes + 2u * dh_bytes;   // [x hi | x lo | dy hi (kh,go) | dy lo (kh,go)]
   uint64_t* s_full = reinterpret_cast<uint64_t*>(smem_raw);
   uint64_t* s_empty = s_full + kWpMaxStages;
   uint64_t* s_done = s_empty + kWpMaxStages;
@@ -437,11 +481,11 @@ wgradp_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__
   uint8_t* s_stage = smem_raw + 128;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  // the constant planes of every stage: ones (x hi, element 0 of each position) and zeros (x lo)
-  for (int i = tid; i < nb * (int)(Px / 16); i += kWpThreads) {
-    const int sg = i / (int)(Px / 16), k = i - sg * (int)(Px / 16);
-    uint4* xh = reinterpret_cast<uint4*>(s_stage + (size_t)sg * stage_bytes + (size_t)(XG - 1) * Px);
-    uint4* xl = reinterpret_cast<uint4*>(s_stage + (size_t)sg * stage_bytes + xh_bytes + (size_t)(XG - 1) * Px);
+  // the constant planes of every stage: ones (x hi, channel 0 of each position) and zeros (x lo)
+  for (int i = tid; i < nb * (int)(Pk / 16); i += kWpThreads) {
+    const int sg = i / (int)(Pk / 16), k = i - sg * (int)(Pk / 16);
+    uint4* xh = reinterpret_cast<uint4*>(s_stage + (size_t)sg * stage_bytes + (size_t)(XG - 1) * Pk);
+    uint4* xl = reinterpret_cast<uint4*>(s_stage + (size_t)sg * stage_bytes + xh_bytes + (size_t)(XG - 1) * Pk);
     xh[k] = make_uint4(0x00003F80u, 0u, 0u, 0u);        // bf16 1.0 in channel 0
     xl[k] = make_uint4(0u, 0u, 0u, 0u);
   }
@@ -466,26 +510,27 @@ wgradp_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__
 
   if (warp == 0) {
     if (elect_one()) {
-      const uint32_t tx = (uint32_t)(6 * G) * Px + (uint32_t)(2 * GO) * Pd;
+      const uint32_t tx = (uint32_t)(6 * G + 6 * GO) * Pk;
       for (int it = 0; it < my_chunks; ++it) {
         const int s = it % nb;
         if (it >= nb && !mbar_wait_bounded(s_empty + s, (uint32_t)(((it / nb) - 1) & 1))) { timed_out = true; break; }
-        const int c16 = ((int)blockIdx.x + it * (int)gridDim.x) * (KC / 16);
+        const int c0 = ((int)blockIdx.x + it * (int)gridDim.x) * KC / a.chunk;
         uint8_t* base = s_stage + (size_t)s * stage_bytes;
         mbar_expect_tx(s_full + s, tx);
-        const CUtensorMap* xm[3] = {&tm_x0, &tm_x1, &tm_x2};
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          tma_load_3d(base + (size_t)(kw * G) * Px, xm[kw], 0, c16, 0, s_full + s);                 // hi planes
-          tma_load_3d(base + xh_bytes + (size_t)(kw * G) * Px, xm[kw], 0, c16, G, s_full + s);      // lo planes
+        for (int k = 0; k < 3; ++k) {
+          tma_load_3d(base + (size_t)(k * G) * Pk, &tm.x[k], 0, c0, 0, s_full + s);                  // x hi, kw = k
+          tma_load_3d(base + xh_bytes + (size_t)(k * G) * Pk, &tm.x[k], 0, c0, G, s_full + s);       // x lo
+          tma_load_3d(base + 2 * (size_t)xh_bytes + (size_t)(k * GO) * Pk, &tm.dy[k], 0, c0, 0, s_full + s);   // dy hi, kh = k
+          tma_load_3d(base + 2 * (size_t)xh_bytes + dh_bytes + (size_t)(k * GO) * Pk, &tm.dy[k], 0, c0, GO, s_full + s);
         }
-        tma_load_3d(base + 2 * (size_t)xh_bytes, &tm_dy, 0, c16, 0, s_full + s);
-        tma_load_3d(base + 2 * (size_t)xh_bytes + (size_t)GO * Pd, &tm_dy, 0, c16, GO, s_full + s);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
-    constexpr uint32_t idesc = umma_idesc(128, COUT) | (1u << 15) | (1u << 16);    // both operands MN-major
+    // both operands MN-major
+    constexpr uint32_t idesc6 = umma_idesc(128, 6 * COUT) | (1u << 15) | (1u << 16);
+    constexpr uint32_t idesc3 = umma_idesc(128, 3 * COUT) | (1u << 15) | (1u << 16);
     for (int it = 0; it < my_chunks; ++it) {
       const int s = it % nb;
       if (!mbar_wait_bounded(s_full + s, (uint32_t)((it / nb) & 1))) { timed_out = true; break; }
@@ -494,22 +539,15 @@ wgradp_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__
         const uint32_t xb = smem_u32(s_stage + (size_t)s * stage_bytes);
         const uint32_t db = xb + 2u * xh_bytes;
         // descriptors with start address 0 (the address field counts 16-byte units)
-        const uint64_t ax = umma_desc(0u, 128u, Px);
-        const uint64_t bd = umma_desc(0u, 128u, Pd);
-        const uint64_t xh = ax + (xb >> 4), xl = xh + (xh_bytes >> 4);
-        const uint64_t dh = bd + (db >> 4), dl = dh + ((GO * Pd) >> 4);
+        const uint64_t d0 = umma_desc(0u, 128u, Pk);
+        const uint64_t xh = d0 + (xb >> 4), xl = xh + (xh_bytes >> 4);
+        const uint64_t dh = d0 + (db >> 4);
         const uint32_t acc0 = it > 0 ? 1u : 0u;
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-          const uint32_t off = (uint32_t)(kh * PW);
-          const uint32_t d_tmem = tmem_base + (uint32_t)(kh * COUT);
-#pragma unroll
-          for (int ks = 0; ks < KC / 16; ++ks) {
-            const uint32_t ko = (uint32_t)(ks * 16);
-            umma_f16(d_tmem, xh + ko + off, dh + ko, idesc, (ks > 0) ? 1u : acc0);
-            umma_f16(d_tmem, xl + ko + off, dh + ko, idesc, 1u);
-            umma_f16(d_tmem, xh + ko + off, dl + ko, idesc, 1u);
-          }
+        for (int ks = 0; ks < KC / 16; ++ks) {
+          const uint32_t ko = (uint32_t)(ks * 16);
+          umma_f16(tmem_base, xh + ko, dh + ko, idesc6, (ks > 0) ? 1u : acc0);
+          umma_f16(tmem_base, xl + ko, dh + ko, idesc3, 1u);
         }
         umma_commit(s_empty + s);
       }
@@ -518,7 +556,7 @@ wgradp_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__
     if (elect_one()) umma_commit(s_done);
     __syncwarp();
   }
-  // ---- drain, then rows (kw, ci) of each kernel row's accumulator -> this CTA's partial ----------
+  // ---- drain, then rows (kw, ci) of the accumulator -> this CTA's partial ------------------------
   if (my_chunks > 0 && !timed_out) {
     if (!mbar_wait_bounded(s_done, 0u)) timed_out = true;
   }
@@ -529,19 +567,22 @@ wgradp_kernel(const __grid_constant__ CUtensorMap tm_x0, const __grid_constant__
   if (warp >= 2) {
     const int row = (warp & 3) * 32 + lane;              // TMEM lane = accumulator row
     const int kw = row / CP, ci = row - kw * CP;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
 #pragma unroll 1
     for (int kh = 0; kh < 3; ++kh) {
-      float v[COUT];
 #pragma unroll
-      for (int hc = 0; hc < COUT / 16; ++hc)
-        tmem_ld<16>(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(kh * COUT + hc * 16), v + hc * 16);
-      if (row < 3 * CP) {
+      for (int hc = 0; hc < COUT / 16; ++hc) {
+        float v[16], v2[16];
+        tmem_ld<16>(lane_addr + (uint32_t)(kh * COUT + hc * 16), v);                 // x * hi(dy)
+        tmem_ld<16>(lane_addr + (uint32_t)(3 * COUT + kh * COUT + hc * 16), v2);     // hi(x) * lo(dy)
+        if (row < 3 * CP) {
 #pragma unroll
-        for (int co = 0; co < COUT; ++co)
-          dst[((size_t)(kh * 3 + kw) * CP + ci) * COUT + co] = my_chunks > 0 ? v[co] : 0.f;
-      } else if (row == 3 * CP && kh == 0) {
+          for (int e = 0; e < 16; ++e)
+            dst[((size_t)(kh * 3 + kw) * CP + ci) * COUT + hc * 16 + e] = my_chunks > 0 ? v[e] + v2[e] : 0.f;
+        } else if (row == 3 * CP && kh == 1) {           // ones row x the unshifted-by-rows dy copy
 #pragma unroll
-        for (int co = 0; co < COUT; ++co) dst[9 * CP * COUT + co] = my_chunks > 0 ? v[co] : 0.f;
+          for (int e = 0; e < 16; ++e) dst[9 * CP * COUT + hc * 16 + e] = my_chunks > 0 ? v[e] + v2[e] : 0.f;
+        }
       }
     }
   }
@@ -558,35 +599,42 @@ static int launch_wgradp(int N, int H, int W, const void* x, const void* dy, flo
   const ConvGeom g = make_geom(N, H, W);
   const long long Lp = planes_positions(N, H, W);
   constexpr int G = CP / 8, GO = COUT / 8, XG = 3 * G + 1;
-  const int nchx = (KC + 2 * g.PW + 15) / 16, nchd = KC / 16;
-  const size_t Px = (size_t)nchx * 256, Pd = (size_t)nchd * 256;
-  const size_t stage = 2 * XG * Px + 2 * GO * Pd;
+  const int CH = planes_chunk() < KC ? planes_chunk() : KC;    // K chunks start on multiples of KC
+  if (KC % CH) return kPlanesTryNext;
+  const int nchx = KC / CH;
+  const size_t Pk = (size_t)KC * 16;
+  const size_t stage = 2 * XG * Pk + 2 * 3 * GO * Pk;
   // the M = 128 MMA reads 16 row groups from each x half: groups past XG are junk rows (never
-  // read back) but their addresses must stay inside the allocation
-  const size_t tail = 16 * Px + (size_t)(2 * g.PW + 2) * 16 + 256;
+  // read back) whose addresses stay inside the stage (x lo is followed by the dy planes)
+  const long long over = (long long)(16 - XG) * (long long)Pk - (long long)(6 * GO) * (long long)Pk;
+  const size_t tail = (over > 0 ? (size_t)over : 0) + 256;
   int nb = kWpMaxStages;
   while (nb > 1 && 128 + nb * stage + tail > 227 * 1024) --nb;
   if (nb < 2) return kPlanesTryNext;
   const size_t smem = 128 + nb * stage + tail;
-  CUtensorMap tx[3], td;
-  for (int kw = 0; kw < 3; ++kw) SEEDRL_TRY_RC(make_plane_map(&tx[kw], x, Lp, 2 * G, kw, nchx, G));
-  SEEDRL_TRY_RC(make_plane_map(&td, dy, Lp, 2 * GO, g.PW + 1, nchd, GO));
+  WgradMaps tm;
+  for (int k = 0; k < 3; ++k) {
+    SEEDRL_TRY_RC(make_plane_map(&tm.x[k], x, Lp, 2 * G, g.PW + k, CH, nchx, G));               // kw = k
+    SEEDRL_TRY_RC(make_plane_map(&tm.dy[k], dy, Lp, 2 * GO, (2 - k) * g.PW + 1, CH, nchx, GO));  // kh = k
+  }
   static bool attr = false;
   if (!attr) {
     SEEDRL_CUDA(cudaFuncSetAttribute(wgradp_kernel<CP, COUT, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      227 * 1024));
     attr = true;
   }
+  static const bool dbg = getenv("SEEDRL_DEBUG_LAUNCH") != nullptr;
+  if (dbg) fprintf(stderr, "wgradp<%d,%d,%d> CH=%d nb=%d stage=%zu smem=%zu\n", CP, COUT, KC, CH, nb, stage, smem);
   constexpr int NW = 9 * CP * COUT + COUT;
   WgradpArgs a;
-  a.PW = g.PW; a.nchx = nchx; a.nchd = nchd; a.nb = nb; a.Q = g.Q; a.err = err;
-  a.nchunks = (int)((g.Q + KC - 1) / KC);
+  a.PW = g.PW; a.nchx = nchx; a.nb = nb; a.err = err; a.chunk = CH;
+  a.nchunks = (int)((g.Q + g.PW + KC - 1) / KC);        // j = p + (kh - 1) * PW ranges over [0, Q + PW)
   const int grid = a.nchunks < kNumSMs ? a.nchunks : kNumSMs;
   if (!batch || batch->n >= kMaxReduceJobs || batch->used + (size_t)grid * NW > batch->cap_floats)
     return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "wgradp: partial buffer too small");
   a.partial = batch->buf + batch->used;
   batch->used += (size_t)grid * NW;
-  wgradp_kernel<CP, COUT, KC><<<grid, kWpThreads, smem, st>>>(tx[0], tx[1], tx[2], td, a);
+  wgradp_kernel<CP, COUT, KC><<<grid, kWpThreads, smem, st>>>(tm, a);
   count_launch(PC_CONV_WGRAD, st);
   SEEDRL_CHECK_LAUNCH();
   batch->jobs[batch->n++] = ReduceJob{a.partial, dw, db, grid, 9 * CP * COUT, COUT};
@@ -600,7 +648,7 @@ int wgradp(int cin, int cout, int N, int H, int W, const void* x, const void* dy
     int rc = launch_wgradp<CI, CO_, 256>(N, H, W, x, dy, dw, db, err, batch, st);                        \
     if (rc == kPlanesTryNext) rc = launch_wgradp<CI, CO_, 128>(N, H, W, x, dy, dw, db, err, batch, st);  \
     if (rc == kPlanesTryNext) rc = launch_wgradp<CI, CO_, 64>(N, H, W, x, dy, dw, db, err, batch, st);   \
-    if (rc == kPlanesTryNext) return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "wgradp: image too wide");   \
+    if (rc == kPlanesTryNext) return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "wgradp: does not fit");     \
     return rc;                                                                                           \
   }
   SEEDRL_WP_CASE(16, 16)
@@ -616,7 +664,7 @@ __global__ void to_planes_kernel(ConvGeom g, int Lp, int G, int relu, const floa
                                  uint4* __restrict__ out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)Lp * G) return;
-  const int go = (int)(i / Lp), s = (int)(i - (long long)go * Lp);
+  const int s = (int)(i / G), go = (int)(i - (long long)s * G);     // group fastest: a warp reads whole pixels
   const int pix = in_pixel(g, s);
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
   if (pix >= 0) {
@@ -634,7 +682,7 @@ __global__ void to_planes_kernel(ConvGeom g, int Lp, int G, int relu, const floa
 __global__ void from_planes_kernel(ConvGeom g, int Lp, int G, const uint4* __restrict__ in, float* __restrict__ y) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)Lp * G) return;
-  const int go = (int)(i / Lp), s = (int)(i - (long long)go * Lp);
+  const int s = (int)(i / G), go = (int)(i - (long long)s * G);     // group fastest: a warp reads whole pixels
   const int pix = in_pixel(g, s);
   if (pix < 0) return;
   const uint4 h = __ldg(in + (size_t)go * Lp + s), l = __ldg(in + (size_t)(G + go) * Lp + s);
@@ -673,7 +721,7 @@ __global__ void poolp_fwd_kernel(ConvGeom go_, int Lp, int G, int H, int W, int 
                                  uint4* __restrict__ out_relu, uint8_t* __restrict__ idx) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)Lp * G) return;
-  const int gq = (int)(i / Lp), s = (int)(i - (long long)gq * Lp);
+  const int s = (int)(i / G), gq = (int)(i - (long long)s * G);
   const int pix = in_pixel(go_, s);           // pooled pixel (n * Ho + ho) * Wo + wo
   float best[8];
   unsigned char arg[8];
@@ -726,7 +774,7 @@ __global__ void poolp_bwd_kernel(ConvGeom gf, int Lpf, ConvGeom gp, int Lpp, int
   int gq, s = 0, pix;
   if (OUT_PLANES) {
     if (i >= (long long)Lpf * G) return;
-    gq = (int)(i / Lpf); s = (int)(i - (long long)gq * Lpf);
+    s = (int)(i / G); gq = (int)(i - (long long)s * G);
     pix = in_pixel(gf, s);
   } else {
     if (i >= (long long)gf.N * H * W * G) return;

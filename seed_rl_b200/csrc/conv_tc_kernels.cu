@@ -49,6 +49,16 @@ __global__ void pack_w_tc_kernel(int CIN, int COUT, int cin_src, int flip, int s
   const float v = ci >= cin_src ? 0.f
                   : (flip ? w[((size_t)(8 - tap) * COUT + co) * CIN + ci] : w[((size_t)tap * cin_src + ci) * COUT + co]);
   const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  if (split == 2) {
+    // merged layout of the plane-tensor kernels (conv_planes.cu): per (tap, slab, kchunk) the hi
+    // c_out groups are followed by the lo c_out groups, so ONE MMA with N = 2*COUT computes
+    // a*hi(w) and a*lo(w) from a single read of the activation tile
+    const int GOc = COUT / 8;
+    const size_t j = ((((size_t)(tap * NS + slab) * 2 + kc) * (2 * GOc) + cog) * 8 + r) * 8 + e;
+    wq[j] = hi;
+    wq[j + (size_t)GOc * 64] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    return;
+  }
   wq[i] = hi;
   if (split) wq[9 * CIN * COUT + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
@@ -74,6 +84,13 @@ __global__ void pack_w_tc_batch_kernel(const __grid_constant__ PackTable t, int 
                             : j.w[((size_t)tap * j.cin_src + ci) * COUT + co]);
   __nv_bfloat16* wq = reinterpret_cast<__nv_bfloat16*>(j.wq);
   const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  if (split == 2 && !j.legacy) {          // merged hi|lo layout (see pack_w_tc_kernel)
+    const int GOc = COUT / 8;
+    const size_t q = ((((size_t)(tap * NS + slab) * 2 + kc) * (2 * GOc) + cog) * 8 + r) * 8 + e;
+    wq[q] = hi;
+    wq[q + (size_t)GOc * 64] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    return;
+  }
   wq[i] = hi;
   if (split) wq[9 * CIN * COUT + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
 }

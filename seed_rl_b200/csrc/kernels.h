@@ -66,7 +66,7 @@ __host__ __device__ __forceinline__ int out_pixel(const ConvGeom& g, int p) {
 // Job tables: one launch packs every layer's weights / reduces every layer's weight-gradient
 // partials (passed to the kernels by value as __grid_constant__ parameters).
 constexpr int kMaxPackJobs = 32, kMaxReduceJobs = 16;
-struct PackJob { const float* w; void* wq; int ck, cout, cin_src, flip; };
+struct PackJob { const float* w; void* wq; int ck, cout, cin_src, flip, legacy; };
 struct PackTable { PackJob jobs[kMaxPackJobs]; int n; };
 struct ReduceJob { const float* partial; float* dw; float* db; int nparts, nw, nb; };
 struct ReduceTable { ReduceJob jobs[kMaxReduceJobs]; };

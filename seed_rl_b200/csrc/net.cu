@@ -246,10 +246,11 @@ static int pack_all_weights(const seedrl_net* n, const float* prm, void* ws, con
       j.w = P(n, prm, l.w);
       j.wq = base + (size_t)ctx->packed.n * kPackSlotBytes;
       j.ck = cin < 16 ? 16 : cin; j.cout = cout; j.cin_src = cin; j.flip = flip;
+      j.legacy = (s == 0 && i == 0) ? 1 : 0;           // the uint8 first conv runs the staged kernel
       ctx->packed.jobs[ctx->packed.n++] = j;
     }
   }
-  return conv3x3_tc_pack_weights_batch(ctx->packed, n->conv_mode >= 2, st);
+  return conv3x3_tc_pack_weights_batch(ctx->packed, n->conv_mode == 3 ? 2 : (n->conv_mode >= 2 ? 1 : 0), st);
 }
 static const void* find_packed(const float* w, int flip) {
   if (!t_ctx) return nullptr;
@@ -428,7 +429,7 @@ static int planes_conv(const seedrl_net* n, void* ws, const Plan& pl, int cin, i
   const void* wq = find_packed(w, flip);
   if (!wq) {
     void* scratch = W<void>(ws, pl.wq);
-    SEEDRL_TRY(conv3x3_tc_pack_weights(cin, cout, flip, 1, w, scratch, st));
+    SEEDRL_TRY(conv3x3_tc_pack_weights(cin, cout, flip, 2, w, scratch, st));
     wq = scratch;
   }
   PlaneConv c;
@@ -911,7 +912,7 @@ extern "C" int seedrl_debug_convp(int cin, int cout, int N, int H, int W, const 
                                   void* out_raw, void* out_relu, float* out_nhwc, void* wq_scratch,
                                   int* error_flag, seedrl_stream_t stream) {
   SEEDRL_CHECK_ARG(convp_supported(cin, cout) && in && w && wq_scratch, "unsupported (cin,cout) or null pointer");
-  SEEDRL_TRY(conv3x3_tc_pack_weights(cin, cout, flip, 1, w, wq_scratch, (cudaStream_t)stream));
+  SEEDRL_TRY(conv3x3_tc_pack_weights(cin, cout, flip, 2, w, wq_scratch, (cudaStream_t)stream));
   PlaneConv c;
   c.N = N; c.H = H; c.W = W; c.in = in; c.wq = wq_scratch; c.bias = bias; c.mask = mask; c.res = res;
   c.out_raw = out_raw; c.out_relu = out_relu; c.out_nhwc = out_nhwc; c.err = error_flag;
