@@ -495,7 +495,7 @@ def main():
       # ---- the other contraction paths, same workload (5 steps each) ----------------------
       others = {}
       for mode in ('simt', 'tc', 'tc3', 'tc3p'):
-        if mode == args.conv:
+        if mode == args.conv or (mode == 'tc3p' and args.net != 'deep'):
           continue
         ag = cls(A, OBS, seed=0, conv_mode=mode)
         stp = learner.LearnerStep(ag, optimizers.Adam(4.8e-4, beta_1=0.0, epsilon=3.125e-7),

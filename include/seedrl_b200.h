@@ -294,9 +294,40 @@ int seedrl_profile_begin(seedrl_stream_t stream);
 int seedrl_profile_end(double* ms_per_category, uint64_t* launches_per_category);
 
 /* ------------------------------------------------------------------------
- * R2D2 post-network pieces.  Written and compiled in round 1, not yet
- * executed on hardware; nothing on the V-trace path calls them.
+ * R2D2 (BASELINE cfg 5): the agent network, then the post-network pieces.
  *
+ * seedrl_r2d2_net_* <- atari/networks.py:221-340 (DuelingLSTMDQNNet: __call__/_unroll/_torso/_head)
+ *   and :176-218 (_unroll_cell).  Parameters: one flat fp32 arena in
+ *   tf.Module.trainable_variables order (_advantage, _body, _core, _value), Keras layouts.
+ *   forward: time-major prev_actions int64 [T,B], reward [T,B], done uint8 [T,B], frames uint8
+ *   [T,B,H,W,C] ALREADY STACKED (C = stack_size; seedrl_r2d2_stack_frames), h0/c0 [B,512] ->
+ *   q_values [T,B,A], action int32 [T,B] (argmax, first maximum; may be NULL), h_out/c_out.
+ *   backward: dq [T,B,A] -> grads (arena layout, overwritten); must follow the forward of the same
+ *   (T,B) on the same workspace.  mode: 0 fp32 SIMT GEMMs, 2 (default) tcgen05 bf16x3.
+ *   Errors: SEEDRL_ERR_INVALID_ARGUMENT for null / undersized buffers (the reference raises from
+ *   TF shape checks); seedrl_r2d2_net_check_error as seedrl_net_check_error. */
+typedef struct seedrl_r2d2_net seedrl_r2d2_net;
+int seedrl_r2d2_net_create(int num_actions, int obs_h, int obs_w, int channels, seedrl_r2d2_net** out);
+void seedrl_r2d2_net_destroy(seedrl_r2d2_net* net);
+int seedrl_r2d2_net_num_param_tensors(const seedrl_r2d2_net* net);      /* 19 */
+size_t seedrl_r2d2_net_num_params(const seedrl_r2d2_net* net);
+size_t seedrl_r2d2_net_arena_floats(const seedrl_r2d2_net* net);
+int seedrl_r2d2_net_set_mode(seedrl_r2d2_net* net, int mode);
+int seedrl_r2d2_net_param_info(const seedrl_r2d2_net* net, int index, char* name_buf, size_t name_buf_len,
+                               int64_t* dims4, int* rank, size_t* offset_floats);
+size_t seedrl_r2d2_net_workspace_bytes(const seedrl_r2d2_net* net, int T, int B);
+int seedrl_r2d2_net_forward(const seedrl_r2d2_net* net, const float* params, int T, int B,
+                            const int64_t* prev_actions, const float* reward, const uint8_t* done,
+                            const uint8_t* frames, const float* h0, const float* c0, float* q_values,
+                            int32_t* action, float* h_out, float* c_out, void* workspace,
+                            size_t workspace_bytes, seedrl_stream_t stream);
+int seedrl_r2d2_net_backward(const seedrl_r2d2_net* net, const float* params, int T, int B,
+                             const uint8_t* done, const float* dq, float* grads, void* workspace,
+                             size_t workspace_bytes, seedrl_stream_t stream);
+int seedrl_r2d2_net_check_error(const seedrl_r2d2_net* net, int T, int B, void* workspace,
+                                size_t workspace_bytes, seedrl_stream_t stream);
+
+/*
  * seedrl_r2d2_stack_frames <- atari/networks.py:57-173 (stack_frames): frames uint8 [T,B,P]
  *   (P = prod(observation_shape), one channel), state int32 [B,P] bit-packed (LSB byte =
  *   oldest of the stack_size-1 kept frames), done [T,B].  stacked uint8 [T,B,P,stack_size],

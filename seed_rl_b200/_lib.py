@@ -93,6 +93,20 @@ SIGNATURES = {
     'seedrl_batcher_next_full': (c_int, [P, c_int, ctypes.POINTER(c_int)]),
     'seedrl_batcher_publish': (c_int, [P, c_int, c_int]),
     'seedrl_batcher_shutdown': (c_int, [P]),
+    'seedrl_r2d2_net_create': (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(P)]),
+    'seedrl_r2d2_net_destroy': (None, [P]),
+    'seedrl_r2d2_net_num_param_tensors': (c_int, [P]),
+    'seedrl_r2d2_net_num_params': (c_size_t, [P]),
+    'seedrl_r2d2_net_arena_floats': (c_size_t, [P]),
+    'seedrl_r2d2_net_set_mode': (c_int, [P, c_int]),
+    'seedrl_r2d2_net_param_info':
+        (c_int, [P, c_int, ctypes.c_char_p, c_size_t, ctypes.POINTER(c_i64), ctypes.POINTER(c_int),
+                 ctypes.POINTER(c_size_t)]),
+    'seedrl_r2d2_net_workspace_bytes': (c_size_t, [P, c_int, c_int]),
+    'seedrl_r2d2_net_forward':
+        (c_int, [P, P, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, c_size_t, P]),
+    'seedrl_r2d2_net_backward': (c_int, [P, P, c_int, c_int, P, P, P, P, c_size_t, P]),
+    'seedrl_r2d2_net_check_error': (c_int, [P, c_int, c_int, P, c_size_t, P]),
     'seedrl_r2d2_stack_frames': (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
     'seedrl_r2d2_loss_scratch_bytes': (c_size_t, [c_int, c_int, c_int]),
     'seedrl_r2d2_loss_fwd_bwd': (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, c_float, c_int, c_float, c_float,

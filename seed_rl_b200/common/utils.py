@@ -8,7 +8,9 @@ for the pieces the V-trace learner uses:
   batch_apply / make_time_major utils.py:714-761   (views; no data movement)
   validate_learner_config       utils.py:989-1002
 
-PrioritizedReplay / HER / TPU encode are out of scope.
+  PrioritizedReplay             utils.py:260-370   (GPU-resident; sampling = seedrl_replay_sample)
+
+HER / TPU encode are out of scope.
 """
 import collections
 import threading
@@ -245,6 +247,69 @@ class Aggregator(object):
       if v.dim() < s.dim():
         v = v.expand([ids.numel()] + list(s.shape[1:]))
       s[ids] = v
+
+
+class PrioritizedReplay(object):
+  """Prioritized replay buffer (reference utils.py:260-370) with storage, priorities and the
+  sampling arithmetic resident in HBM.  Not thread-safe, like the reference's: call insert()
+  and sample() from a single thread.
+
+  Sampling (:327-352) for priority_exp != 0 is ONE kernel (seedrl_replay_sample: p_i =
+  prio_i^alpha / sum, inverse-CDF draw, importance weights normalised by their max); the
+  reference draws the indices with tf.random.categorical -- same distribution, different random
+  stream (its own test is statistical, tests/utils_test.py:353-365)."""
+
+  def __init__(self, size, specs, importance_sampling_exponent, name='PrioritizedReplay', device='cuda'):
+    self._size = int(size)
+    self._specs = specs
+    self._device = torch.device(device)
+    self._priorities = torch.zeros([self._size], dtype=torch.float32, device=self._device)
+    self._buffer = map_structure(
+        lambda ts: torch.zeros([self._size] + list(ts.shape), dtype=as_torch_dtype(ts.dtype), device=self._device),
+        specs)
+    self.num_inserted = 0
+    self._importance_sampling_exponent = float(importance_sampling_exponent)
+
+  def insert(self, values, priorities):
+    """FIFO insertion/removal with wrap-around (:277-309).  Returns the inserted indices."""
+    assert_same_structure(values, self._buffer)
+    flat_v = [_lib.require_cuda(v, b.dtype, 'values') for v, b in zip(flatten(values), flatten(self._buffer))]
+    append_size = int(flat_v[0].shape[0])
+    start = self.num_inserted
+    insert_indices = (torch.arange(start, start + append_size, device=self._device) % self._size)
+    for b, v in zip(flatten(self._buffer), flat_v):
+      if tuple(v.shape[1:]) != tuple(b.shape[1:]):
+        raise ValueError('value of shape %s does not match the spec %s' % (tuple(v.shape[1:]), tuple(b.shape[1:])))
+      b.index_copy_(0, insert_indices, v)
+    self.num_inserted += append_size
+    self._priorities.index_copy_(0, insert_indices, _lib.require_cuda(priorities, torch.float32, 'priorities'))
+    return insert_indices
+
+  def sample(self, num_samples, priority_exp, generator=None, uniforms=None):
+    """(:311-357) -> (indices int64 [num_samples], weights float32 [num_samples], sampled values
+    with an added front batch dimension)."""
+    if self.num_inserted <= 0:
+      raise ValueError('Cannot sample if replay buffer is empty')
+    limit = min(self._size, self.num_inserted)
+    if priority_exp == 0:
+      indices = torch.randint(0, limit, [num_samples], dtype=torch.int64, device=self._device, generator=generator)
+      weights = torch.ones([num_samples], dtype=torch.float32, device=self._device)
+    else:
+      if uniforms is None:
+        uniforms = torch.rand(num_samples, device=self._device, generator=generator)
+      u = _lib.require_cuda(uniforms, torch.float32, 'uniforms')
+      indices = torch.empty(num_samples, dtype=torch.int64, device=self._device)
+      weights = torch.empty(num_samples, dtype=torch.float32, device=self._device)
+      _lib.check(_lib.lib().seedrl_replay_sample(
+          limit, _lib.ptr(self._priorities), float(priority_exp), self._importance_sampling_exponent,
+          int(num_samples), _lib.ptr(u), _lib.ptr(indices), _lib.ptr(weights), None, _lib.stream_ptr()))
+    sampled_values = map_structure(lambda b: b.index_select(0, indices), self._buffer)
+    return indices, weights, sampled_values
+
+  def update_priorities(self, indices, priorities):
+    """(:359-370) duplicate indices: which priority wins is unspecified, as in the reference."""
+    self._priorities.index_copy_(0, _lib.require_cuda(indices, torch.int64, 'indices'),
+                                 _lib.require_cuda(priorities, torch.float32, 'priorities'))
 
 
 class QueueClosedError(RuntimeError):

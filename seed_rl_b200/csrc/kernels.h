@@ -180,11 +180,11 @@ int lstm_pointwise_bwd(int B, int Hd, const float* gates, const float* c_t, cons
                        cudaStream_t st);
 int fill(size_t n, float* p, float v, cudaStream_t st);
 
-// lstm_persistent.cu
-int lstm_forward_persistent(int T1, int B, const float* U, const uint8_t* done, float* z,
+// lstm_persistent.cu (H = 256: ImpalaDeep core; H = 512: DuelingLSTMDQNNet core)
+int lstm_forward_persistent(int H, int T1, int B, const float* U, const uint8_t* done, float* z,
                             const float* h0, const float* c0, float* hs, float* cs, float* hp,
                             unsigned int* counter, int* err, cudaStream_t st);
-int lstm_backward_persistent(int T1, int B, const float* U, const uint8_t* done, const float* gates,
+int lstm_backward_persistent(int H, int T1, int B, const float* U, const uint8_t* done, const float* gates,
                              const float* cs, const float* c0, const float* dhs, float* dz,
                              unsigned int* counter, int* err, cudaStream_t st);
 

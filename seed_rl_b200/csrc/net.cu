@@ -543,7 +543,7 @@ extern "C" int seedrl_net_forward(const seedrl_net* n, const float* prm, int T1,
   eacc.accumulate = 1;
   if (n->lstm_mode == 1) {
     // one cooperative kernel for the whole recurrence (lstm_persistent.cu)
-    SEEDRL_TRY(lstm_forward_persistent(T1, B, P(n, prm, n->p_core_u), done, z, h0, c0buf, hs, cs, hp,
+    SEEDRL_TRY(lstm_forward_persistent(kHidden, T1, B, P(n, prm, n->p_core_u), done, z, h0, c0buf, hs, cs, hp,
                                        W<unsigned int>(ws, pl.counter), W<int>(ws, pl.tcerr), st));
   } else {
     SEEDRL_TRY(lstm_mask_state(B, kHidden, done, h0, hp, st));
@@ -746,7 +746,7 @@ extern "C" int seedrl_net_backward(const seedrl_net* n, const float* prm, int T1
                    eacc, st));
   // BPTT
   if (n->lstm_mode == 1)
-    SEEDRL_TRY(lstm_backward_persistent(T1, B, P(n, prm, n->p_core_u), done, z, cs, c0buf, dhs, dz,
+    SEEDRL_TRY(lstm_backward_persistent(kHidden, T1, B, P(n, prm, n->p_core_u), done, z, cs, c0buf, dhs, dz,
                                         W<unsigned int>(ws, pl.counter), W<int>(ws, pl.tcerr), st));
   for (int t = T1 - 1; t >= 0 && n->lstm_mode == 0; --t) {
     const bool last = (t + 1 == T1);

@@ -78,3 +78,148 @@ def test_replay_sample_and_clip():
   n64 = np.sqrt((g.astype(np.float64) ** 2).sum())
   np.testing.assert_allclose(float(norm), n64, rtol=1e-5)
   np.testing.assert_allclose(gc.cpu().numpy(), g * np.float32(40.0 / max(n64, 40.0)), rtol=1e-5)
+
+
+# ---- DuelingLSTMDQNNet (csrc/r2d2_net.cu) and the cfg-5 learner step vs the CPU oracle -----------
+def _net_case(T, B, A, obs, S, seed, done_p=0.15):
+  from oracle import r2d2_learner_oracle as RL, r2d2_net_oracle as NO
+  params = NO.init_params(A, obs, S, seed=seed)
+  b = RL.synthetic_replay_batch(T, B, A, obs, seed=seed + 1, done_p=done_p)
+  return params, b
+
+
+def _to_cuda_inputs(b, S):
+  from seed_rl_b200.atari import networks
+  from seed_rl_b200.common import utils
+  c = lambda a: torch.as_tensor(np.asarray(a)).cuda()
+  T, B = b['reward'].shape
+  env = utils.EnvOutput(c(b['reward']), c(b['done']), c(b['observation']),
+                        torch.zeros(T, B, dtype=torch.bool).cuda(), torch.zeros(T, B, dtype=torch.int32).cuda())
+  state = networks.AgentState((c(b['h0']), c(b['c0'])), c(b['frame_state']) if S > 1 else ())
+  return c(b['prev_actions']), env, state
+
+
+@pytest.mark.parametrize('mode,tol', [('simt', 2e-4), ('tc3', 5e-4)])
+@pytest.mark.parametrize('T,B,A,obs,S', [(5, 3, 6, (36, 36, 1), 4), (3, 2, 18, (84, 84, 1), 4), (4, 2, 4, (44, 40, 4), 1)])
+def test_dueling_net_forward_backward_vs_oracle(mode, tol, T, B, A, obs, S):
+  from oracle import r2d2_net_oracle as NO
+  from seed_rl_b200.atari import networks
+  params, b = _net_case(T, B, A, obs, S, seed=T + A)
+  agent = networks.DuelingLSTMDQNNet(A, obs, S, gemm_mode=mode)
+  assert len(agent.trainable_variables) == 19          # atari/networks_test.py: variable structure
+  agent.load_named_parameters(params)
+  pa, env, state = _to_cuda_inputs(b, S)
+  out, new_state = agent((pa, env), state, unroll=True, is_training=True)
+  agent.check_errors()
+  pt = {k: torch.tensor(v, requires_grad=True) for k, v in params.items()}
+  fs = b['frame_state'] if S > 1 else ()
+  want, want_state = NO.unroll(pt, b['prev_actions'], b['reward'], b['done'], b['observation'],
+                               NO.AgentState((torch.as_tensor(b['h0']), torch.as_tensor(b['c0'])), fs), A, S)
+  q, wq = out.q_values.cpu().numpy(), want.q_values.detach().numpy()
+  scale = np.abs(wq).max()
+  assert np.abs(q - wq).max() <= tol * scale + 1e-6, np.abs(q - wq).max() / scale
+  # greedy action: bit-exact wherever the top-2 gap of the oracle exceeds the forward tolerance
+  srt = np.sort(wq, axis=-1)
+  clear = (srt[..., -1] - srt[..., -2]) > 4 * tol * scale
+  np.testing.assert_array_equal(out.action.cpu().numpy()[clear], want.action.numpy()[clear])
+  np.testing.assert_array_equal(out.action.cpu().numpy(), q.argmax(-1))       # argmax of its own Q, first max
+  np.testing.assert_allclose(new_state.core_state[0].cpu().numpy(), want_state.core_state[0].detach().numpy(),
+                             atol=tol)
+  np.testing.assert_allclose(new_state.core_state[1].cpu().numpy(), want_state.core_state[1].detach().numpy(),
+                             atol=2 * tol)
+  if S > 1:
+    np.testing.assert_array_equal(new_state.frame_stacking_state.cpu().numpy(), want_state.frame_stacking_state)
+  # backward: random dq
+  rng = np.random.default_rng(3)
+  dq = rng.normal(size=wq.shape).astype(np.float32)
+  (want.q_values * torch.as_tensor(dq)).sum().backward()
+  agent.backward(torch.as_tensor(dq).cuda())
+  agent.check_errors()
+  mine = agent.named_gradients()
+  gtol = {'simt': 2e-3, 'tc3': 5e-3}[mode]
+  for k, v in pt.items():
+    w = v.grad.numpy()
+    err = np.abs(mine[k].cpu().numpy() - w).max() / (np.abs(w).max() + 1e-30)
+    assert err < gtol, (k, err)
+
+
+@pytest.mark.parametrize('mode', ['simt', 'tc3'])
+def test_r2d2_learner_step_vs_oracle(mode):
+  """compute_loss_and_priorities with burn-in + minimize (clip, Adam) + target sync, 2 steps."""
+  from oracle import r2d2_learner_oracle as RL, r2d2_net_oracle as NO
+  from seed_rl_b200.agents.r2d2 import learner
+  from seed_rl_b200.atari import networks
+  from seed_rl_b200.common import optimizers
+  A, obs, S, T, B, burn = 6, (36, 36, 1), 4, 12, 4, 4
+  params = NO.init_params(A, obs, S, seed=5)
+  tparams = NO.init_params(A, obs, S, seed=6)
+  cpu = RL.CpuR2D2Learner(A, obs, S, burn_in=burn, params=params, target_params=tparams, lr=1e-3)
+  agent = networks.DuelingLSTMDQNNet(A, obs, S, gemm_mode=mode); agent.load_named_parameters(params)
+  target = networks.DuelingLSTMDQNNet(A, obs, S, gemm_mode=mode); target.load_named_parameters(tparams)
+  st = learner.default_settings(burn_in=burn, update_target_every_n_step=10**9)
+  step = learner.R2D2LearnerStep(agent, target, optimizers.Adam(1e-3, epsilon=1e-3), settings=st)
+  step.optimizer.iterations = 1          # no target sync at iteration 0 in this test: the targets differ
+  tol = {'simt': 2e-3, 'tc3': 6e-3}[mode]
+  for it in range(2):
+    b = RL.synthetic_replay_batch(T, B, A, obs, seed=20 + it, done_p=0.1)
+    pa, env, state = _to_cuda_inputs(b, S)
+    c = lambda a: torch.as_tensor(np.asarray(a)).cuda()
+    unrolls = learner.Unroll(state, None, pa, env, learner.AgentOutput(c(b['action']), None))
+    sampled = learner.SampledUnrolls(unrolls, c(b['indices']), c(b['importance_weights']))
+    total, loss_b, prio, g, norm, _ = cpu.grads(b)
+    loss, priorities, indices, gnorm = step.compute_gradients(sampled)
+    agent.check_errors()
+    assert abs(float(loss) - total) < 1e-3 * max(1.0, abs(total)), (float(loss), total)
+    np.testing.assert_allclose(priorities.cpu().numpy(), prio, rtol=2e-3, atol=1e-4)
+    np.testing.assert_allclose(float(gnorm), norm, rtol=5e-3)
+    scale = np.float32(st.clip_norm / max(norm, st.clip_norm))
+    mine = agent.named_gradients()
+    for k in g:
+      w = g[k] * scale
+      err = np.abs(mine[k].cpu().numpy() - w).max() / (np.abs(w).max() + 1e-30)
+      assert err < tol, (it, k, err)
+    step.apply_gradients()
+    cpu.step(b)
+    for k, v in agent.named_parameters().items():
+      np.testing.assert_allclose(v.cpu().numpy(), cpu.params[k].detach().numpy(), atol=2e-4, rtol=0)
+  # update_target_agent: target_var.assign(source_var)
+  step.update_target_agent()
+  assert torch.equal(target.params, agent.params)
+
+
+def test_prioritized_replay_and_feeder():
+  """insert wrap-around / sample / update_priorities (common/utils.py:260-370; sequences of
+  tests/utils_test.py:304-365) on the GPU-resident buffer, and the ReplayFeeder hand-off."""
+  from seed_rl_b200.agents.r2d2 import learner
+  from seed_rl_b200.common import utils
+  spec = (utils.TensorSpec([2], 'float32', 'a'), utils.TensorSpec([], 'int32', 'b'))
+  rb = utils.PrioritizedReplay(4, spec, importance_sampling_exponent=0.6)
+  with pytest.raises(ValueError, match='Cannot sample if replay buffer is empty'):
+    rb.sample(1, 1.0)
+  c = lambda a: torch.as_tensor(np.asarray(a)).cuda()
+  idx = rb.insert((c(np.arange(6, dtype=np.float32).reshape(3, 2)), c(np.array([10, 11, 12], np.int32))),
+                  c(np.array([1., 2., 3.], np.float32)))
+  assert idx.tolist() == [0, 1, 2] and rb.num_inserted == 3
+  idx = rb.insert((c(np.arange(6, 10, dtype=np.float32).reshape(2, 2)), c(np.array([13, 14], np.int32))),
+                  c(np.array([4., 5.], np.float32)))
+  assert idx.tolist() == [3, 0] and rb.num_inserted == 5              # FIFO wrap-around
+  u = np.linspace(0.01, 0.99, 512).astype(np.float32)
+  i, w, (a, bvals) = rb.sample(512, 1.0, uniforms=c(u))
+  prio = np.array([5., 2., 3., 4.], np.float32)
+  p = R.replay_probabilities(prio, 5, 1.0)
+  np.testing.assert_allclose(w.cpu().numpy(), R.replay_importance_weights(p, i.cpu().numpy(), 0.6), rtol=5e-5)
+  np.testing.assert_array_equal(bvals.cpu().numpy(), np.array([14, 11, 12, 13])[i.cpu().numpy()])
+  freq = np.bincount(i.cpu().numpy(), minlength=4) / 512
+  assert np.abs(freq - p).max() < 0.01
+  rb.update_priorities(c(np.array([1, 2], np.int64)), c(np.array([0., 0.], np.float32)))
+  i, _, _ = rb.sample(256, 1.0)
+  assert set(i.cpu().numpy().tolist()) <= {0, 3}                       # zero-priority items are never drawn
+  i, w, _ = rb.sample(64, 0)                                           # uniform branch (:335-337)
+  assert float(w.min()) == 1.0 and i.max() < 4
+  # epsilon schedule (agents/r2d2/learner_test.py:60-70) and greedy override
+  eps = learner.get_envs_epsilon(torch.arange(5), 3, 2, 0.001).cpu().numpy()
+  np.testing.assert_allclose(eps, R.get_envs_epsilon(np.arange(5), 3, 2, 0.001), rtol=1e-6)
+  acts = learner.apply_epsilon_greedy(torch.full([4096], 7, dtype=torch.int32).cuda(), torch.zeros(4096, dtype=torch.int64),
+                                      2, 1, 0.0, 18)
+  frac = float((acts != 7).float().mean())
+  assert abs(frac - 0.4 * 17 / 18) < 0.05
