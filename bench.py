@@ -39,6 +39,9 @@ def parse_args():
   p.add_argument('--warmup', type=int, default=10)
   p.add_argument('--impl', default='b200', choices=['b200', 'reference'])
   p.add_argument('--net', default='deep', choices=['deep', 'shallow'])
+  p.add_argument('--agent', default='vtrace', choices=['vtrace', 'r2d2'],
+                 help='vtrace = the headline IMPALA learner (BASELINE configs[1..3]); r2d2 = configs[4]: '
+                      'DuelingLSTMDQNNet learner step on synthetic prioritized replay')
   p.add_argument('--batch', type=int, default=64, help='unrolls per GPU')
   p.add_argument('--unroll', type=int, default=20)
   p.add_argument('--cpu-batch', type=int, default=0,
@@ -231,6 +234,239 @@ def conv_bytes_per_step_planes(N, cat):
   return tot, launches
 
 
+def inference_path_bench(agent, iters=200, warmup=30, N=64, num_envs=256, T=20, batch=64):
+  """Hot path (1) of the north star: the batched central-inference step (reference
+  agents/vtrace/learner.py:349-407) -- host batch -> H2D -> gather of the previous action / LSTM
+  state -> T=1 ImpalaDeep forward -> in-kernel sampling -> write-back + unroll-store append ->
+  actions back on the host -- through the public `InferenceHost.inference` call (no RPC
+  transport), with a consumer draining the zero-copy training batches as a learner would.
+  Wall clock (the call returns host actions, i.e. it is synchronous per batch)."""
+  import threading
+  import numpy as np
+  import torch
+  from seed_rl_b200 import _lib
+  from seed_rl_b200.agents.vtrace import learner_loop
+  from seed_rl_b200.common import utils
+  host = learner_loop.InferenceHost(agent, num_envs, T, N, OBS, training_batch_size=batch)
+  stop = []
+
+  def drain():
+    try:
+      while True:
+        slot, _ = learner_loop.assembled_batch(host.assembler)
+        host.assembler.release(slot)
+        stop.append(1)
+    except utils.QueueClosedError:
+      return
+  th = threading.Thread(target=drain, daemon=True); th.start()
+  rng = np.random.default_rng(7)
+  run_ids = rng.integers(1, 2**40, num_envs)
+  groups = [np.arange(g * N, (g + 1) * N, dtype=np.int32) for g in range(num_envs // N)]
+  obs = [torch.from_numpy(rng.integers(0, 256, (N,) + OBS, dtype=np.uint8)).pin_memory().numpy() for _ in groups]
+  zeros = np.zeros(N, np.float32)
+
+  def one(i):
+    g = i % len(groups)
+    ids = groups[g]
+    env = utils.EnvOutput(rng.normal(size=N).astype(np.float32), rng.random(N) < 0.01, obs[g],
+                          np.zeros(N, bool), np.full(N, i, np.int32))
+    return host.inference(ids, run_ids[ids], env, zeros)
+  for i in range(warmup):
+    one(i)
+  torch.cuda.synchronize()
+  n0 = _lib.launch_count()
+  lat = []
+  t0 = time.perf_counter()
+  for i in range(iters):
+    t1 = time.perf_counter()
+    one(warmup + i)
+    lat.append(time.perf_counter() - t1)
+  dt = time.perf_counter() - t0
+  launches = (_lib.launch_count() - n0) / iters
+  host.assembler.close()
+  lat.sort()
+  h2d = N * (28224 + 4 + 1 + 1 + 4) + N * 4 + N * 8
+  return {
+      'what': 'central inference step (agents/vtrace/learner.py:349-407): host batch -> H2D -> gather prev '
+              'action/state -> T=1 ImpalaDeep forward (conv_mode %s) -> sample -> scatter + unroll-store append '
+              '-> actions D2H; public API InferenceHost.inference, no RPC transport' % agent.conv_mode,
+      'inference_batch_size': N, 'num_envs': num_envs, 'iters': iters,
+      'inferences_per_sec': N * iters / dt, 'us_per_batch_mean': dt / iters * 1e6,
+      'us_per_batch_p50': lat[len(lat) // 2] * 1e6, 'us_per_batch_p99': lat[int(len(lat) * 0.99)] * 1e6,
+      'library_launches_per_batch': launches, 'h2d_bytes_per_batch': h2d, 'd2h_bytes_per_batch': N * 8,
+      'training_batches_assembled': len(stop),
+      'bound': 'latency: 64 frames x 0.11 GFLOP = 7 GFLOP and 1.8 MB of frames per batch are ~10 us of '
+               'tensor / HBM time; the step is a chain of ~40 dependent small launches plus host glue',
+  }
+
+
+def r2d2_cpu_throughput(B, steps, warmup, burn_in=40, unroll=100):
+  """The reference's R2D2 learner step (oracle port, torch-CPU fp32) on a bounded sample."""
+  import torch
+  from oracle import r2d2_learner_oracle as RL
+  torch.set_num_threads(min(32, os.cpu_count() or 1))
+  T = burn_in + unroll + 1
+  lr = RL.CpuR2D2Learner(A, (84, 84, 1), 4, burn_in=burn_in, lr=0.00048, eps=1e-3)
+  b = RL.synthetic_replay_batch(T, B, A, (84, 84, 1), seed=1234)
+  for _ in range(warmup):
+    lr.step(b)
+  t0 = time.perf_counter()
+  for _ in range(steps):
+    lr.step(b)
+  dt = (time.perf_counter() - t0) / max(steps, 1)
+  return dict(value=B * unroll / dt, ms_per_step=dt * 1e3, cores=torch.get_num_threads(),
+              sample='%d steps of B=%d sampled unrolls x (burn-in %d + %d + 1) after %d warm-up; torch-CPU fp32 '
+                     'oracle port of agents/r2d2/learner.py:333-386,581-634, %d threads' %
+                     (steps, B, burn_in, unroll, warmup, torch.get_num_threads()))
+
+
+def run_r2d2(args):
+  """BASELINE configs[4]: R2D2 LSTM agent, synthetic replay, n-step targets, 1 x B200.  A step =
+  insert `batch/replay_ratio` new unrolls into the prioritized replay -> sample `batch` unrolls by
+  priority (+ importance weights) -> burn-in + suffix unrolls of the online and target networks ->
+  n-step double-DQN loss -> backward -> global-norm clip -> Adam -> priority write-back
+  (reference agents/r2d2/learner.py:389-467,581-634,856-885)."""
+  import numpy as np
+  import torch
+  from seed_rl_b200 import _lib
+  from seed_rl_b200.agents.r2d2 import learner
+  from seed_rl_b200.atari import networks
+  from seed_rl_b200.common import optimizers, utils
+  if args.impl == 'reference':
+    if int(os.environ.get('RANK', '0')) != 0:
+      return
+    r = r2d2_cpu_throughput(4, max(1, min(args.steps, 3)), 1)
+    return emit({'impl': 'reference', 'metric': R2D2_METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': args.gpus,
+                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': r['ms_per_step'],
+                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                 'data': 'synthetic', 'config': r2d2_config(args), 'gpu_launches': 0,
+                 'cpu_baseline': {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
+                                  'sample': r['sample']},
+                 'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}})
+  torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+  st = learner.default_settings(batch_size=args.batch)
+  obs, S = (84, 84, 1), 4
+  T = st.burn_in + st.unroll_length + 1
+  B, n_ins = st.batch_size, learner.get_replay_insertion_batch_size(st)
+  agent = networks.DuelingLSTMDQNNet(A, obs, S, seed=0)
+  target = networks.DuelingLSTMDQNNet(A, obs, S, seed=0)
+  step = learner.R2D2LearnerStep(agent, target, optimizers.Adam(0.00048, epsilon=1e-3), settings=st)
+  TS = utils.TensorSpec
+  agent_state_specs = networks.AgentState((TS([512], 'float32', 'h'), TS([512], 'float32', 'c')),
+                                          TS([84 * 84], 'int32', 'frames'))
+  env_specs = utils.EnvOutput(TS([T], 'float32', 'reward'), TS([T], 'bool', 'done'),
+                              TS([T, 84, 84, 1], 'uint8', 'observation'), TS([T], 'bool', 'abandoned'),
+                              TS([T], 'int32', 'episode_step'))
+  unroll_specs = learner.Unroll(agent_state_specs, TS([], 'float32', 'priority'), TS([T], 'int32', 'prev_actions'),
+                                env_specs, learner.AgentOutput(TS([T], 'int32', 'action'), TS([T, A], 'float32', 'q')))
+  replay = utils.PrioritizedReplay(st.replay_buffer_size, unroll_specs, st.importance_sampling_exponent)
+  feeder = learner.ReplayFeeder(replay, st, generator=torch.Generator(device='cuda').manual_seed(1))
+  rng = np.random.default_rng(1234)
+
+  def host_unrolls(n):       # what the inference side would enqueue: env-major [n, T, ...], pinned
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    return learner.Unroll(
+        networks.AgentState((pin(np.zeros((n, 512), np.float32)), pin(np.zeros((n, 512), np.float32))),
+                            pin(np.zeros((n, 84 * 84), np.int32))),
+        pin((rng.random(n) + 0.1).astype(np.float32)), pin(rng.integers(0, A, (n, T)).astype(np.int32)),
+        utils.EnvOutput(pin(rng.normal(size=(n, T)).astype(np.float32)), pin(rng.random((n, T)) < 0.01),
+                        pin(rng.integers(0, 256, (n, T) + obs, dtype=np.uint8)), pin(np.zeros((n, T), bool)),
+                        pin(np.zeros((n, T), np.int32))),
+        learner.AgentOutput(pin(rng.integers(0, A, (n, T)).astype(np.int32)),
+                            pin(rng.normal(size=(n, T, A)).astype(np.float32))))
+  host_new = host_unrolls(n_ins)
+  h2d = sum(t.numel() * t.element_size() for t in utils.flatten(host_new))
+  dev_new = utils.map_structure(lambda t: t.cuda(), host_new)
+  while not feeder.ready() or replay.num_inserted < st.replay_buffer_size:
+    feeder.insert(dev_new)
+
+  def one_step(from_host):
+    new = utils.map_structure(lambda t: t.cuda(non_blocking=True), host_new) if from_host else dev_new
+    feeder.insert(new)
+    sampled = feeder.sample()
+    loss, priorities, indices, norm = step.minimize(sampled)
+    feeder.update_priorities(indices, priorities)
+    return loss
+
+  def timed(fn, k):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(k):
+      fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / k
+  for _ in range(max(args.warmup, 8)):      # the caching allocator settles after a few sample/gather shapes
+    one_step(False)
+  sampler = ClockSampler(torch.cuda.current_device())
+  n0 = _lib.launch_count()
+  ms = timed(lambda: one_step(False), args.steps)
+  launches = (_lib.launch_count() - n0) // args.steps
+  agent.check_errors()
+  clocks = sampler.stop()
+  ms_e2e = timed(lambda: float(one_step(True)), args.steps)
+  frames = B * st.unroll_length
+  line = {'metric': R2D2_METRIC, 'value': frames / (ms * 1e-3), 'unit': UNIT, 'n_gpus': 1, 'steps': args.steps,
+          'warmup': max(args.warmup, 8), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+          'vs_baseline': None, 'dtype': 'bf16x3 (fp32-faithful tensor-core contraction), f32 elsewhere',
+          'data': 'synthetic', 'config': r2d2_config(args), 'clocks': clocks,
+          'e2e': {'value': frames / (ms_e2e * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e,
+                  'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
+                  'api': 'ReplayFeeder.insert/sample/update_priorities + R2D2LearnerStep.minimize; the %d new '
+                         'unrolls of every step come from pinned host memory' % n_ins},
+          'gpu_launches': int(launches * args.steps), 'gpu_launches_per_step': int(launches), 'impl': 'b200'}
+  if not args.no_extras:
+    import ctypes
+    L = _lib.lib()
+    ncat = L.seedrl_profile_num_categories()
+    ms_c = (ctypes.c_double * ncat)(); n_c = (ctypes.c_uint64 * ncat)()
+    _lib.check(L.seedrl_profile_begin(_lib.stream_ptr()))
+    one_step(False)
+    _lib.check(L.seedrl_profile_end(ms_c, n_c))
+    line['kernel_time_ms_per_step'] = {L.seedrl_profile_category_name(i).decode(): round(ms_c[i], 4) for i in range(ncat)}
+    line['kernel_time_note'] = ('conv3x3_fwd = im2col, conv3x3_dgrad = col2im, sgemm = every GEMM incl. the three '
+                                'convolutions (tcgen05 bf16x3), lstm_pointwise = the persistent LSTM(512) recurrences')
+    # roofline of the dominant family: the tcgen05 GEMMs, against the dense bf16 peak x 1/3 (bf16x3)
+    peaks = {}
+    try:
+      peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+      pass
+    fl = r2d2_gemm_flops(T, B, st.burn_in)
+    tf = fl * 3 / (ms_c[[L.seedrl_profile_category_name(i).decode() for i in range(ncat)].index('sgemm')] * 1e-3) / 1e12
+    peak = float(peaks.get('bf16_tflops_sustained', 1465.2))
+    line['roofline'] = {'kernel': 'gemm_tc_kernel (all contractions of the step, bf16x3: 3 MMAs per fp32 product)',
+                        'bound': 'tensor', 'achieved': tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': tf / peak,
+                        'traffic': None, 'fp32_equivalent_flops_per_step': fl}
+    r = r2d2_cpu_throughput(4, 2, 1)
+    line['cpu_baseline'] = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
+                            'sample': r['sample'], 'ms_per_step': r['ms_per_step']}
+  emit(line)
+
+
+R2D2_METRIC = ('learner env-frames/sec (R2D2 learner step, device-timed; frames = batch_size x unroll_length) on '
+               'synthetic prioritized replay @1 B200')
+
+
+def r2d2_config(args):
+  return {'workload': 'R2D2 learner step (BASELINE configs[4]): DuelingLSTMDQNNet 84x84x1 frames, stack 4, batch %d '
+                      'sampled unrolls x (burn-in 40 + unroll 100 + 1), replay 100 unrolls, priority exponent 0.9, '
+                      'n_steps 5, gamma 0.997, clip_norm 40, Adam lr 4.8e-4 eps 1e-3 (agents/r2d2/learner.py:43-92, '
+                      'atari/r2d2_main.py:36-51)' % args.batch,
+          'batch_size': args.batch, 'unroll_length': 100, 'burn_in': 40, 'num_actions': A, 'parallelism': 'dp1',
+          'l2': 'per-step activations (>10 GB) exceed the 126 MB L2; no explicit flush'}
+
+
+def r2d2_gemm_flops(T, B, burn_in):
+  """2*MAC of every contraction of one step: online + target forward over all T rows, backward
+  (2x) of the online suffix."""
+  per_frame = (20 * 20 * 256 * 32 + 9 * 9 * 512 * 64 + 7 * 7 * 576 * 64 + 3136 * 512 + (512 + 1 + A) * 2048 +
+               512 * 2048 + 2 * 512 * 512 + 512 * (1 + A))
+  fwd = 2 * T * B * per_frame
+  bwd = 2 * (T - burn_in) * B * per_frame
+  return 2 * (fwd + bwd)
+
+
 _JSON_FD = None
 
 
@@ -250,6 +486,8 @@ def main():
   sys.stdout.flush()
   _JSON_FD = os.dup(1)
   os.dup2(2, 1)
+  if args.agent == 'r2d2':
+    return run_r2d2(args)
   if args.impl == 'reference':
     return run_reference(args)
 
@@ -510,6 +748,12 @@ def main():
       r = cpu_learner_throughput(args.net, T, args.cpu_batch, 5, 2)
       line['cpu_baseline'] = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port',
                               'sample': r['sample'], 'ms_per_step': r['ms_per_step']}
+
+    if rank == 0 and world == 1 and args.net == 'deep':
+      try:
+        line['inference_path'] = inference_path_bench(agent)
+      except Exception as exc:        # pylint: disable=broad-except
+        line['inference_path'] = {'unavailable': repr(exc)[:300]}
 
     if rank == 0 and world == 1 and args.net == 'deep' and args.conv != 'simt':
       # ---- the most time-consuming single kernel instance of the step, alone: the 16->16 conv

@@ -238,6 +238,29 @@ int seedrl_store_gather_field(uint8_t* state, const int32_t* completed_ids,
                               int n_completed, int full_length, size_t row_bytes,
                               int overlap, int time_major, uint8_t* unrolls,
                               seedrl_stream_t stream);
+/* (a6) Every per-environment row move of one inference batch in ONE launch: the reads of the
+ * previous action / agent state (Aggregator.read, common/utils.py:504-516), their write-back
+ * (Aggregator.replace, :519-543) and the append of all fields of the step to the unroll store
+ * (UnrollStore.append, :187-190) -- agents/vtrace/learner.py:381-383,394-403 issues one TF op per
+ * table.  mode 0 gather rows[j] = table[env_ids[j]]; 1 scatter; 2 append at index[env].  The
+ * caller guarantees unique env_ids for scatter/append (the reference asserts it, :533-540). */
+#define SEEDRL_MAX_ROW_JOBS 16
+typedef struct seedrl_row_job {
+  void* table;          /* [num_envs(, full_length), row_bytes] */
+  void* rows;           /* [n, row_bytes] */
+  size_t row_bytes;
+  int32_t mode;
+  int32_t full_length;  /* append only */
+} seedrl_row_job;
+int seedrl_rows_multi(const seedrl_row_job* jobs, int njobs, const int32_t* env_ids, int n,
+                      const int32_t* index, seedrl_stream_t stream);
+/* Zero-copy minibatch assembly (replaces the queue-element copy, tf.stack and
+ * make_time_major of agents/vtrace/learner.py:418-432): like seedrl_store_gather_field with
+ * time_major = 1, but unroll i lands in column col0 + i of the caller's batch tensor
+ * [full_length, batch_cols, row_bytes]. */
+int seedrl_store_gather_field_into(uint8_t* state, const int32_t* completed_ids, int n_completed,
+                                   int full_length, size_t row_bytes, int overlap, uint8_t* batch,
+                                   int batch_cols, int col0, seedrl_stream_t stream);
 int seedrl_store_finish(int32_t* index, const int32_t* completed_ids,
                         int n_completed, int overlap, seedrl_stream_t stream);
 int seedrl_store_reset(uint8_t* state, int32_t* index, const int32_t* env_ids,
@@ -309,7 +332,7 @@ int seedrl_profile_end(double* ms_per_category, uint64_t* launches_per_category)
 typedef struct seedrl_r2d2_net seedrl_r2d2_net;
 int seedrl_r2d2_net_create(int num_actions, int obs_h, int obs_w, int channels, seedrl_r2d2_net** out);
 void seedrl_r2d2_net_destroy(seedrl_r2d2_net* net);
-int seedrl_r2d2_net_num_param_tensors(const seedrl_r2d2_net* net);      /* 19 */
+int seedrl_r2d2_net_num_param_tensors(const seedrl_r2d2_net* net);      /* 18 */
 size_t seedrl_r2d2_net_num_params(const seedrl_r2d2_net* net);
 size_t seedrl_r2d2_net_arena_floats(const seedrl_r2d2_net* net);
 int seedrl_r2d2_net_set_mode(seedrl_r2d2_net* net, int mode);
@@ -384,6 +407,9 @@ int seedrl_debug_set_wgrad_chunk(int kc);
 /* Output positions per tile of the tensor-core forward / data-gradient kernel: the largest
  * of 512 / 256 / 128 not above `mt` that keeps two CTAs per SM is used (default 512). */
 int seedrl_debug_set_conv_tile(int mt);
+/* 1 = conv_mode 3 keeps the dense first-layer backward (pool backward + full-resolution weight
+ * gradient) instead of csrc/conv_first.cu's gather from the pooled gradient (A/B parity tests). */
+int seedrl_debug_set_first_layer_dense(int on);
 int seedrl_debug_conv3x3_wgrad(int cin, int cout, int in_mode, int N, int H, int W,
                                const void* x, const float* dy, float* dw, float* db,
                                float* partial, size_t partial_bytes,

@@ -31,6 +31,26 @@ class LossConfig(ctypes.Structure):
               ('entropy_cost_adjustment_speed', c_float)]
 
 
+class RowJob(ctypes.Structure):
+  _fields_ = [('table', ctypes.c_void_p), ('rows', ctypes.c_void_p), ('row_bytes', ctypes.c_size_t),
+              ('mode', ctypes.c_int32), ('full_length', ctypes.c_int32)]
+
+
+ROW_GATHER, ROW_SCATTER, ROW_APPEND = 0, 1, 2
+
+
+def rows_multi(jobs, env_ids_i32, index=None):
+  """jobs: list of (table tensor, rows tensor, mode).  One launch (seedrl_rows_multi)."""
+  n = int(env_ids_i32.numel())
+  arr = (RowJob * len(jobs))()
+  for k, (table, rows, mode) in enumerate(jobs):
+    rb = (table[0, 0] if mode == ROW_APPEND else table[0]).numel() * table.element_size()
+    if rows.numel() * rows.element_size() != n * rb or rows.dtype != table.dtype or not rows.is_contiguous():
+      raise ValueError('rows_multi: rows do not match the table (job %d)' % k)
+    arr[k] = RowJob(table.data_ptr(), rows.data_ptr(), rb, mode, table.shape[1] if mode == ROW_APPEND else 0)
+  check(lib().seedrl_rows_multi(arr, len(jobs), ptr(env_ids_i32), n, ptr(index), stream_ptr()))
+
+
 class NetConfig(ctypes.Structure):
   """struct seedrl_net_config."""
   _fields_ = [('net', ctypes.c_int32), ('num_actions', ctypes.c_int32),
@@ -78,6 +98,8 @@ SIGNATURES = {
     'seedrl_store_append_field': (c_int, [P, P, P, c_int, c_int, c_size_t, P, P]),
     'seedrl_store_advance': (c_int, [P, P, c_int, c_int, P, P, P]),
     'seedrl_store_gather_field': (c_int, [P, P, c_int, c_int, c_size_t, c_int, c_int, P, P]),
+    'seedrl_rows_multi': (c_int, [P, c_int, P, c_int, P, P]),
+    'seedrl_store_gather_field_into': (c_int, [P, P, c_int, c_int, c_size_t, c_int, P, c_int, c_int, P]),
     'seedrl_store_finish': (c_int, [P, P, c_int, c_int, P]),
     'seedrl_store_reset': (c_int, [P, P, P, c_int, c_int, c_size_t, c_int, P]),
     'seedrl_batcher_create':
@@ -133,6 +155,7 @@ SIGNATURES = {
     'seedrl_debug_set_loss_stream': (c_int, [c_int]),
     'seedrl_debug_set_wgrad_chunk': (c_int, [c_int]),
     'seedrl_debug_set_conv_tile': (c_int, [c_int]),
+    'seedrl_debug_set_first_layer_dense': (c_int, [c_int]),
     'seedrl_debug_conv3x3_wgrad_tc':
         (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, c_size_t, P, P]),
     'seedrl_debug_conv3x3_wgrad':

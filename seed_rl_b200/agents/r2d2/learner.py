@@ -33,8 +33,7 @@ def _define(fn, name, default, help_):
   (batch_size, unroll_length, discounting ...).  When both mirrors are imported into one
   process (the test-suite does) the first definition stands; R2D2 code therefore never reads
   those flags directly but goes through `settings_from_flags` / `default_settings`."""
-  if name not in FLAGS:
-    fn(name, default, help_)
+  common_flags.define_once(fn, name, default, help_)
 
 
 _define(flags.DEFINE_integer, 'save_checkpoint_secs', 1800, 'Checkpoint save period in seconds.')

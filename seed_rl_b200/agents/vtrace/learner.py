@@ -22,34 +22,34 @@ from seed_rl_b200.common import common_flags  # pylint: disable=unused-import
 from seed_rl_b200.common import utils
 
 # Training.
-flags.DEFINE_integer('save_checkpoint_secs', 1800, 'Checkpoint save period in seconds.')
-flags.DEFINE_integer('total_environment_frames', int(1e9),
+common_flags.define_once(flags.DEFINE_integer, 'save_checkpoint_secs', 1800, 'Checkpoint save period in seconds.')
+common_flags.define_once(flags.DEFINE_integer, 'total_environment_frames', int(1e9),
                      'Total environment frames to train for.')
-flags.DEFINE_integer('batch_size', 32, 'Batch size for training.')
-flags.DEFINE_integer('inference_batch_size', -1, 'Batch size for inference, -1 for auto-tune.')
-flags.DEFINE_integer('unroll_length', 100, 'Unroll length in agent steps.')
-flags.DEFINE_integer('num_training_tpus', 1, 'Unused on B200 (kept for flag compatibility).')
-flags.DEFINE_string('init_checkpoint', None,
+common_flags.define_once(flags.DEFINE_integer, 'batch_size', 32, 'Batch size for training.')
+common_flags.define_once(flags.DEFINE_integer, 'inference_batch_size', -1, 'Batch size for inference, -1 for auto-tune.')
+common_flags.define_once(flags.DEFINE_integer, 'unroll_length', 100, 'Unroll length in agent steps.')
+common_flags.define_once(flags.DEFINE_integer, 'num_training_tpus', 1, 'Unused on B200 (kept for flag compatibility).')
+common_flags.define_once(flags.DEFINE_string, 'init_checkpoint', None,
                     'Path to the checkpoint used to initialize the agent.')
 # Loss settings.
-flags.DEFINE_float('entropy_cost', 0.00025, 'Entropy cost/multiplier.')
-flags.DEFINE_float('target_entropy', None, 'If not None, the entropy cost is '
+common_flags.define_once(flags.DEFINE_float, 'entropy_cost', 0.00025, 'Entropy cost/multiplier.')
+common_flags.define_once(flags.DEFINE_float, 'target_entropy', None, 'If not None, the entropy cost is '
                    'automatically adjusted to reach the desired entropy level.')
-flags.DEFINE_float('entropy_cost_adjustment_speed', 10., 'Controls how fast '
+common_flags.define_once(flags.DEFINE_float, 'entropy_cost_adjustment_speed', 10., 'Controls how fast '
                    'the entropy cost coefficient is adjusted.')
-flags.DEFINE_float('baseline_cost', .5, 'Baseline cost/multiplier.')
-flags.DEFINE_float('kl_cost', 0., 'KL(old_policy|new_policy) loss multiplier.')
-flags.DEFINE_float('discounting', .99, 'Discounting factor.')
-flags.DEFINE_float('lambda_', 1., 'Lambda.')
-flags.DEFINE_float('max_abs_reward', 0., 'Maximum absolute reward when calculating loss.'
+common_flags.define_once(flags.DEFINE_float, 'baseline_cost', .5, 'Baseline cost/multiplier.')
+common_flags.define_once(flags.DEFINE_float, 'kl_cost', 0., 'KL(old_policy|new_policy) loss multiplier.')
+common_flags.define_once(flags.DEFINE_float, 'discounting', .99, 'Discounting factor.')
+common_flags.define_once(flags.DEFINE_float, 'lambda_', 1., 'Lambda.')
+common_flags.define_once(flags.DEFINE_float, 'max_abs_reward', 0., 'Maximum absolute reward when calculating loss.'
                    'Use 0. to disable clipping.')
 # Logging
-flags.DEFINE_integer('log_batch_frequency', 100, 'We average that many batches '
+common_flags.define_once(flags.DEFINE_integer, 'log_batch_frequency', 100, 'We average that many batches '
                      'before logging batch statistics like entropy.')
-flags.DEFINE_integer('log_episode_frequency', 1, 'We average that many episodes'
+common_flags.define_once(flags.DEFINE_integer, 'log_episode_frequency', 1, 'We average that many episodes'
                      ' before logging average episode return and length.')
 # B200 additions
-flags.DEFINE_enum('grad_reduce', 'sum', ['sum', 'mean'],
+common_flags.define_once(flags.DEFINE_enum, 'grad_reduce', 'sum', ['sum', 'mean'],
                   'Cross-replica gradient reduction. The reference SUMs '
                   '(tests/utils_test.py:609-650).')
 

@@ -21,6 +21,7 @@ from absl import logging
 import numpy as np
 import torch
 
+from seed_rl_b200 import _lib
 from seed_rl_b200.agents.vtrace import learner as learner_lib
 from seed_rl_b200.common import utils
 from seed_rl_b200.common.parametric_distribution import get_parametric_distribution_for_action_space
@@ -35,7 +36,11 @@ class InferenceHost(object):
   """Everything `create_host` builds in the reference (learner.py:314-413) for one GPU."""
 
   def __init__(self, agent, num_envs, unroll_length, inference_batch_size, obs_shape,
-               num_action_repeats=1, device='cuda', info_queue=None):
+               num_action_repeats=1, device='cuda', info_queue=None, training_batch_size=None):
+    """training_batch_size: when given, completed unrolls are gathered straight into the columns
+    of preallocated time-major training batches (`self.assembler`, utils.BatchAssembler: zero-copy
+    minibatch assembly); otherwise they go through the reference's capacity-1 `unroll_queue` of
+    single unrolls and `dequeue_batch` stacks them."""
     self.agent = agent
     self.device = torch.device(device)
     self.N = inference_batch_size
@@ -63,6 +68,11 @@ class InferenceHost(object):
     self.actions = utils.Aggregator(num_envs, action_specs, 'actions', device)
     self.unroll_specs = Unroll(agent_state_specs, *self.store.unroll_specs)
     self.unroll_queue = utils.StructuredFIFOQueue(1, self.unroll_specs)      # capacity 1, :336
+    self.assembler = None
+    if training_batch_size:
+      self.assembler = utils.BatchAssembler((action_specs, self.env_output_specs, agent_output_specs),
+                                            agent_state_specs, unroll_length + 1, training_batch_size,
+                                            slots=2, device=device)
     self.info_queue = info_queue
     N = self.N
     self.inference_specs = (
@@ -108,16 +118,35 @@ class InferenceHost(object):
       self.env_infos[0][env_ids] += self.num_action_repeats
       # Inference (:381-390): one H2D copy per field, T=1 forward on the GPU.
       ids_dev = torch.as_tensor(env_ids.astype(np.int64)).to(self.device, non_blocking=True)
+      ids32 = ids_dev.to(torch.int32)
       env_dev = utils.EnvOutput(*(torch.as_tensor(np.asarray(x)).to(self.device, non_blocking=True)
                                   for x in env_outputs))
-      prev_actions = self.actions.read(ids_dev)
-      prev_states = self.agent_states.read(ids_dev)
+      # previous action + recurrent state of these environments: ONE gather launch (:381-383)
+      n = int(ids32.numel())
+      prev_actions = torch.empty([n], dtype=torch.int64, device=self.device)
+      prev_states = tuple(torch.empty([n, networks.LSTM_UNITS], dtype=torch.float32, device=self.device)
+                          for _ in range(2))
+      _lib.rows_multi([(self.actions._state[0], prev_actions, _lib.ROW_GATHER),
+                       (self.agent_states._state[0], prev_states[0], _lib.ROW_GATHER),
+                       (self.agent_states._state[1], prev_states[1], _lib.ROW_GATHER)], ids32)
       agent_outputs, curr_states = self.agent(prev_actions, env_dev, prev_states, is_training=False)
       # Append to the unroll store, enqueue completed unrolls (:394-399).
-      completed_ids, unrolls = self.store.append(env_ids, (prev_actions, env_dev, agent_outputs),
-                                                 check_duplicates=True)
-      n_done = int(completed_ids.numel())
       pending = []
+      if self.assembler is not None:
+        def on_placed(slot, col0, ids):
+          first = self.first_agent_states.read(ids.to(torch.int64))
+          for dst, src in zip(self.assembler._states[slot], first):
+            dst[col0:col0 + int(ids.numel())].copy_(src)
+        completed_ids, placed = self.store.append(env_ids, (prev_actions, env_dev, agent_outputs),
+                                                  check_duplicates=True, into=self.assembler,
+                                                  on_placed=on_placed)
+        n_done = 0
+        if placed:
+          self.first_agent_states.replace(completed_ids, self.agent_states.read(completed_ids))
+      else:
+        completed_ids, unrolls = self.store.append(env_ids, (prev_actions, env_dev, agent_outputs),
+                                                   check_duplicates=True)
+        n_done = int(completed_ids.numel())
       if n_done:
         first = self.first_agent_states.read(completed_ids)
         flat = utils.flatten(unrolls)
@@ -126,8 +155,10 @@ class InferenceHost(object):
           pending.append(Unroll((first[0][i], first[1][i]), *u))
         self.first_agent_states.replace(completed_ids, self.agent_states.read(completed_ids))
       # Update current state (:402-403) and return the actions (:405).
-      self.agent_states.replace(ids_dev, curr_states)
-      self.actions.replace(ids_dev, agent_outputs.action)
+      # (ids are unique: UnrollStore.append checked them)  ONE scatter launch
+      _lib.rows_multi([(self.agent_states._state[0], curr_states[0].contiguous(), _lib.ROW_SCATTER),
+                       (self.agent_states._state[1], curr_states[1].contiguous(), _lib.ROW_SCATTER),
+                       (self.actions._state[0], agent_outputs.action.contiguous(), _lib.ROW_SCATTER)], ids32)
       out = agent_outputs.action.cpu()       # D2H + sync of this stream
     # The unrolls were produced on self.stream, which the blocking copy above has drained: only
     # now are they handed to the learner thread (which consumes them on another stream).
@@ -155,10 +186,69 @@ def dequeue_batch(unroll_queue, batch_size):
   return Unroll(state, stack('prev_actions'), stack('env_outputs'), stack('agent_outputs'))
 
 
+def save_checkpoint(path, agent, optimizer, extra=None):
+  """tf.train.CheckpointManager.save analogue (reference learner.py:283-296,470-476): one
+  `torch.save` blob {agent: flat fp32 arena + tensor table, optimizer: Adam m / v / iterations}
+  written atomically.  NOT interchangeable with the reference's tf.train.Checkpoint files (no
+  TensorFlow here); `named_parameters()` gives the Keras-layout tensors by name for conversion."""
+  blob = {'agent': agent.state_dict(), 'optimizer': optimizer.state_dict(), 'format': 'seed_rl_b200/1'}
+  if extra:
+    blob.update(extra)
+  torch.save(blob, path + '.tmp')
+  os.replace(path + '.tmp', path)
+
+
+def restore_checkpoint(path, agent, optimizer):
+  """ckpt.restore(...).assert_consumed() analogue: raises on a tensor-table mismatch."""
+  d = torch.load(path, map_location='cpu', weights_only=False)
+  info = d['agent'].get('param_info')
+  if info is not None and [tuple(x) for x in info] != [tuple(x) for x in agent.param_info]:
+    raise ValueError('checkpoint %s was written by a different network (tensor table mismatch)' % path)
+  agent.load_state_dict(d['agent'])
+  optimizer.load_state_dict(d['optimizer'], device=str(agent.device))
+  return d
+
+
+def rank_server_address(address, rank):
+  """One server per replica (reference: one per host, learner.py:339-347): replica r binds the
+  flag's address with its port (or unix-socket path) offset by r."""
+  if rank == 0:
+    return address
+  if address.startswith('unix:'):
+    return '%s.%d' % (address, rank)
+  host, _, port = address.rpartition(':')
+  return '%s:%d' % (host, int(port) + rank)
+
+
+def init_replicas():
+  """torchrun starts one learner process per GPU; returns (rank, world)."""
+  import torch.distributed as td
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  if world > 1 and not td.is_initialized():
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if torch.cuda.is_available():
+      torch.cuda.set_device(local)
+      td.init_process_group('nccl', device_id=torch.device('cuda', local))
+    else:
+      td.init_process_group('gloo')
+  return rank, world
+
+
+def assembled_batch(assembler):
+  """The zero-copy counterpart of `dequeue_batch`: the next full time-major batch of the
+  assembler as an `Unroll` of views (no copy).  Returns (slot, Unroll); call
+  assembler.release(slot) after the step that consumes it has been enqueued."""
+  slot, state, (prev_actions, env_outputs, agent_outputs) = assembler.get()
+  return slot, Unroll(tuple(state), prev_actions, utils.EnvOutput(*env_outputs),
+                      networks.AgentOutput(*agent_outputs))
+
+
 def learner_loop(create_env_fn, create_agent_fn, create_optimizer_fn):
-  """reference learner.py:170-483 (single replica)."""
+  """reference learner.py:170-483 (one replica per process / GPU)."""
   logging.info('Starting learner loop')
   utils.validate_learner_config(FLAGS)
+  rank, world = init_replicas()
   env = create_env_fn(0, FLAGS)
   dist = get_parametric_distribution_for_action_space(env.action_space)
   agent = create_agent_fn(env.action_space, env.observation_space, dist)
@@ -168,57 +258,68 @@ def learner_loop(create_env_fn, create_agent_fn, create_optimizer_fn):
   final_iteration = int(math.ceil(FLAGS.total_environment_frames / iter_frame_ratio))
   optimizer, learning_rate_fn = create_optimizer_fn(final_iteration)
   settings = learner_lib.loss_settings_from_flags()
-  step = learner_lib.LearnerStep(agent, optimizer, dist, settings, grad_reduce=FLAGS.grad_reduce)
+  # summaries + periodic progress export (learner.py:236-237,280,286,447-465)
+  os.makedirs(FLAGS.logdir, exist_ok=True)
+  summary_writer = utils.SummaryWriter(FLAGS.logdir) if rank == 0 else None
+  logger = utils.ProgressLogger(summary_writer=summary_writer,
+                                starting_step=optimizer.iterations * iter_frame_ratio)
+  step = learner_lib.LearnerStep(agent, optimizer, dist, settings, logger=logger, grad_reduce=FLAGS.grad_reduce)
 
   ckpt_path = os.path.join(FLAGS.logdir, 'ckpt.pt')
-  os.makedirs(FLAGS.logdir, exist_ok=True)
   init = FLAGS.init_checkpoint or (ckpt_path if os.path.exists(ckpt_path) else None)
   if init:                                                                 # :286-296
     logging.info('Restoring checkpoint: %s', init)
-    d = torch.load(init, map_location='cpu')
-    agent.load_state_dict(d['agent'])
-    optimizer.load_state_dict(d['optimizer'])
+    restore_checkpoint(init, agent, optimizer)
+    logger.reset(summary_writer, optimizer.iterations * iter_frame_ratio)
 
   def save():
-    torch.save({'agent': agent.state_dict(), 'optimizer': optimizer.state_dict()}, ckpt_path + '.tmp')
-    os.replace(ckpt_path + '.tmp', ckpt_path)
+    if rank == 0:                      # replicas are bit-identical; one writer, no os.replace race
+      save_checkpoint(ckpt_path, agent, optimizer)
 
   info_specs = (utils.TensorSpec([], 'int64', 'episode_num_frames'),
                 utils.TensorSpec([], 'float32', 'episode_returns'),
                 utils.TensorSpec([], 'float32', 'episode_raw_returns'))
   info_queue = utils.StructuredFIFOQueue(-1, info_specs)
-  world = step.world
+  assert step.world == world
+  per_replica = FLAGS.batch_size // world                                   # :422
   host = InferenceHost(agent, FLAGS.num_envs, FLAGS.unroll_length, FLAGS.inference_batch_size,
-                       env.observation_space.shape, FLAGS.num_action_repeats, info_queue=info_queue)
-  server = grpc.Server([FLAGS.server_address])
+                       env.observation_space.shape, FLAGS.num_action_repeats, info_queue=info_queue,
+                       training_batch_size=per_replica)
+  server = grpc.Server([rank_server_address(FLAGS.server_address, rank)])
   server.bind(host.inference)
   server.start()
 
+  def additional_logs():                                                    # :447-463
+    if summary_writer:
+      summary_writer.scalar('learning_rate', learning_rate_fn(optimizer.iterations))
+    n = info_queue.size()
+    n -= n % FLAGS.log_episode_frequency
+    if n:
+      stats = info_queue.dequeue_many(n)
+      for key, values in zip(('episode_num_frames', 'episode_return', 'episode_raw_return'), stats):
+        for chunk in torch.split(values.float(), FLAGS.log_episode_frequency):
+          if summary_writer:
+            summary_writer.scalar(key, float(chunk.mean()))
+      for fr, ret, raw in zip(*stats):
+        logging.info('Return: %f Raw return: %f Frames: %i', float(ret), float(raw), int(fr))
+
+  logger.start(additional_logs)
   last_ckpt_time = 0
-  last_log, last_frames = time.time(), optimizer.iterations * iter_frame_ratio
-  per_replica = FLAGS.batch_size // world                                   # :422
   try:
     while optimizer.iterations < final_iteration:                           # :467-476
       now = time.time()
       if now - last_ckpt_time >= FLAGS.save_checkpoint_secs:
         save()
         last_ckpt_time = now
-      batch = dequeue_batch(host.unroll_queue, per_replica)
-      loss, logs = step.minimize(batch)
-      if optimizer.iterations % FLAGS.log_batch_frequency == 0:
-        frames = optimizer.iterations * iter_frame_ratio
-        dt = time.time() - last_log
-        logging.info('step %d  speed/steps_per_sec %.1f  %s', optimizer.iterations,
-                     (frames - last_frames) / max(dt, 1e-9),
-                     {k: round(float(v), 5) for k, v in logs})
-        last_log, last_frames = time.time(), frames
-        n = info_queue.size()
-        n -= n % FLAGS.log_episode_frequency
-        if n:
-          fr, ret, raw = info_queue.dequeue_many(n)
-          logging.info('episode_return %.3f raw %.3f frames %.1f', float(ret.float().mean()),
-                       float(raw.float().mean()), float(fr.float().mean()))
+      slot, batch = assembled_batch(host.assembler)
+      _, logs = step.minimize(batch)
+      host.assembler.release(slot)
+      logger.step_end(logs, None, iter_frame_ratio)                         # :280
   finally:
+    logger.shutdown()
     save()
     server.shutdown()
     host.unroll_queue.close()
+    host.assembler.close()
+    if summary_writer:
+      summary_writer.close()

@@ -5,7 +5,7 @@
     agent.initial_state(batch_size) -> AgentState(core_state=(h, c), frame_stacking_state)
     agent((prev_actions, env_outputs), agent_state, unroll=False)
         -> (AgentOutput(action int32, q_values float32), AgentState)
-    agent.trainable_variables     (19 tensors, tf.Module order: _advantage, _body, _core, _value)
+    agent.trainable_variables     (18 tensors, tf.Module order: _advantage, _body, _core, _value)
 
 All math runs in libseedrl_b200 (seedrl_r2d2_stack_frames, seedrl_r2d2_net_forward /
 _backward: csrc/r2d2_kernels.cu, csrc/r2d2_net.cu)."""

@@ -11,3 +11,11 @@ flags.DEFINE_integer('env_batch_size', 1,
                      'How many environments to operate on together in a batch.')
 flags.DEFINE_integer('num_envs', 4, 'Total number of environments in all actors.')
 flags.DEFINE_integer('num_action_repeats', 1, 'Number of action repeats.')
+
+
+def define_once(define_fn, name, *args, **kwargs):
+  """The reference's learners are separate binaries that re-use flag names (batch_size,
+  unroll_length, discounting, save_checkpoint_secs ...).  Here both mirrors can live in one
+  process (the test-suite imports both): the first definition of a name stands."""
+  if name not in flags.FLAGS:
+    define_fn(name, *args, **kwargs)

@@ -9,6 +9,7 @@ for the pieces the V-trace learner uses:
   validate_learner_config       utils.py:989-1002
 
   PrioritizedReplay             utils.py:260-370   (GPU-resident; sampling = seedrl_replay_sample)
+  ProgressLogger                utils.py:546-677   (periodic scalar export; JSON-lines writer)
 
 HER / TPU encode are out of scope.
 """
@@ -130,6 +131,9 @@ class UnrollStore(object):
                              device=self._device)                     # :142-145
     self._completed = torch.empty([num_envs], dtype=torch.int32, device=self._device)
     self._ncomp = torch.zeros([1], dtype=torch.int32, device=self._device)
+    # host mirror of `_index`: which unrolls complete is a pure function of the ids appended so
+    # far, so the host never has to read the device counter back (no sync per inference batch)
+    self._host_index = np.full([num_envs], num_overlapping_steps, np.int32)
 
   @property
   def unroll_specs(self):
@@ -141,8 +145,9 @@ class UnrollStore(object):
     s = self._state[i]
     return int(s[0, 0].numel()) * s.element_size()
 
-  def append(self, env_ids, values, check_duplicates=True):
-    """Appends values; returns (completed env ids int64 [n], completed unrolls)."""
+  def append(self, env_ids, values, check_duplicates=True, into=None, on_placed=None):
+    """Appends values; returns (completed env ids int64 [n], completed unrolls) -- or, with
+    `into` (a BatchAssembler), (completed env ids, [(slot, first column, count)])."""
     L = _lib.lib()
     ids, host = _ids_to_device(env_ids, self._device)
     if check_duplicates:
@@ -158,18 +163,61 @@ class UnrollStore(object):
         raise ValueError('Batch dimension must equal the number of environments in store %s.'
                          % self.name)
       keep.append(v)
-      _lib.check(L.seedrl_store_append_field(
-          _lib.ptr(s), _lib.ptr(self._index), _lib.ptr(ids), n, self._full_length,
-          self._row_bytes(i), _lib.ptr(v), st))                       # :187-190
+    if n and len(keep) <= 16:
+      # every field of the step in ONE launch (seedrl_rows_multi, mode append)   :187-190
+      _lib.rows_multi([(s, v, _lib.ROW_APPEND) for s, v in zip(self._state, keep)], ids, index=self._index)
+    else:
+      for i, (s, v) in enumerate(zip(self._state, keep)):
+        _lib.check(L.seedrl_store_append_field(
+            _lib.ptr(s), _lib.ptr(self._index), _lib.ptr(ids), n, self._full_length,
+            self._row_bytes(i), _lib.ptr(v), st))
     _lib.check(L.seedrl_store_advance(
         _lib.ptr(self._index), _lib.ptr(ids), n, self._full_length,
         _lib.ptr(self._completed), _lib.ptr(self._ncomp), st))        # :194
-    return self._complete_unrolls()
+    nc = None
+    if host is not None and self._host_index is not None:
+      hid = np.asarray(host).astype(np.int64).reshape(-1)
+      self._host_index[hid] += 1
+      done_host = hid[self._host_index[hid] == self._full_length]      # in env_ids order, like the kernel
+      self._host_index[done_host] = 1 + self._num_overlapping_steps   # :254-255
+      nc = int(done_host.size)
+    else:
+      self._host_index = None          # ids live on the device only: fall back to reading the counter
+    if into is not None:
+      return self._complete_unrolls_into(nc, into, on_placed)
+    return self._complete_unrolls(nc)
 
-  def _complete_unrolls(self):
+  def _complete_unrolls_into(self, nc, into, on_placed=None):
+    """Gathers the completed unrolls straight into free columns of `into` (a BatchAssembler): no
+    per-unroll tensors, no stack, no transpose.  Returns (completed env ids, [(slot, col0, n)])."""
     L = _lib.lib()
     st = _lib.stream_ptr()
-    nc = int(self._ncomp.item())        # the only host sync: sizes the outputs
+    if nc is None:
+      nc = int(self._ncomp.item())
+    done_ids = self._completed[:nc]
+    placed, start = [], 0
+    while start < nc:
+      slot, col0, room = into.claim(nc - start)
+      ids = done_ids[start:start + room]
+      for i, s in enumerate(self._state):
+        dst = into.field(slot, i)
+        _lib.check(L.seedrl_store_gather_field_into(
+            _lib.ptr(s), _lib.ptr(ids), room, self._full_length, self._row_bytes(i),
+            self._num_overlapping_steps, _lib.ptr(dst), into.batch_size, col0, st))
+      if on_placed is not None:
+        on_placed(slot, col0, ids)       # e.g. the first agent states of these unrolls
+      into.commit()                      # publishes the slot if this filled it
+      placed.append((slot, col0, room))
+      start += room
+    _lib.check(L.seedrl_store_finish(_lib.ptr(self._index), _lib.ptr(done_ids), nc,
+                                     self._num_overlapping_steps, st))
+    return done_ids.to(torch.int64), placed
+
+  def _complete_unrolls(self, nc=None):
+    L = _lib.lib()
+    st = _lib.stream_ptr()
+    if nc is None:
+      nc = int(self._ncomp.item())      # device-resident ids: the one host sync that sizes the outputs
     done_ids = self._completed[:nc]
     unrolls = []
     for i, s in enumerate(self._state):
@@ -187,16 +235,117 @@ class UnrollStore(object):
   def reset(self, env_ids):
     """Reset after actor preemption (reference utils.py:198-225)."""
     L = _lib.lib()
-    ids, _ = _ids_to_device(env_ids, self._device)
+    ids, host = _ids_to_device(env_ids, self._device)
     n = int(ids.numel())
     if n == 0:
       return
+    if host is not None and self._host_index is not None:
+      self._host_index[np.asarray(host).astype(np.int64).reshape(-1)] = self._num_overlapping_steps
+    else:
+      self._host_index = None
     st = _lib.stream_ptr()
     _lib.check(L.seedrl_store_reset(None, _lib.ptr(self._index), _lib.ptr(ids), n,
                                     self._full_length, 0, self._num_overlapping_steps, st))
     for i, s in enumerate(self._state):
       _lib.check(L.seedrl_store_reset(_lib.ptr(s), None, _lib.ptr(ids), n, self._full_length,
                                       self._row_bytes(i), self._num_overlapping_steps, st))
+
+
+class BatchAssembler(object):
+  """Zero-copy minibatch assembly.  Holds `slots` preallocated time-major
+  training batches ([T+1, B, ...] per field of the unroll specs, plus the [B, ...] first agent
+  states); the inference thread's UnrollStore.append(..., into=self) gathers every completed
+  unroll straight into the next free column.  A full slot is handed to the learner (`get`), which
+  returns it with `release(slot)` once its step is enqueued.  Replaces the reference's
+  capacity-1 queue of single unrolls + tf.stack + make_time_major (agents/vtrace/learner.py:336,
+  418-432); the back-pressure is the same: with every slot full or in use, `claim` blocks the
+  inference thread."""
+
+  def __init__(self, timestep_specs, state_specs, full_length, batch_size, slots=2, device='cuda'):
+    self._specs = timestep_specs
+    self.batch_size = int(batch_size)
+    self.full_length = int(full_length)
+    dev = torch.device(device)
+    flat = flatten(timestep_specs)
+    self._fields = [[torch.zeros([full_length, batch_size] + list(s.shape), dtype=as_torch_dtype(s.dtype),
+                                 device=dev) for s in flat] for _ in range(slots)]
+    self._states = [[torch.zeros([batch_size] + list(s.shape), dtype=as_torch_dtype(s.dtype), device=dev)
+                     for s in flatten(state_specs)] for _ in range(slots)]
+    self._state_specs = state_specs
+    self._fill = [0] * slots
+    self._free = collections.deque(range(slots))     # slots the inference thread may fill
+    self._cur = None
+    self._ready = collections.deque()                # full slots, with the event that completes them
+    self._released = {}                              # slot -> event after which it may be rewritten
+    self._cv = threading.Condition()
+    self._closed = False
+
+  def field(self, slot, i):
+    return self._fields[slot][i]
+
+  def state(self, slot):
+    return pack_sequence_as(self._state_specs, self._states[slot])
+
+  def claim(self, want):
+    """-> (slot, first free column, columns granted <= want).  Blocks while no slot is free."""
+    with self._cv:
+      while self._cur is None:
+        if self._closed:
+          raise QueueClosedError('assembler closed')
+        if self._free:
+          self._cur = self._free.popleft()
+          self._fill[self._cur] = 0
+          ev = self._released.pop(self._cur, None)
+          if ev is not None and torch.cuda.is_available():
+            torch.cuda.current_stream().wait_event(ev)   # the step that read this slot has finished
+        else:
+          self._cv.wait(0.05)
+      slot, col0 = self._cur, self._fill[self._cur]
+      n = min(int(want), self.batch_size - col0)
+      self._fill[slot] += n
+      return slot, col0, n
+
+  def commit(self):
+    """Called by the filling thread after the gathers of a claim are enqueued: publishes the slot
+    if it is full."""
+    with self._cv:
+      if self._cur is not None and self._fill[self._cur] == self.batch_size:
+        ev = None
+        if torch.cuda.is_available():
+          ev = torch.cuda.Event()
+          ev.record(torch.cuda.current_stream())
+        self._ready.append((self._cur, ev))
+        self._cur = None
+        self._cv.notify_all()
+
+  def get(self, timeout=None):
+    """-> (slot, first agent states, time-major nest of the unroll specs); the caller's current
+    stream waits for the gathers that filled it."""
+    with self._cv:
+      while not self._ready:
+        if self._closed:
+          raise QueueClosedError('assembler closed')
+        if not self._cv.wait(timeout if timeout is not None else 0.05) and timeout is not None:
+          raise TimeoutError('no full batch')
+      slot, ev = self._ready.popleft()
+    if ev is not None:
+      torch.cuda.current_stream().wait_event(ev)
+    return slot, self.state(slot), pack_sequence_as(self._specs, self._fields[slot])
+
+  def release(self, slot):
+    ev = None
+    if torch.cuda.is_available():
+      ev = torch.cuda.Event()
+      ev.record(torch.cuda.current_stream())
+    with self._cv:
+      self._released[slot] = ev
+      self._free.append(slot)
+      self._cv.notify_all()
+
+  def close(self):
+    with self._cv:
+      self._closed = True
+      self._cv.notify_all()
 
 
 class Aggregator(object):
@@ -310,6 +459,146 @@ class PrioritizedReplay(object):
     """(:359-370) duplicate indices: which priority wins is unspecified, as in the reference."""
     self._priorities.index_copy_(0, _lib.require_cuda(indices, torch.int64, 'indices'),
                                  _lib.require_cuda(priorities, torch.float32, 'priorities'))
+
+
+class SummaryWriter(object):
+  """Stand-in for tf.summary.create_file_writer (TensorFlow is not part of this stack): scalars
+  go to `<logdir>/summaries.jsonl`, one {"step", "tag", "value", "wall_time"} object per line --
+  the same (step, tag, value) triples TensorBoard event files hold."""
+
+  def __init__(self, logdir, filename='summaries.jsonl'):
+    import os
+    os.makedirs(logdir, exist_ok=True)
+    self.path = os.path.join(logdir, filename)
+    self._f = open(self.path, 'a')
+    self._lock = threading.Lock()
+    self.step = 0
+
+  def set_step(self, step):
+    self.step = int(step)
+
+  def scalar(self, tag, value, step=None):
+    import json, time
+    with self._lock:
+      self._f.write(json.dumps({'step': int(self.step if step is None else step), 'tag': tag,
+                                'value': float(value), 'wall_time': time.time()}) + '\n')
+
+  def flush(self):
+    with self._lock:
+      self._f.flush()
+
+  def close(self):
+    with self._lock:
+      self._f.close()
+
+
+class ProgressLogger(object):
+  """Periodic logging of the training progress (reference utils.py:546-677): the learner
+  thread hands the step's scalars over with `step_end` (device tensors: no host sync on the hot
+  path); a logger thread exports the latest values with exponential back-off of the period
+  (initial_period * period_factor^k, capped at max_period) plus `speed/steps_per_sec`."""
+
+  def __init__(self, summary_writer=None, initial_period=0.1, period_factor=1.01, max_period=10.0,
+               starting_step=0):
+    self.summary_writer = None
+    self.last_log_time = None
+    self.last_log_step = 0
+    self.period = initial_period
+    self.period_factor = period_factor
+    self.max_period = max_period
+    self.log_keys = []
+    self.log_keys_set = set()
+    self.step_cnt = -1
+    self.ready_values = None
+    self.logger_thread = None
+    self.logging_callback = None
+    self.terminator = None
+    self._lock = threading.Lock()
+    self.reset(summary_writer, starting_step)
+
+  def reset(self, summary_writer=None, starting_step=0):
+    import timeit
+    with self._lock:
+      self.summary_writer = summary_writer
+      self.step_cnt = int(starting_step)
+      self.ready_values = None
+      self.last_log_time = timeit.default_timer()
+      self.last_log_step = int(starting_step)
+
+  def start(self, logging_callback=None):
+    assert self.logger_thread is None
+    self.logging_callback = logging_callback
+    self.terminator = threading.Event()
+    self.logger_thread = threading.Thread(target=self._logging_loop, daemon=True)
+    self.logger_thread.start()
+
+  def shutdown(self):
+    assert self.logger_thread
+    self.terminator.set()
+    self.logger_thread.join()
+    self.logger_thread = None
+
+  def log_session(self):
+    return []
+
+  def log(self, session, name, value):
+    if name not in self.log_keys_set:
+      self.log_keys.append(name)
+      self.log_keys_set.add(name)
+    session.append(value)
+
+  def log_session_from_dict(self, dic):
+    session = self.log_session()
+    for key in dic:
+      self.log(session, key, dic[key])
+    return session
+
+  def step_end(self, session, strategy=None, step_increment=1):
+    """`strategy` is accepted for signature compatibility (one replica per process here; the
+    reference logs replica 0's value, utils.py:631-635)."""
+    with self._lock:
+      self.ready_values = list(session)
+      self.step_cnt += int(step_increment)
+
+  def _log(self):
+    import timeit
+    logging_time = timeit.default_timer()
+    with self._lock:
+      step_cnt, values = self.step_cnt, self.ready_values
+    if step_cnt == self.last_log_step or values is None:
+      return
+    assert len(values) == len(self.log_keys), (
+        'Mismatch between number of keys and values to log: %r vs %r' % (values, self.log_keys))
+    values = [float(v) for v in values]      # device -> host here, on the logger thread
+    w = self.summary_writer
+    if w:
+      w.set_step(step_cnt)
+    if self.logging_callback:
+      self.logging_callback()
+    dt = logging_time - self.last_log_time
+    df = float(step_cnt - self.last_log_step)
+    if w:
+      for key, value in zip(self.log_keys, values):
+        w.scalar(key, value)
+      w.scalar('speed/steps_per_sec', df / dt)
+      w.flush()
+    self.last_values = dict(zip(self.log_keys, values), **{'speed/steps_per_sec': df / dt})
+    self.last_log_time, self.last_log_step = logging_time, step_cnt
+
+  def _logging_loop(self):
+    import timeit
+    last_log_try = timeit.default_timer()
+    while not self.terminator.is_set():
+      try:
+        self._log()
+      except Exception:                       # pylint: disable=broad-except
+        import logging as _logging
+        _logging.getLogger(__name__).critical('Logging failed.', exc_info=True)
+      now = timeit.default_timer()
+      elapsed = now - last_log_try
+      last_log_try = now
+      self.period = min(self.period_factor * self.period, self.max_period)
+      self.terminator.wait(timeout=max(0, self.period - elapsed))
 
 
 class QueueClosedError(RuntimeError):

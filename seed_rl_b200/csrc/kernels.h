@@ -121,6 +121,11 @@ int poolp_forward(int N, int H, int W, int C, const float* x, void* out_raw, voi
 int poolp_backward(int N, int H, int W, int C, const void* dy, const uint8_t* idx, void* dx_planes,
                    float* dx_nhwc, cudaStream_t st);
 
+// conv_first.cu (first layer of the deep net: weight gradient straight from the pooled gradient)
+bool first_wgrad_pooled_supported(int cin, int cout, int H, int W);
+int first_wgrad_pooled(int N, int H, int W, const uint8_t* frames, const void* g_planes, const uint8_t* idx,
+                       float* dw, float* db, WgradBatch* batch, cudaStream_t st);
+
 // conv_kernels.cu
 int conv3x3_forward(int cin, int cout, int in_mode, int N, int H, int W, const void* in,
                     const float* w, const float* bias, const float* mask, const float* res,
@@ -146,6 +151,11 @@ int convgen_dgrad(int N, int H, int W, int cin, int cout, int k, int stride, con
 int convgen_wgrad(int N, int H, int W, int cin, int cout, int k, int stride, int in_u8,
                   const void* x, const float* dy, float* dw, float* db, float* partial,
                   size_t partial_bytes, cudaStream_t st);
+
+// r2d2_net.cu: 'valid' strided convolutions as im2col + GEMM (R2D2 body, shallow IMPALA net)
+int im2col_nhwc(int N, int H, int W, int C, int K, int S, int in_u8, const void* x, float* col, cudaStream_t st);
+int col2im_nhwc(int N, int H, int W, int C, int K, int S, const float* dcol, const float* xmask, float* dx,
+                cudaStream_t st);
 
 // gemm_kernels.cu
 struct GemmEpi {

@@ -104,6 +104,7 @@ struct Plan {
   int N;                       // T1 * B frames
   std::vector<StackBufs> st;
   size_t sh_a1, sh_a2;         // shallow conv outputs (post-relu)
+  size_t sh_col0, sh_col1;     // shallow net, tensor-core modes: im2col matrices (kept for the backward)
   size_t xc, z, hp, cs, hs, c0buf;
   // backward scratch
   size_t dhs, dz, dhrec, dc0, dc1, dd, gA, gB, gC, gFull, wt, partial, wq, tcerr, counter, gemm_ws, wq_all, partial_all;
@@ -151,6 +152,11 @@ static Plan make_plan(const seedrl_net* n, int T1, int B) {
     const size_t a1 = N * n->sh_h1 * n->sh_w1 * 16, a2 = N * n->sh_h2 * n->sh_w2 * 32;
     p.sh_a1 = b.take(a1 * 4);
     p.sh_a2 = b.take(a2 * 4);
+    p.sh_col0 = p.sh_col1 = 0;
+    if (n->conv_mode >= 1) {
+      p.sh_col0 = b.take(N * n->sh_h1 * n->sh_w1 * (size_t)(64 * n->cfg.obs_c) * 4);
+      p.sh_col1 = b.take(N * n->sh_h2 * n->sh_w2 * (size_t)(16 * 16) * 4);
+    }
     pooled_max = a1 > a2 ? a1 : a2;
     full_max = 0;
   }
@@ -226,6 +232,8 @@ struct StepCtx {
   WgradBatch wb;
 };
 static thread_local StepCtx* t_ctx = nullptr;
+// test hook: 1 = keep the dense (pool backward + full-resolution weight gradient) first-layer path
+static int g_first_dense = 0;
 
 // Packs the weights of every conv of the deep torso with one launch: forward forms, or the
 // flipped/transposed forms of the data-gradient convolutions (all but the first layer).
@@ -480,6 +488,21 @@ static int torso_forward_shallow(const seedrl_net* n, const float* prm, const Pl
   const int N = pl.N;
   float* a1 = W<float>(ws, pl.sh_a1);
   float* a2 = W<float>(ws, pl.sh_a2);
+  if (n->conv_mode >= 1 && n->cfg.obs_c % 4 == 0) {
+    // tensor-core modes: im2col + tcgen05 GEMM with bias + ReLU in the epilogue (the R2D2 body's path)
+    const int C = n->cfg.obs_c, K0 = 64 * C, K1 = 16 * 16;
+    float* col0 = W<float>(ws, pl.sh_col0); float* col1 = W<float>(ws, pl.sh_col1);
+    SEEDRL_TRY(im2col_nhwc(N, n->cfg.obs_h, n->cfg.obs_w, C, 8, 4, 1, obs, col0, st));
+    GemmEpi e = epi_none();
+    e.bias = P(n, prm, n->sh_c0b); e.relu = 1;
+    SEEDRL_TRY(run_gemm(n, ws, pl, false, false, N * n->sh_h1 * n->sh_w1, 16, K0, col0, K0, P(n, prm, n->sh_c0w), 16, a1,
+                        16, e, st));
+    SEEDRL_TRY(im2col_nhwc(N, n->sh_h1, n->sh_w1, 16, 4, 2, 0, a1, col1, st));
+    e.bias = P(n, prm, n->sh_c1b);
+    SEEDRL_TRY(run_gemm(n, ws, pl, false, false, N * n->sh_h2 * n->sh_w2, 32, K1, col1, K1, P(n, prm, n->sh_c1w), 32, a2,
+                        32, e, st));
+    return SEEDRL_OK;
+  }
   SEEDRL_TRY(convgen_forward(N, n->cfg.obs_h, n->cfg.obs_w, n->cfg.obs_c, 16, 8, 4, 1, obs,
                              P(n, prm, n->sh_c0w), P(n, prm, n->sh_c0b), 1, a1, st));
   SEEDRL_TRY(convgen_forward(N, n->sh_h1, n->sh_w1, 16, 32, 4, 2, 0, a1, P(n, prm, n->sh_c1w),
@@ -683,7 +706,12 @@ static int torso_backward_planes(const seedrl_net* n, const float* prm, float* g
     SEEDRL_TRY(planes_conv_bwd(n, prm, grd, k.r01, N, H, Wd, c0r, g3, c0r, nullptr, g2, ws, pl, st));
     SEEDRL_TRY(planes_conv_bwd(n, prm, grd, k.r00, N, H, Wd, prelu, g2, prelu, g3, g1, ws, pl, st));
     // max-pool, then the stack's first conv
-    if (s == 0) {
+    if (s == 0 && t_ctx && first_wgrad_pooled_supported(k.cin, k.c, k.hin, k.win) && !g_first_dense) {
+      // no gradient flows into the frames: the weight gradient is taken straight from the pooled
+      // gradient and the pool's arg-max taps (conv_first.cu), the full-resolution tensor never exists
+      SEEDRL_TRY(first_wgrad_pooled(N, k.hin, k.win, obs, g1, W<uint8_t>(ws, b.idx), G(n, grd, k.conv.w),
+                                    G(n, grd, k.conv.b), &t_ctx->wb, st));
+    } else if (s == 0) {
       SEEDRL_TRY(poolp_backward(N, k.hin, k.win, k.c, g1, W<uint8_t>(ws, b.idx), nullptr, gF, st));
       SEEDRL_TRY(conv_bwd(n, prm, grd, k.conv, N, k.hin, k.win, obs, IN_U8, gF, nullptr, nullptr, nullptr, ws, pl,
                           st));
@@ -702,6 +730,19 @@ static int torso_backward_shallow(const seedrl_net* n, const float* prm, float* 
   const int N = pl.N;
   float* gA = W<float>(ws, pl.gA); float* gB = W<float>(ws, pl.gB);
   const float* a1 = W<float>(ws, pl.sh_a1);
+  if (n->conv_mode >= 1 && n->cfg.obs_c % 4 == 0) {
+    const int C = n->cfg.obs_c, K0 = 64 * C, K1 = 16 * 16;
+    const int M1 = N * n->sh_h2 * n->sh_w2, M0 = N * n->sh_h1 * n->sh_w1;
+    float* col0 = W<float>(ws, pl.sh_col0); float* col1 = W<float>(ws, pl.sh_col1);
+    const GemmEpi e0 = epi_none();
+    SEEDRL_TRY(run_gemm(n, ws, pl, true, false, K1, 32, M1, col1, K1, gA, 32, G(n, grd, n->sh_c1w), 32, e0, st));
+    SEEDRL_TRY(colsum(M1, 32, gA, 32, G(n, grd, n->sh_c1b), st));
+    SEEDRL_TRY(run_gemm(n, ws, pl, false, true, M1, K1, 32, gA, 32, P(n, prm, n->sh_c1w), 32, col1, K1, e0, st));
+    SEEDRL_TRY(col2im_nhwc(N, n->sh_h1, n->sh_w1, 16, 4, 2, col1, a1, gB, st));
+    SEEDRL_TRY(run_gemm(n, ws, pl, true, false, K0, 16, M0, col0, K0, gB, 16, G(n, grd, n->sh_c0w), 16, e0, st));
+    SEEDRL_TRY(colsum(M0, 16, gB, 16, G(n, grd, n->sh_c0b), st));
+    return SEEDRL_OK;
+  }
   SEEDRL_TRY(convgen_wgrad(N, n->sh_h1, n->sh_w1, 16, 32, 4, 2, 0, a1, gA, G(n, grd, n->sh_c1w),
                            G(n, grd, n->sh_c1b), W<float>(ws, pl.partial),
                            conv3x3_wgrad_partial_bytes(), st));
@@ -873,6 +914,10 @@ extern "C" int seedrl_debug_conv3x3_wgrad_tc(int cin, int cout, int in_mode, int
 }
 // Bench knob: output positions per tile of the tensor-core forward / data-gradient kernel
 // (the largest of 512/256/128 not above `mt` that keeps >= 2 CTAs per SM is used; default 512).
+extern "C" int seedrl_debug_set_first_layer_dense(int on) {
+  g_first_dense = on ? 1 : 0;
+  return SEEDRL_OK;
+}
 extern "C" int seedrl_debug_set_conv_tile(int mt) {
   SEEDRL_CHECK_ARG(mt == 128 || mt == 256 || mt == 512, "tile must be 128, 256 or 512");
   conv3x3_tc_set_tile(mt);

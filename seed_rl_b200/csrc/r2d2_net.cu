@@ -117,6 +117,9 @@ static RPlan r_plan(const seedrl_r2d2_net* n, int T, int B) {
   return p;
 }
 
+static int im2col(int N, const RConv& c, bool u8, const void* x, float* col, cudaStream_t st);
+static int col2im(int N, const RConv& c, const float* dcol, const float* xmask, float* dx, cudaStream_t st);
+
 template <typename T>
 static inline T* RW(void* ws, size_t off) {
   return reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + off);
@@ -169,6 +172,20 @@ im2col_kernel(long long total, int H, int W, int C, int K, int S, int Ho, int Wo
     if (U8) *dst = (float)__ldg(reinterpret_cast<const uint8_t*>(x_) + src) * (1.0f / 255.0f);
     else *dst = __ldg(reinterpret_cast<const float*>(x_) + src);
   }
+}
+
+int im2col_nhwc(int N, int H, int W, int C, int K, int S, int in_u8, const void* x, float* col, cudaStream_t st) {
+  RConv c;
+  c.k = K; c.s = S; c.cin = C; c.cout = 0; c.hin = H; c.win = W; c.hout = (H - K) / S + 1; c.wout = (W - K) / S + 1;
+  c.w = c.b = 0;
+  return im2col(N, c, in_u8 != 0, x, col, st);
+}
+int col2im_nhwc(int N, int H, int W, int C, int K, int S, const float* dcol, const float* xmask, float* dx,
+                cudaStream_t st) {
+  RConv c;
+  c.k = K; c.s = S; c.cin = C; c.cout = 0; c.hin = H; c.win = W; c.hout = (H - K) / S + 1; c.wout = (W - K) / S + 1;
+  c.w = c.b = 0;
+  return col2im(N, c, dcol, xmask, dx, st);
 }
 
 static int im2col(int N, const RConv& c, bool u8, const void* x, float* col, cudaStream_t st) {

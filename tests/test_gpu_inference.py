@@ -200,3 +200,53 @@ def test_device_feeder_double_buffering():
   assert seen == [2.0, 4.0, 6.0, 8.0, 10.0]
   with pytest.raises(RuntimeError):
     f.get()
+
+
+def test_zero_copy_batch_assembly_matches_queue_path():
+  """the assembler path (completed unrolls gathered straight into columns of
+  the time-major training batch; no per-unroll tensors, no stack, no host read-back of the
+  completion count) yields bit-identical training batches to the reference-shaped path (capacity-1
+  queue of single unrolls + dequeue_batch), including batches that straddle inference calls."""
+  from seed_rl_b200.agents.vtrace import learner_loop
+  from seed_rl_b200.common import utils
+  from seed_rl_b200.dmlab import networks
+  num_envs, T, N, B = 6, 3, 3, 4
+  agent = networks.ImpalaDeep(A, OBS, seed=3)
+  host_q = learner_loop.InferenceHost(agent, num_envs, T, N, OBS)
+  host_q.unroll_queue = type(host_q.unroll_queue)(-1, host_q.unroll_specs)
+  host_a = learner_loop.InferenceHost(agent, num_envs, T, N, OBS, training_batch_size=B)
+  # same sampling noise on both hosts: the agent's RNG offset advances per call, so replay it
+  rng = np.random.default_rng(0)
+  run_ids = rng.integers(1, 2**40, num_envs)
+  calls = []
+  for step in range(9):
+    for ids in (np.array([0, 1, 2], np.int32), np.array([5, 3, 4], np.int32)):
+      calls.append((ids, _env_batch(rng, ids, step)))
+  batches_a = []
+
+  def learner_thread():
+    try:
+      while True:
+        slot, u = learner_loop.assembled_batch(host_a.assembler)
+        batches_a.append(utils.map_structure(lambda t: t.clone(), tuple(u)))
+        host_a.assembler.release(slot)
+    except utils.QueueClosedError:
+      return
+  th = threading.Thread(target=learner_thread); th.start()
+  for host in (host_q, host_a):
+    agent._rng_offset = 0
+    for ids, env in calls:
+      host.inference(ids, run_ids[ids], env, np.zeros(len(ids), np.float32))
+  torch.cuda.synchronize()
+  import time
+  for _ in range(100):
+    if len(batches_a) == 3:
+      break
+    time.sleep(0.05)
+  host_a.assembler.close(); th.join(10)
+  assert host_q.unroll_queue.size() == 12 and len(batches_a) == 3      # 12 unrolls = 3 batches of 4
+  assert host_a.store._host_index is not None                          # completion tracked on the host
+  for k in range(3):
+    want = learner_loop.dequeue_batch(host_q.unroll_queue, B)
+    for x, y in zip(utils.flatten(batches_a[k]), utils.flatten(tuple(want))):
+      assert torch.equal(x, y)

@@ -268,3 +268,39 @@ def test_inference_step_planes_matches_tc3():
     ag.check_errors()
     outs[mode] = o.policy_logits.cpu().numpy()
   assert np.abs(outs['tc3p'] - outs['simt']).max() < 2e-4 * np.abs(outs['simt']).max()
+
+
+@pytest.mark.parametrize('T,B', [(3, 2), (20, 8)])
+def test_first_layer_gather_backward_matches_dense(T, B):
+  """csrc/conv_first.cu (weight gradient of the uint8 first conv gathered from the POOLED gradient
+  and the pool's arg-max taps) against the dense path it replaces (pool backward -> full-resolution
+  gradient -> tcgen05 bf16x3 weight-gradient conv): every gradient tensor of the step; only
+  stack0/conv/{kernel,bias} may differ, by summation order / operand split (2e-4 of max-abs)."""
+  from oracle import learner_oracle, loss_oracle, net_oracle
+  from seed_rl_b200 import _lib
+  from seed_rl_b200.agents.vtrace import learner
+  from seed_rl_b200.common import optimizers
+  from seed_rl_b200.dmlab import networks
+  from test_gpu_parity import _batch_to_cuda
+  A = 18
+  params = net_oracle.init_params('deep', A, (84, 84, 4), seed=2)
+  u = _batch_to_cuda(learner_oracle.synthetic_batch(T, B, A, seed=11))
+  grads = {}
+  try:
+    for dense in (1, 0):
+      _lib.check(_lib.lib().seedrl_debug_set_first_layer_dense(dense))
+      ag = networks.ImpalaDeep(A, (84, 84, 4), conv_mode='tc3p')
+      ag.load_named_parameters(params)
+      st = learner.LearnerStep(ag, optimizers.Adam(4.8e-4, beta_1=0.0, epsilon=3.125e-7),
+                               settings=learner.default_loss_settings())
+      st.compute_gradients(u)
+      ag.check_errors()
+      grads[dense] = {k: v.cpu().numpy().copy() for k, v in ag.named_gradients().items()}
+  finally:
+    _lib.check(_lib.lib().seedrl_debug_set_first_layer_dense(0))
+  for k in grads[0]:
+    a, w = grads[0][k], grads[1][k]
+    if k.startswith('stack0/conv/'):
+      assert np.abs(a - w).max() <= 2e-4 * np.abs(w).max(), (k, np.abs(a - w).max() / np.abs(w).max())
+    else:
+      np.testing.assert_array_equal(a, w, err_msg=k)

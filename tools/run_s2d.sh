@@ -1,0 +1,10 @@
+set +e
+O=gpurun_out/s2d; mkdir -p $O
+timeout 900 python -m pytest tests/test_gpu_r2d2.py tests/test_gpu_planes.py tests/test_gpu_fullsize.py tests/test_gpu_checkpoint.py -q > $O/pytest.log 2>&1; echo "rc=$?" >> $O/pytest.log
+tail -40 $O/pytest.log
+timeout 400 python bench.py --steps 20 --warmup 5 > $O/bench_tc3p.json 2> $O/bench.err; tail -3 $O/bench.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/s2d/bench_tc3p.json'))
+print(d['ms_per_step'], d['value'], d['e2e']['value'], d['kernel_time_ms_per_step'], d['kernel_launches_per_step'])
+PY
