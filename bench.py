@@ -633,6 +633,16 @@ def main():
       'gpu_launches': int(launches * args.steps), 'gpu_launches_per_step': int(launches),
       'impl': 'b200'}
 
+  if world > 1:
+    # data-parallel replicas must stay bit-identical (deterministic kernels + the same reduced
+    # gradient everywhere): compare a checksum of the parameter arena across ranks
+    cs = agent.params.double().sum().reshape(1)
+    lo, hi = cs.clone(), cs.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    line['replicas_in_sync'] = bool((lo == hi).item())
+    line['grad_exchange'] = ('ncclAllReduce(SUM) in two buckets: heads+Dense+LSTM (94 %% of the %.2f MB arena) on a '
+                             'side stream during the conv backward, conv stacks after it' %
+                             (agent.params.numel() * 4 / 1e6))
   peaks = {}
   try:
     peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))

@@ -204,6 +204,17 @@ int seedrl_net_backward(const seedrl_net* net, const float* params, int T1, int 
                         const float* dlogits, const float* dbaseline,
                         float* grads, void* workspace, size_t workspace_bytes,
                         seedrl_stream_t stream);
+/* Overlap of the data-parallel exchange (the reference's strategy.run + cross-replica SUM,
+ * agents/vtrace/learner.py:255-280, tests/utils_test.py:640-650): seedrl_net_backward plus a
+ * cudaEvent_t recorded on `stream` once the first arena bucket -- floats
+ * [0, seedrl_net_grad_split(net)): heads, Dense, LSTM -- is final, so its all-reduce can run on a side
+ * stream during the convolution torso's backward. */
+int seedrl_net_backward_overlap(const seedrl_net* net, const float* params, int T1, int B,
+                                const int64_t* prev_actions, const float* reward, const uint8_t* done,
+                                const uint8_t* observation, const float* dlogits, const float* dbaseline,
+                                float* grads, void* workspace, size_t workspace_bytes,
+                                void* head_ready_event, seedrl_stream_t stream);
+size_t seedrl_net_grad_split(const seedrl_net* net);
 /* The tcgen05 / persistent kernels never spin forever: a barrier wait that expires sets an
  * error flag in the workspace and the kernel bails out (its results are then garbage).
  * seedrl_net_forward clears the flag; this call copies it back (synchronising `stream`) and
@@ -410,6 +421,10 @@ int seedrl_debug_set_conv_tile(int mt);
 /* 1 = conv_mode 3 keeps the dense first-layer backward (pool backward + full-resolution weight
  * gradient) instead of csrc/conv_first.cu's gather from the pooled gradient (A/B parity tests). */
 int seedrl_debug_set_first_layer_dense(int on);
+/* The fused first layer (conv 4->16 on uint8 frames + bias + max-pool 3x3/2 SAME) on its own:
+ * pooled plane tensors (raw, ReLU'd) + arg-max taps [N,Ho,Wo,16]. */
+int seedrl_debug_conv0pool(int N, int H, int W, const uint8_t* frames, const float* w, const float* bias,
+                           void* praw, void* prelu, uint8_t* idx, int* err, seedrl_stream_t stream);
 int seedrl_debug_conv3x3_wgrad(int cin, int cout, int in_mode, int N, int H, int W,
                                const void* x, const float* dy, float* dw, float* db,
                                float* partial, size_t partial_bytes,

@@ -94,6 +94,9 @@ SIGNATURES = {
         (c_int, [P, P, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, c_size_t, P]),
     'seedrl_net_backward':
         (c_int, [P, P, c_int, c_int, P, P, P, P, P, P, P, P, c_size_t, P]),
+    'seedrl_net_backward_overlap':
+        (c_int, [P, P, c_int, c_int, P, P, P, P, P, P, P, P, c_size_t, P, P]),
+    'seedrl_net_grad_split': (c_size_t, [P]),
     'seedrl_net_check_error': (c_int, [P, c_int, c_int, P, c_size_t, P]),
     'seedrl_store_append_field': (c_int, [P, P, P, c_int, c_int, c_size_t, P, P]),
     'seedrl_store_advance': (c_int, [P, P, c_int, c_int, P, P, P]),
@@ -156,6 +159,7 @@ SIGNATURES = {
     'seedrl_debug_set_wgrad_chunk': (c_int, [c_int]),
     'seedrl_debug_set_conv_tile': (c_int, [c_int]),
     'seedrl_debug_set_first_layer_dense': (c_int, [c_int]),
+    'seedrl_debug_conv0pool': (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, P, P]),
     'seedrl_debug_conv3x3_wgrad_tc':
         (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, P, P, P, P, P, c_size_t, P, P]),
     'seedrl_debug_conv3x3_wgrad':

@@ -192,8 +192,11 @@ class LearnerStep(object):
   """`minimize` of reference learner.py:255-280 for one replica (= one GPU/process)."""
 
   def __init__(self, agent, optimizer, parametric_action_distribution=None, settings=None,
-               logger=None, process_group=None, grad_reduce='sum', check_errors_every=64):
+               logger=None, process_group=None, grad_reduce='sum', check_errors_every=64,
+               overlap_reduce=True):
     self.agent = agent
+    self.overlap_reduce = overlap_reduce
+    self._side = self._head_ev = self._head_work = None
     # the kernels' bounded-wait error flag is polled (one 4-byte D2H + stream sync) every
     # `check_errors_every` steps; 0 = never (the caller polls agent.check_errors() itself)
     self.check_errors_every = int(check_errors_every)
@@ -217,14 +220,34 @@ class LearnerStep(object):
                               unroll.prev_actions, unroll.env_outputs, unroll.agent_outputs,
                               self.settings)
     r = self.agent._loss_grads
-    grads = self.agent.backward(r['dlogits'], r['dbaseline'])                     # :264
+    self._head_work = None
+    if self.world > 1 and self.overlap_reduce and torch.cuda.is_available():
+      # bucket 1 (heads, Dense, LSTM = 94 % of the arena) is all-reduced on a side stream while
+      # the convolution torso's backward still runs; bucket 2 follows in apply_gradients
+      import torch.distributed as td
+      if self._side is None:
+        self._side, self._head_ev = torch.cuda.Stream(), torch.cuda.Event()
+      grads = self.agent.backward(r['dlogits'], r['dbaseline'], head_ready_event=self._head_ev)
+      with torch.cuda.stream(self._side):
+        self._side.wait_event(self._head_ev)
+        self._head_work = td.all_reduce(grads[:self.agent.grad_split], op=td.ReduceOp.SUM, group=self.pg,
+                                        async_op=True)
+    else:
+      grads = self.agent.backward(r['dlogits'], r['dbaseline'])                   # :264
     grads[self.agent.entropy_cost_param_index] = r['d_entropy_cost_param']
     self.last_loss_terms = r['loss_terms']
     return loss, logs
 
   def apply_gradients(self):
     grads = self.agent.grads
-    scale = reduce_gradients(grads, self.world, self.pg, self.grad_reduce)
+    if getattr(self, '_head_work', None) is not None:
+      import torch.distributed as td
+      td.all_reduce(grads[self.agent.grad_split:], op=td.ReduceOp.SUM, group=self.pg)
+      self._head_work.wait()              # the compute stream waits for the side-stream bucket
+      self._head_work = None
+      scale = 1.0 / self.world if self.grad_reduce == 'mean' else 1.0
+    else:
+      scale = reduce_gradients(grads, self.world, self.pg, self.grad_reduce)
     mul = self.settings.entropy_cost_adjustment_speed
     self.optimizer.apply_gradients(
         self.agent.params, grads, grad_scale=scale,

@@ -1,5 +1,5 @@
 // First layer of ImpalaDeep (dmlab/networks.py:31-37: Conv2D(16, 3, 'same') on the uint8 frames,
-// then MaxPool 3x3 / 2 'same') -- backward, fused.
+// then MaxPool 3x3 / 2 'same'), fused: backward here, forward (conv0pool_kernel) at the end of the file.
 //
 // The gradient that reaches the convolution output is the max-pool's scatter of the pooled gradient
 // g: at most one position per (pooled pixel, channel) is non-zero.  Materialising that full-
@@ -32,7 +32,7 @@ struct FirstWgradArgs {
 };
 
 __global__ void __launch_bounds__(kFwThreads, 3) first_wgrad_pooled_kernel(const FirstWgradArgs a) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
+  extern __shared__ __align__(128) uint8_t smem_raw[];
   uint2* s_x = reinterpret_cast<uint2*>(smem_raw);               // [(H+2)][(W+2)] pixels x 4 bf16
   const int tid = threadIdx.x;
   const int co = tid & (kFwCo - 1), ql = tid >> 4;               // 16 pooled-pixel lanes
@@ -72,24 +72,28 @@ __global__ void __launch_bounds__(kFwThreads, 3) first_wgrad_pooled_kernel(const
     const uint8_t* idx_n = a.idx + (size_t)n * nq * kFwCo;
     // The arg-max tap and the gradient of pooled pixel q + 16 are fetched (L2 latency) while the 36
     // FMAs of pixel q run: without this the loop is a chain of dependent global loads.
-    auto fetch = [&](int q, int* t, uint32_t* ghi, uint32_t* glo, int* qh_, int* qw_) {
-      const int qh = q / a.Wo, qw = q - qh * a.Wo;
-      const size_t sp = (size_t)(n * a.RHp + qh + 1) * a.PWp + qw + 1;
-      *t = idx_n[(size_t)q * kFwCo + co];
-      *ghi = gh[plane_off + sp * 8];
-      *glo = gh[lo_off + plane_off + sp * 8];
-      *qh_ = qh; *qw_ = qw;
-    };
+    // (pooled row / column advance incrementally: one runtime division per unit, not per pixel;
+    //  32-bit element offsets)
+    const unsigned short* gh_n = gh + plane_off + (size_t)n * a.RHp * a.PWp * 8;
     const int qend = r1 * a.Wo;
     int q = r0 * a.Wo + ql;
-    int t_n = 0, qh_n = 0, qw_n = 0;
+    int qh_n = q / a.Wo, qw_n = q - qh_n * a.Wo;
+    int t_n = 0;
     uint32_t ghi_n = 0, glo_n = 0;
-    if (q < qend) fetch(q, &t_n, &ghi_n, &glo_n, &qh_n, &qw_n);
+    auto fetch = [&]() {
+      const int spo = ((qh_n + 1) * a.PWp + qw_n + 1) * 8;
+      t_n = idx_n[q * kFwCo + co];
+      ghi_n = gh_n[spo];
+      glo_n = gh_n[lo_off + spo];
+    };
+    if (q < qend) fetch();
     while (q < qend) {
       const int t = t_n, qh = qh_n, qw = qw_n;
       const float gv = __uint_as_float(ghi_n << 16) + __uint_as_float(glo_n << 16);
       q += kFwThreads / kFwCo;
-      if (q < qend) fetch(q, &t_n, &ghi_n, &glo_n, &qh_n, &qw_n);
+      qw_n += kFwThreads / kFwCo;
+      while (qw_n >= a.Wo) { qw_n -= a.Wo; ++qh_n; }
+      if (q < qend) fetch();
       const int kh = t / 3, kw = t - kh * 3;
       // arg-max position in frame coordinates; its 3x3 patch starts at smem (ph, pw)
       const int ph = qh * 2 - a.pt + kh, pw = qw * 2 - a.pl + kw;
@@ -168,6 +172,267 @@ int first_wgrad_pooled(int N, int H, int W, const uint8_t* frames, const void* g
   count_launch(PC_CONV_WGRAD, st);
   SEEDRL_CHECK_LAUNCH();
   batch->jobs[batch->n++] = ReduceJob{a.partial, dw, db, grid, 36 * kFwCo, kFwCo};
+  return SEEDRL_OK;
+}
+
+// =================================================================================================
+// First layer, forward, fused: Conv2D(16, 3, 'same') on the uint8 frames + bias + MaxPool 3x3/2
+// 'same' (dmlab/networks.py:31-37,47-48) -> the pooled activation as plane tensors (raw and ReLU'd)
+// + the arg-max taps.  The full-resolution conv output (607 MB fp32 at 1 344 frames, written once and
+// read once by a separate pool kernel: 0.53 ms of the step) never leaves the SM.
+//
+// Work unit = (frame, band of kCpRows pooled rows).  Per unit:
+//   1. the band's frame rows -> shared memory as a PAIR array: entry e = [pixel e, pixel e+1] of the
+//      zero-bordered band (row pitch SW = W + 2), 4 channels each, bf16 (exact for 0..255) = 16 bytes.
+//      That array IS a K-major UMMA operand whose row p reads, for kernel row kh, the 16 bytes at
+//      e = p + kh*SW (taps kw = 0, 1) and at e + 2 (taps kw = 2 and a 4th, zero-weight, tap): the two
+//      K-groups of one K = 16 instruction are the same array 32 bytes apart (LBO = 32 B).  A whole
+//      kernel row per MMA: 3 MMAs of 128 x 32 x 16 per 128 positions, no im2col pass.
+//   2. one elected thread issues them: D[128, 0:16] = A hi(W), D[128, 16:32] = A lo(W)
+//      (frames are exact in bf16, so two products make the fp32-faithful result);
+//   3. epilogue: TMEM -> (hi + lo) / 255 + bias -> fp32 tile in shared memory;
+//   4. pooling from shared memory, TF-SAME windows, first maximum wins; hi/lo split; coalesced
+//      16-byte plane stores; padding positions of the plane tensors written as zeros.
+// 2 CTAs / SM (TMEM 2 x 256 columns): the phases of one CTA overlap the other's.
+constexpr int kCpRows = 3;          // pooled rows per unit
+constexpr int kCpMaxBlocks = 6;     // 128-position blocks per unit (TMEM: 6 x 32 columns)
+constexpr int kCpThreadsF = 256;
+constexpr int kCpOutStride = 20;    // floats per position in the fp32 tile (16 + 4: pool reads 2-way conflict)
+
+struct Conv0PoolArgs {
+  int N, H, W, Ho, Wo, pt, pl;
+  int Lpp, PWp, RHp;                 // pooled plane-tensor geometry
+  unsigned int sw_mul; int sw_sh;    // division by SW = W + 2
+  const uint8_t* frames;             // [N,H,W,4]
+  const float* w;                    // [3,3,4,16]
+  const float* bias;                 // [16]
+  uint4* praw; uint4* prelu;         // plane tensors, 16 channels (2 hi planes, 2 lo planes)
+  uint8_t* idx;                      // [N,Ho,Wo,16]
+  int* err;
+};
+
+__device__ __forceinline__ uint2 u8x4_to_bf16x4(uint32_t w32) {
+  // byte -> float without I2F: 0x4B0000kk is 2^23 + kk; the high half of the float is its bf16
+  const uint32_t f0 = __float_as_uint(__uint_as_float(__byte_perm(w32, 0x4B000000u, 0x7540)) - 8388608.0f);
+  const uint32_t f1 = __float_as_uint(__uint_as_float(__byte_perm(w32, 0x4B000000u, 0x7541)) - 8388608.0f);
+  const uint32_t f2 = __float_as_uint(__uint_as_float(__byte_perm(w32, 0x4B000000u, 0x7542)) - 8388608.0f);
+  const uint32_t f3 = __float_as_uint(__uint_as_float(__byte_perm(w32, 0x4B000000u, 0x7543)) - 8388608.0f);
+  return make_uint2(__byte_perm(f0, f1, 0x7632), __byte_perm(f2, f3, 0x7632));
+}
+
+__global__ void __launch_bounds__(kCpThreadsF, 2) conv0pool_kernel(const Conv0PoolArgs a) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int W = a.W, H = a.H, SW = W + 2;
+  const int npair = kCpMaxBlocks * 128 + 2 * SW + 8;          // pair entries an MMA may touch
+  uint4* s_p = reinterpret_cast<uint4*>(smem_raw);            // pair array, 16 B per entry
+  float* s_out = reinterpret_cast<float*>(smem_raw + (size_t)npair * 16);           // [positions][20] fp32
+  uint8_t* s_bq = reinterpret_cast<uint8_t*>(s_out + (size_t)kCpMaxBlocks * 128 * kCpOutStride);
+  s_bq = reinterpret_cast<uint8_t*>(((uintptr_t)s_bq + 127) & ~(uintptr_t)127);     // B: 48 x 32 bf16 = 3 KB
+  float* s_bias = reinterpret_cast<float*>(s_bq + 48 * 32 * 2);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 16);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
+
+  // ---- one-time setup: B operand (K-major, [N = 32][K = 48]: hi(w) | lo(w); k = kh*16 + kw*4 + ci,
+  //      the 4th tap of a row has zero weights), bias, barrier, TMEM -------------------------------
+  for (int i = tid; i < 48 * 32; i += kCpThreadsF) {
+    const int k = i / 32, nn = i - k * 32;
+    const int kh = k >> 4, kw = (k >> 2) & 3, ci = k & 3;
+    float v = 0.f;
+    if (kw < 3) {
+      const float wv = __ldg(a.w + ((kh * 3 + kw) * 4 + ci) * 16 + (nn & 15));
+      v = nn < 16 ? wv : bf16_resid(wv);
+    }
+    const uint32_t off = (uint32_t)(k >> 3) * 512u + (uint32_t)(nn >> 3) * 128u + (uint32_t)(nn & 7) * 16u +
+                         (uint32_t)(k & 7) * 2u;
+    *reinterpret_cast<__nv_bfloat16*>(s_bq + off) = __float2bfloat16_rn(v);
+  }
+  if (tid < 16) s_bias[tid] = __ldg(a.bias + tid);
+  for (int i = tid; i < npair; i += kCpThreadsF) s_p[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(s_tmem);
+  constexpr uint32_t idesc = umma_idesc(128, 32);
+  const uint32_t a_base = smem_u32(s_p), b_base = smem_u32(s_bq);
+
+  const int bands = (a.Ho + kCpRows - 1) / kCpRows;
+  const int units = a.N * bands;
+  uint32_t phase = 0;
+  bool timed_out = false;
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    const int n = u / bands, band = u - n * bands;
+    const int r0 = band * kCpRows, r1 = min(a.Ho, r0 + kCpRows);
+    // conv rows this band's windows touch (clipped to the frame)
+    const int cr0 = max(0, 2 * r0 - a.pt), cr1 = min(H - 1, 2 * (r1 - 1) - a.pt + 2);
+    const int CR = cr1 - cr0 + 1, npos = CR * SW, nblk = (npos + 127) >> 7;
+    // ---- 1. pair array of band rows cr0-1 .. cr1+1 (band row lr, band column bc = frame column + 1) ----
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.frames) + (size_t)n * H * W;
+    for (int e = tid; e < (CR + 2) * SW; e += kCpThreadsF) {
+      const int lr = (int)(__umulhi((unsigned)e, a.sw_mul) >> a.sw_sh), bc = e - lr * SW;
+      const int fr = cr0 - 1 + lr;
+      uint2 p0 = make_uint2(0u, 0u), p1 = p0;
+      if (fr >= 0 && fr < H) {
+        const uint32_t* row = src + (size_t)fr * W;
+        if (bc >= 1 && bc <= W) p0 = u8x4_to_bf16x4(__ldg(row + bc - 1));
+        if (bc + 1 >= 1 && bc + 1 <= W) p1 = u8x4_to_bf16x4(__ldg(row + bc));        // e + 1 is the same row
+      }
+      s_p[e] = make_uint4(p0.x, p0.y, p1.x, p1.y);       // (the pair of a row's last column pairs with zero)
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    // ---- 2. MMAs: one per kernel row and 128-position block -------------------------------------
+    if (warp == 0 && elect_one()) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      for (int m = 0; m < nblk; ++m) {
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const uint64_t da = umma_desc(a_base + (uint32_t)(m * 128 + kh * SW) * 16u, 32u, 128u);
+          const uint64_t db = umma_desc(b_base + (uint32_t)(2 * kh) * 512u, 512u, 128u);
+          umma_f16(tmem_base + (uint32_t)(m * 32), da, db, idesc, kh > 0 ? 1u : 0u);
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(s_bar))
+                   : "memory");
+    }
+    if (!mbar_wait_bounded(s_bar, phase)) timed_out = true;
+    phase ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // ---- 3. epilogue: accumulators -> fp32 tile [position o = lr*SW + c][16 (+4 pad)] --------------
+    for (int m = warp >> 2; m < nblk; m += 2) {
+      const int q = warp & 3;
+      const int o = m * 128 + q * 32 + lane;
+      float v[32];
+      tmem_ld<32>(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(m * 32), v);
+      if (o < npos) {
+        float4* dst = reinterpret_cast<float4*>(s_out + (size_t)o * kCpOutStride);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4) {
+          const float4 bq = reinterpret_cast<const float4*>(s_bias)[c4];
+          dst[c4] = make_float4(fmaf(v[c4 * 4 + 0] + v[16 + c4 * 4 + 0], 1.0f / 255.0f, bq.x),
+                                fmaf(v[c4 * 4 + 1] + v[16 + c4 * 4 + 1], 1.0f / 255.0f, bq.y),
+                                fmaf(v[c4 * 4 + 2] + v[16 + c4 * 4 + 2], 1.0f / 255.0f, bq.z),
+                                fmaf(v[c4 * 4 + 3] + v[16 + c4 * 4 + 3], 1.0f / 255.0f, bq.w));
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    // ---- 4. max-pool 3x3 / 2 from the tile; thread = (pooled pixel, 8-channel group) ----------------
+    const int nout = (r1 - r0) * a.Wo * 2;
+    for (int i = tid; i < nout; i += kCpThreadsF) {
+      const int gq = i & 1, qq = i >> 1;
+      const int qr = qq / a.Wo, qw = qq - qr * a.Wo, qh = r0 + qr;
+      float best[8];
+      unsigned char arg[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; arg[e] = 0; }
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        const int h = qh * 2 - a.pt + kh;
+        if (h < 0 || h >= H) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int w = qw * 2 - a.pl + kw;
+          if (w < 0 || w >= W) continue;
+          const float4* s4 = reinterpret_cast<const float4*>(s_out + (size_t)((h - cr0) * SW + w) * kCpOutStride + gq * 8);
+          const float4 x0 = s4[0], x1 = s4[1];
+          const float vv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+          const unsigned char t = (unsigned char)(kh * 3 + kw);
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            if (vv[e] > best[e]) { best[e] = vv[e]; arg[e] = t; }
+        }
+      }
+      const size_t pix = ((size_t)n * a.Ho + qh) * a.Wo + qw;
+      uint2 packed;
+      packed.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | ((uint32_t)arg[3] << 24);
+      packed.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | ((uint32_t)arg[7] << 24);
+      *reinterpret_cast<uint2*>(a.idx + pix * 16 + gq * 8) = packed;
+      const size_t sp = (size_t)(n * a.RHp + qh + 1) * a.PWp + qw + 1;
+      const float4 va = make_float4(best[0], best[1], best[2], best[3]), vb = make_float4(best[4], best[5], best[6], best[7]);
+      a.praw[(size_t)gq * a.Lpp + sp] = pack8_bf16(va, vb);
+      a.praw[(size_t)(2 + gq) * a.Lpp + sp] = pack8_bf16(bf16_resid4(va), bf16_resid4(vb));
+      const float4 ra = make_float4(fmaxf(va.x, 0.f), fmaxf(va.y, 0.f), fmaxf(va.z, 0.f), fmaxf(va.w, 0.f));
+      const float4 rb = make_float4(fmaxf(vb.x, 0.f), fmaxf(vb.y, 0.f), fmaxf(vb.z, 0.f), fmaxf(vb.w, 0.f));
+      a.prelu[(size_t)gq * a.Lpp + sp] = pack8_bf16(ra, rb);
+      a.prelu[(size_t)(2 + gq) * a.Lpp + sp] = pack8_bf16(bf16_resid4(ra), bf16_resid4(rb));
+    }
+    // ---- padding positions of the plane tensors owned by this unit: zeros -------------------------
+    {
+      // per pooled row: columns 0 and Wo+1; band 0 also the separator row above the image; the last
+      // unit also the tail [N*RHp*PWp, Lpp)
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      const int rows = r1 - r0;
+      for (int i = tid; i < rows * 2 * 4; i += kCpThreadsF) {
+        const int pl_ = i & 3, side = (i >> 2) & 1, rr = i >> 3;
+        const size_t sp = (size_t)(n * a.RHp + r0 + rr + 1) * a.PWp + (side ? a.Wo + 1 : 0);
+        a.praw[(size_t)pl_ * a.Lpp + sp] = z;
+        a.prelu[(size_t)pl_ * a.Lpp + sp] = z;
+      }
+      if (band == 0) {
+        for (int i = tid; i < a.PWp * 4; i += kCpThreadsF) {
+          const int pl_ = i & 3, cc = i >> 2;
+          const size_t sp = (size_t)(n * a.RHp) * a.PWp + cc;
+          a.praw[(size_t)pl_ * a.Lpp + sp] = z;
+          a.prelu[(size_t)pl_ * a.Lpp + sp] = z;
+        }
+      }
+      if (u == units - 1) {
+        const int t0 = a.N * a.RHp * a.PWp;
+        for (int i = tid; i < (a.Lpp - t0) * 4; i += kCpThreadsF) {
+          const int pl_ = i & 3, cc = i >> 2;
+          a.praw[(size_t)pl_ * a.Lpp + t0 + cc] = z;
+          a.prelu[(size_t)pl_ * a.Lpp + t0 + cc] = z;
+        }
+      }
+    }
+    __syncthreads();      // s_out and the pair array are rewritten by the next unit
+  }
+  if (timed_out && a.err) atomicExch(a.err, 1);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+  }
+}
+
+bool conv0pool_supported(int cin, int cout, int H, int W) {
+  return cin == 4 && cout == 16 && (2 * kCpRows + 1) * (W + 2) <= kCpMaxBlocks * 128 && H >= 3 && W >= 3;
+}
+
+int conv0pool_forward(int N, int H, int W, const uint8_t* frames, const float* w, const float* bias, void* praw,
+                      void* prelu, uint8_t* idx, int* err, cudaStream_t st) {
+  Conv0PoolArgs a;
+  a.N = N; a.H = H; a.W = W;
+  same_pad3s2_(H, &a.Ho, &a.pt);
+  same_pad3s2_(W, &a.Wo, &a.pl);
+  a.Lpp = (int)planes_positions(N, a.Ho, a.Wo); a.PWp = a.Wo + 2; a.RHp = a.Ho + 1;
+  fast_div_setup((unsigned int)(W + 2), &a.sw_mul, &a.sw_sh);
+  a.frames = frames; a.w = w; a.bias = bias;
+  a.praw = reinterpret_cast<uint4*>(praw); a.prelu = reinterpret_cast<uint4*>(prelu); a.idx = idx; a.err = err;
+  const size_t smem = (size_t)(kCpMaxBlocks * 128 + 2 * (W + 2) + 8) * 16 +
+                      (size_t)kCpMaxBlocks * 128 * kCpOutStride * 4 + 128 + 48 * 32 * 2 + 16 * 4 + 64;
+  static bool attr = false;
+  if (!attr) {
+    SEEDRL_CUDA(cudaFuncSetAttribute(conv0pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    attr = true;
+  }
+  if (smem > 110 * 1024) return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "conv0pool: image too wide");
+  const int units = N * ((a.Ho + kCpRows - 1) / kCpRows);
+  const int grid = units < 2 * kNumSMs ? units : 2 * kNumSMs;
+  conv0pool_kernel<<<grid, kCpThreadsF, smem, st>>>(a);
+  count_launch(PC_CONV_FWD, st);
+  SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
 }
 

@@ -125,6 +125,9 @@ int poolp_backward(int N, int H, int W, int C, const void* dy, const uint8_t* id
 bool first_wgrad_pooled_supported(int cin, int cout, int H, int W);
 int first_wgrad_pooled(int N, int H, int W, const uint8_t* frames, const void* g_planes, const uint8_t* idx,
                        float* dw, float* db, WgradBatch* batch, cudaStream_t st);
+bool conv0pool_supported(int cin, int cout, int H, int W);
+int conv0pool_forward(int N, int H, int W, const uint8_t* frames, const float* w, const float* bias, void* praw,
+                      void* prelu, uint8_t* idx, int* err, cudaStream_t st);
 
 // conv_kernels.cu
 int conv3x3_forward(int cin, int cout, int in_mode, int N, int H, int W, const void* in,

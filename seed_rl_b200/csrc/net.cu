@@ -109,6 +109,7 @@ struct Plan {
   // backward scratch
   size_t dhs, dz, dhrec, dc0, dc1, dd, gA, gB, gC, gFull, wt, partial, wq, tcerr, counter, gemm_ws, wq_all, partial_all;
   size_t gP1, gP2, gP3, gFP;   // conv_mode 3: plane-tensor gradients (pooled resolution x3, full resolution)
+  size_t obs4, w0pad, dw0pad;  // 3-channel frames: zero-padded frames / first-conv weights / their gradient
   size_t total;
 };
 
@@ -172,6 +173,12 @@ static Plan make_plan(const seedrl_net* n, int T1, int B) {
   p.dc0 = b.take((size_t)B * kHidden * 4);
   p.dc1 = b.take((size_t)B * kHidden * 4);
   p.dd = b.take(N * kHidden * 4);
+  p.obs4 = p.w0pad = p.dw0pad = 0;
+  if (n->cfg.net == SEEDRL_NET_DEEP && n->cfg.obs_c == 3) {
+    p.obs4 = b.take(N * n->cfg.obs_h * n->cfg.obs_w * 4);
+    p.w0pad = b.take(9 * 4 * 16 * 4);
+    p.dw0pad = b.take(9 * 4 * 16 * 4);
+  }
   p.gA = b.take(pooled_max * 4);
   p.gB = p.gC = p.gP1 = p.gP2 = p.gP3 = p.gFP = 0;
   if (!planes) {
@@ -202,11 +209,40 @@ static Plan make_plan(const seedrl_net* n, int T1, int B) {
     if (rc__ != SEEDRL_OK) return rc__; \
   } while (0)
 
+// 3-channel frames (DMLab's 72x96x3, dmlab/env.py:44-54): the first convolution's kernels are built
+// for 4 input channels, so a forward/backward call works on a zero-padded copy of the frames and of
+// the first conv's weights ([3,3,3,16] -> [3,3,4,16]); its weight gradient is computed in the padded
+// shape and copied back without the 4th channel.  These thread-local overrides redirect the one
+// parameter for the duration of a call.
+static thread_local int t_w0_index = -1;
+static thread_local const float* t_w0_pad = nullptr;
+static thread_local float* t_dw0_pad = nullptr;
 static inline const float* P(const seedrl_net* n, const float* arena, int idx) {
+  if (idx == t_w0_index && t_w0_pad) return t_w0_pad;
   return arena + n->params[idx].offset;
 }
 static inline float* G(const seedrl_net* n, float* arena, int idx) {
+  if (idx == t_w0_index && t_dw0_pad) return t_dw0_pad;
   return arena + n->params[idx].offset;
+}
+
+__global__ void pad_frames3_kernel(size_t npix, const uint8_t* __restrict__ src, uchar4* __restrict__ dst) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  dst[i] = make_uchar4(src[3 * i], src[3 * i + 1], src[3 * i + 2], 0);
+}
+// w[tap][3][co] <-> wp[tap][4][co]
+__global__ void pad_w0_kernel(int cout, const float* __restrict__ w, float* __restrict__ wp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 9 * 4 * cout) return;
+  const int co = i % cout, ci = (i / cout) % 4, tap = i / (4 * cout);
+  wp[i] = ci < 3 ? w[(tap * 3 + ci) * cout + co] : 0.f;
+}
+__global__ void unpad_dw0_kernel(int cout, const float* __restrict__ dwp, float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 9 * 3 * cout) return;
+  const int co = i % cout, ci = (i / cout) % 3, tap = i / (3 * cout);
+  dw[i] = dwp[(tap * 4 + ci) * cout + co];
 }
 template <typename T>
 static inline T* W(void* ws, size_t off) {
@@ -232,6 +268,7 @@ struct StepCtx {
   WgradBatch wb;
 };
 static thread_local StepCtx* t_ctx = nullptr;
+static thread_local void* t_head_ready = nullptr;   // cudaEvent_t recorded by seedrl_net_backward_overlap
 // test hook: 1 = keep the dense (pool backward + full-resolution weight gradient) first-layer path
 static int g_first_dense = 0;
 
@@ -292,6 +329,29 @@ static int run_conv(const seedrl_net* n, void* ws, const Plan& pl, int cin, int 
   return conv3x3_forward(cin, cout, in_mode, N, H, Wd, in, w, bias, mask, res, out, st);
 }
 
+// Scope of one forward/backward call on 3-channel frames: builds the padded frames and first-conv
+// weights in the workspace and installs the parameter overrides; no-op for 4-channel frames.
+struct PadScope {
+  int rc = SEEDRL_OK;
+  bool active = false;
+  const uint8_t* obs;
+  PadScope(const seedrl_net* n, const float* prm, const Plan& pl, const uint8_t* observation, void* ws,
+           cudaStream_t st) : obs(observation) {
+    if (n->cfg.net != SEEDRL_NET_DEEP || n->cfg.obs_c != 3) return;
+    active = true;
+    const size_t npix = (size_t)pl.N * n->cfg.obs_h * n->cfg.obs_w;
+    pad_frames3_kernel<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(npix, observation, W<uchar4>(ws, pl.obs4));
+    count_launch(PC_MISC, st);
+    const int wi = n->stacks[0].conv.w;
+    pad_w0_kernel<<<ceil_div(9 * 4 * 16, 128), 128, 0, st>>>(16, prm + n->params[wi].offset, W<float>(ws, pl.w0pad));
+    count_launch(PC_MISC, st);
+    if (cudaGetLastError() != cudaSuccess) rc = set_error(SEEDRL_ERR_INTERNAL, "3-channel padding launch failed");
+    obs = W<uint8_t>(ws, pl.obs4);
+    t_w0_index = wi; t_w0_pad = W<float>(ws, pl.w0pad); t_dw0_pad = W<float>(ws, pl.dw0pad);
+  }
+  ~PadScope() { t_w0_index = -1; t_w0_pad = nullptr; t_dw0_pad = nullptr; }
+};
+
 }  // namespace seedrl
 
 using namespace seedrl;
@@ -310,10 +370,10 @@ extern "C" int seedrl_net_create(const seedrl_net_config* cfg, seedrl_net** out)
   n->p_base_b = add_param(n, "baseline/bias", {1});
   int flat = 0;
   if (cfg->net == SEEDRL_NET_DEEP) {
-    if (cfg->obs_c != 4) {
+    if (cfg->obs_c != 4 && cfg->obs_c != 3) {
       delete n;
       return set_error(SEEDRL_ERR_INVALID_ARGUMENT,
-                       "seedrl_net_create: deep net kernels are built for 4-channel uint8 frames");
+                       "seedrl_net_create: the deep net takes 3- or 4-channel uint8 frames");
     }
     int h = cfg->obs_h, w = cfg->obs_w;
     const int chans[3] = {16, 32, 32};
@@ -338,9 +398,10 @@ extern "C" int seedrl_net_create(const seedrl_net_config* cfg, seedrl_net** out)
     for (int s = 0; s < 3; ++s) {
       Stack st;
       const std::string pre = "stack" + std::to_string(s);
-      st.hin = h; st.win = w; st.cin = c; st.c = chans[s];
+      st.hin = h; st.win = w; st.cin = (s == 0 && c == 3) ? 4 : c; st.c = chans[s];
       st.hout = (h + 1) / 2; st.wout = (w + 1) / 2;
-      st.conv = add_conv(n, pre + "/conv", 3, c, st.c);
+      st.conv = add_conv(n, pre + "/conv", 3, c, st.c);      // the parameter keeps the frame's channel count
+      st.conv.cin = st.cin;                                  // ... the kernels see the padded one
       // tf.Module order inside _Stack: _conv, _res_convs0[0..1], _res_convs1[0..1]
       st.r00 = add_conv(n, pre + "/res_0/conv2d_0", 3, st.c, st.c);
       st.r10 = add_conv(n, pre + "/res_1/conv2d_0", 3, st.c, st.c);
@@ -459,13 +520,19 @@ static int torso_forward_planes(const seedrl_net* n, const float* prm, const Pla
     void* c0r = W<void>(ws, b.c0r); void* o0raw = W<void>(ws, b.o0raw);
     void* o0relu = W<void>(ws, b.o0relu); void* c1r = W<void>(ws, b.c1r);
     const bool last = s + 1 == ns;
-    if (s == 0)
-      SEEDRL_TRY(run_conv(n, ws, pl, k.cin, k.c, IN_U8, N, k.hin, k.win, obs, P(n, prm, k.conv.w),
-                          P(n, prm, k.conv.b), nullptr, nullptr, a0, 0, st));
-    else
-      SEEDRL_TRY(planes_conv(n, ws, pl, k.cin, k.c, N, k.hin, k.win, prev, P(n, prm, k.conv.w), 0,
-                             P(n, prm, k.conv.b), nullptr, nullptr, nullptr, nullptr, a0, st));
-    SEEDRL_TRY(poolp_forward(N, k.hin, k.win, k.c, a0, praw, prelu, W<uint8_t>(ws, b.idx), st));
+    if (s == 0 && conv0pool_supported(k.cin, k.c, k.hin, k.win) && !g_first_dense) {
+      // first conv + bias + max-pool in one kernel: the full-resolution activation never reaches HBM
+      SEEDRL_TRY(conv0pool_forward(N, k.hin, k.win, obs, P(n, prm, k.conv.w), P(n, prm, k.conv.b), praw, prelu,
+                                   W<uint8_t>(ws, b.idx), W<int>(ws, pl.tcerr), st));
+    } else {
+      if (s == 0)
+        SEEDRL_TRY(run_conv(n, ws, pl, k.cin, k.c, IN_U8, N, k.hin, k.win, obs, P(n, prm, k.conv.w),
+                            P(n, prm, k.conv.b), nullptr, nullptr, a0, 0, st));
+      else
+        SEEDRL_TRY(planes_conv(n, ws, pl, k.cin, k.c, N, k.hin, k.win, prev, P(n, prm, k.conv.w), 0,
+                               P(n, prm, k.conv.b), nullptr, nullptr, nullptr, nullptr, a0, st));
+      SEEDRL_TRY(poolp_forward(N, k.hin, k.win, k.c, a0, praw, prelu, W<uint8_t>(ws, b.idx), st));
+    }
     const int H = k.hout, Wd = k.wout, C = k.c;
     // res block 0: c0 = conv00(relu(p)); o0 = conv01(relu(c0)) + p        (networks.py:52-58)
     SEEDRL_TRY(planes_conv(n, ws, pl, C, C, N, H, Wd, prelu, P(n, prm, k.r00.w), 0, P(n, prm, k.r00.b), nullptr,
@@ -531,6 +598,9 @@ extern "C" int seedrl_net_forward(const seedrl_net* n, const float* prm, int T1,
   if (n->cfg.net == SEEDRL_NET_DEEP) {
     StepCtx ctx;
     ctx.wb = WgradBatch{nullptr, 0, 0, 0, {}};
+    PadScope pad(n, prm, pl, observation, ws, st);
+    SEEDRL_TRY(pad.rc);
+    observation = pad.obs;
     SEEDRL_TRY(pack_all_weights(n, prm, ws, pl, 0, &ctx, st));
     t_ctx = &ctx;
     const int rc_t = n->conv_mode == 3 ? torso_forward_planes(n, prm, pl, observation, ws, st)
@@ -819,6 +889,9 @@ extern "C" int seedrl_net_backward(const seedrl_net* n, const float* prm, int T1
   SEEDRL_TRY(run_gemm(n, ws, pl, true, false, n->flat, kHidden, N, flat_src, n->flat, dd, kHidden,
                    G(n, grd, n->p_dense_w), kHidden, ea, st));
   SEEDRL_TRY(colsum(N, kHidden, dd, kHidden, G(n, grd, n->p_dense_b), st));
+  // every gradient of the arena's first bucket (heads, Dense, LSTM: floats [0, seedrl_net_grad_split))
+  // is final here -- the conv torso's backward below only writes the second bucket
+  if (t_head_ready) SEEDRL_CUDA(cudaEventRecord((cudaEvent_t)t_head_ready, st));
   GemmEpi ef = epi_none();
   ef.mask = flat_src; ef.ldm = n->flat;
   SEEDRL_TRY(run_gemm(n, ws, pl, false, true, N, n->flat, kHidden, dd, kHidden, P(n, prm, n->p_dense_w), kHidden,
@@ -826,15 +899,46 @@ extern "C" int seedrl_net_backward(const seedrl_net* n, const float* prm, int T1
   if (n->cfg.net == SEEDRL_NET_DEEP) {
     StepCtx ctx;
     ctx.wb = WgradBatch{W<float>(ws, pl.partial_all), kPartialAllBytes / sizeof(float), 0, 0, {}};
+    PadScope pad(n, prm, pl, observation, ws, st);
+    SEEDRL_TRY(pad.rc);
+    observation = pad.obs;
     SEEDRL_TRY(pack_all_weights(n, prm, ws, pl, 1, &ctx, st));
     t_ctx = &ctx;
     int rc_t = n->conv_mode == 3 ? torso_backward_planes(n, prm, grd, pl, observation, ws, st)
                                  : torso_backward_deep(n, prm, grd, pl, observation, ws, st);
     t_ctx = nullptr;
     if (rc_t == SEEDRL_OK) rc_t = wgrad_reduce_batch(&ctx.wb, st);
+    if (rc_t == SEEDRL_OK && pad.active) {        // padded [3,3,4,16] gradient -> the [3,3,3,16] parameter slot
+      unpad_dw0_kernel<<<ceil_div(9 * 3 * 16, 128), 128, 0, st>>>(16, W<float>(ws, pl.dw0pad),
+                                                                   grd + n->params[n->stacks[0].conv.w].offset);
+      count_launch(PC_MISC, st);
+    }
     return rc_t;
   }
   return torso_backward_shallow(n, prm, grd, pl, observation, ws, st);
+}
+
+// Data-parallel overlap (the one exchange step): same as seedrl_net_backward, and
+// `head_ready_event` (a cudaEvent_t) is recorded on `stream` as soon as the gradients of the first
+// arena bucket -- floats [0, seedrl_net_grad_split(net)): baseline, conv_to_linear, core,
+// policy_logits = 94 % of ImpalaDeep's parameters -- are final, i.e. before the convolution torso's
+// backward (about half of the backward's time): the caller all-reduces that bucket on a side
+// stream while the torso runs, then the remaining bucket.
+extern "C" int seedrl_net_backward_overlap(const seedrl_net* n, const float* prm, int T1, int B,
+                                           const int64_t* prev_actions, const float* reward, const uint8_t* done,
+                                           const uint8_t* observation, const float* dlogits, const float* dbaseline,
+                                           float* grd, void* ws, size_t ws_bytes, void* head_ready_event,
+                                           seedrl_stream_t stream) {
+  t_head_ready = head_ready_event;
+  const int rc = seedrl_net_backward(n, prm, T1, B, prev_actions, reward, done, observation, dlogits, dbaseline, grd,
+                                     ws, ws_bytes, stream);
+  t_head_ready = nullptr;
+  return rc;
+}
+extern "C" size_t seedrl_net_grad_split(const seedrl_net* n) {
+  if (!n) return 0;
+  const int first_conv = n->cfg.net == SEEDRL_NET_DEEP ? n->stacks[0].conv.w : n->sh_c0w;
+  return n->params[first_conv].offset;
 }
 
 // ---- single-kernel test hooks (exported so the GPU parity tests can localise a
@@ -914,6 +1018,12 @@ extern "C" int seedrl_debug_conv3x3_wgrad_tc(int cin, int cout, int in_mode, int
 }
 // Bench knob: output positions per tile of the tensor-core forward / data-gradient kernel
 // (the largest of 512/256/128 not above `mt` that keeps >= 2 CTAs per SM is used; default 512).
+extern "C" int seedrl_debug_conv0pool(int N, int H, int W, const uint8_t* frames, const float* w, const float* bias,
+                                      void* praw, void* prelu, uint8_t* idx, int* err, seedrl_stream_t stream) {
+  SEEDRL_CHECK_ARG(frames && w && bias && praw && prelu && idx && err, "null pointer");
+  SEEDRL_CHECK_ARG(conv0pool_supported(4, 16, H, W), "unsupported frame size");
+  return conv0pool_forward(N, H, W, frames, w, bias, praw, prelu, idx, err, (cudaStream_t)stream);
+}
 extern "C" int seedrl_debug_set_first_layer_dense(int on) {
   g_first_dense = on ? 1 : 0;
   return SEEDRL_OK;

@@ -231,16 +231,31 @@ class _CudaAgent(object):
       out = AgentOutput(*(t.squeeze(0) for t in out))
     return out, (h, c)
 
-  def backward(self, dlogits, dbaseline):
-    """d loss / d parameters for the last is_training unroll -> self.grads (overwritten)."""
+  def backward(self, dlogits, dbaseline, head_ready_event=None):
+    """d loss / d parameters for the last is_training unroll -> self.grads (overwritten).
+    head_ready_event: a torch.cuda.Event recorded once grads[:self.grad_split] (heads, Dense,
+    LSTM) are final -- before the convolution torso's backward -- for an overlapped all-reduce."""
     if self._saved is None:
       raise RuntimeError('backward() needs a preceding __call__(..., unroll=True, is_training=True)')
     T1, B, prev_actions, reward, done, frame, ws = self._saved
-    _lib.check(_lib.lib().seedrl_net_backward(
-        self._h, _lib.ptr(self.params), T1, B, _lib.ptr(prev_actions), _lib.ptr(reward),
-        _lib.ptr(done), _lib.ptr(frame), _lib.ptr(dlogits), _lib.ptr(dbaseline),
-        _lib.ptr(self.grads), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+    L = _lib.lib()
+    if head_ready_event is None:
+      _lib.check(L.seedrl_net_backward(
+          self._h, _lib.ptr(self.params), T1, B, _lib.ptr(prev_actions), _lib.ptr(reward),
+          _lib.ptr(done), _lib.ptr(frame), _lib.ptr(dlogits), _lib.ptr(dbaseline),
+          _lib.ptr(self.grads), _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
+    else:
+      head_ready_event.record()        # creates the underlying cudaEvent_t; re-recorded by the library
+      _lib.check(L.seedrl_net_backward_overlap(
+          self._h, _lib.ptr(self.params), T1, B, _lib.ptr(prev_actions), _lib.ptr(reward),
+          _lib.ptr(done), _lib.ptr(frame), _lib.ptr(dlogits), _lib.ptr(dbaseline),
+          _lib.ptr(self.grads), _lib.ptr(ws), ws.numel(), ctypes.c_void_p(head_ready_event.cuda_event),
+          _lib.stream_ptr()))
     return self.grads
+
+  @property
+  def grad_split(self):
+    return int(_lib.lib().seedrl_net_grad_split(self._h))
 
   # learner.py:225-234 adds these to the agent when it has no entropy_cost()
   def init_entropy_cost(self, entropy_cost, adjustment_speed):
