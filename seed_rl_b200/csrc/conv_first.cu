@@ -20,11 +20,12 @@ namespace seedrl {
 
 constexpr int kFwThreads = 256;
 constexpr int kFwCo = 16;
-constexpr int kFwBands = 4;
+constexpr int kFwRowsPerBand = 6;   // pooled rows per work unit
 
 struct FirstWgradArgs {
   int N, H, W, Ho, Wo, pt, pl;
   int Lpp, PWp, RHp;             // pooled plane-tensor geometry
+  int rb;                        // pooled rows per work unit
   const uint8_t* frames;         // [N,H,W,4]
   const uint4* g;                // pooled gradient planes: 2 hi planes then 2 lo planes, [Lpp] x 16 B
   const uint8_t* idx;            // [N,Ho,Wo,16] window tap kh*3+kw of the forward arg-max
@@ -33,72 +34,72 @@ struct FirstWgradArgs {
 
 __global__ void __launch_bounds__(kFwThreads, 3) first_wgrad_pooled_kernel(const FirstWgradArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  uint2* s_x = reinterpret_cast<uint2*>(smem_raw);               // [(H+2)][(W+2)] pixels x 4 bf16
   const int tid = threadIdx.x;
   const int co = tid & (kFwCo - 1), ql = tid >> 4;               // 16 pooled-pixel lanes
-  const int SW = a.W + 2, SH = a.H + 2;
-  const int nq = a.Ho * a.Wo;
+  const int SW = a.W + 2;
+  const int RB = a.rb;                                           // pooled rows per band
+  const int SR = 2 * RB + 3;                                     // staged frame rows (incl. the two border rows)
+  uint2* s_x = reinterpret_cast<uint2*>(smem_raw);               // [SR][SW] pixels x 4 bf16
+  float* s_g = reinterpret_cast<float*>(s_x + SR * SW);          // [RB*Wo][16] pooled gradient (hi + lo)
+  uint8_t* s_t = reinterpret_cast<uint8_t*>(s_g + RB * a.Wo * kFwCo);   // [RB*Wo][16] arg-max taps
   float acc[36];
 #pragma unroll
   for (int i = 0; i < 36; ++i) acc[i] = 0.f;
   float accb = 0.f;
-  // zero border once (the interior is rewritten per frame)
-  for (int i = tid; i < SH * SW; i += kFwThreads) s_x[i] = make_uint2(0u, 0u);
-  __syncthreads();
-  const unsigned short* gh = reinterpret_cast<const unsigned short*>(a.g);
-  const size_t lo_off = (size_t)2 * a.Lpp * 8;                   // in bf16 elements: 2 hi planes
-  const size_t plane_off = (size_t)(co >> 3) * a.Lpp * 8 + (co & 7);
-  // work unit = (frame, band of pooled rows): 4 bands per frame keep the static schedule balanced
-  // (1 344 frames over 444 CTA slots would leave a 4-vs-3 frame imbalance)
-  const int RB = (a.Ho + kFwBands - 1) / kFwBands;
-  const int units = a.N * kFwBands;
+  const int bands = (a.Ho + RB - 1) / RB;
+  const int units = a.N * bands;
+  // work unit = (frame, band of pooled rows): keeps the static schedule balanced and the staged
+  // working set small enough for 4+ CTAs per SM
   for (int u = blockIdx.x; u < units; u += gridDim.x) {
-    const int n = u / kFwBands, band = u - n * kFwBands;
+    const int n = u / bands, band = u - n * bands;
     const int r0 = band * RB, r1 = min(a.Ho, r0 + RB);
-    if (r0 >= r1) continue;
-    // ---- stage the frame rows this band's patches can touch: uint8 x4 -> 4 halves ----------------
-    const int fs = max(0, 2 * r0 - a.pt - 1), fe = min(a.H, 2 * (r1 - 1) - a.pt + 4);
-    const uchar4* src = reinterpret_cast<const uchar4*>(a.frames) + (size_t)n * a.H * a.W;
-    for (int i = fs * a.W + tid; i < fe * a.W; i += kFwThreads) {
-      const int h = i / a.W, w = i - h * a.W;
-      const uchar4 u4 = __ldg(src + i);
-      // bf16 pairs (exact for 0..255): the consumer turns them back into floats with one shift /
-      // one mask each (fp16 needed F2F conversions: the conversion pipe, not the FMAs, bounded the loop)
-      const uint32_t f0 = __float_as_uint((float)u4.x) >> 16, f1 = __float_as_uint((float)u4.y) & 0xFFFF0000u;
-      const uint32_t f2 = __float_as_uint((float)u4.z) >> 16, f3 = __float_as_uint((float)u4.w) & 0xFFFF0000u;
-      s_x[(h + 1) * SW + w + 1] = make_uint2(f0 | f1, f2 | f3);
+    const int nq = (r1 - r0) * a.Wo;
+    // ---- stage: frame rows f0 .. f0+SR-1 (zero outside the frame / at the two border columns) ----
+    const int f0 = 2 * r0 - a.pt - 1;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.frames) + (size_t)n * a.H * a.W;
+    for (int i = tid; i < SR * SW; i += kFwThreads) {
+      const int lr = i / SW, bc = i - lr * SW, fr = f0 + lr;
+      uint32_t w32 = 0u;
+      if (fr >= 0 && fr < a.H && bc >= 1 && bc <= a.W) w32 = __ldg(src + (size_t)fr * a.W + bc - 1);
+      // bf16 x 4 (exact for 0..255): the consumer turns them back into floats with one shift / mask each
+      const uint32_t f0_ = __float_as_uint(__uint_as_float(__byte_perm(w32, 0x4B000000u, 0x7540)) - 8388608.0f);
+      const uint32_t f1_ = __float_as_uint(__uint_as_float(__byte_perm(w32, 0x4B000000u, 0x7541)) - 8388608.0f);
+      const uint32_t f2_ = __float_as_uint(__uint_as_float(__byte_perm(w32, 0x4B000000u, 0x7542)) - 8388608.0f);
+      const uint32_t f3_ = __float_as_uint(__uint_as_float(__byte_perm(w32, 0x4B000000u, 0x7543)) - 8388608.0f);
+      s_x[i] = make_uint2(__byte_perm(f0_, f1_, 0x7632), __byte_perm(f2_, f3_, 0x7632));
+    }
+    // ---- stage: the band's pooled gradient (hi + lo planes -> fp32) and arg-max taps: coalesced
+    //      16-byte loads, all independent (the main loop then touches shared memory only) ----
+    for (int i = tid; i < nq * 2; i += kFwThreads) {
+      const int gq = i & 1, qq = i >> 1;
+      const int qr = qq / a.Wo, qw = qq - qr * a.Wo;
+      const size_t sp = (size_t)(n * a.RHp + r0 + qr + 1) * a.PWp + qw + 1;
+      const uint4 hh = __ldg(a.g + (size_t)gq * a.Lpp + sp), ll = __ldg(a.g + (size_t)(2 + gq) * a.Lpp + sp);
+      float4* dst = reinterpret_cast<float4*>(s_g + (size_t)qq * kFwCo + gq * 8);
+      dst[0] = make_float4(__uint_as_float(hh.x << 16) + __uint_as_float(ll.x << 16),
+                           __uint_as_float(hh.x & 0xFFFF0000u) + __uint_as_float(ll.x & 0xFFFF0000u),
+                           __uint_as_float(hh.y << 16) + __uint_as_float(ll.y << 16),
+                           __uint_as_float(hh.y & 0xFFFF0000u) + __uint_as_float(ll.y & 0xFFFF0000u));
+      dst[1] = make_float4(__uint_as_float(hh.z << 16) + __uint_as_float(ll.z << 16),
+                           __uint_as_float(hh.z & 0xFFFF0000u) + __uint_as_float(ll.z & 0xFFFF0000u),
+                           __uint_as_float(hh.w << 16) + __uint_as_float(ll.w << 16),
+                           __uint_as_float(hh.w & 0xFFFF0000u) + __uint_as_float(ll.w & 0xFFFF0000u));
+    }
+    {
+      const uint4* isrc = reinterpret_cast<const uint4*>(a.idx + ((size_t)n * a.Ho + r0) * a.Wo * kFwCo);
+      for (int i = tid; i < nq; i += kFwThreads) reinterpret_cast<uint4*>(s_t)[i] = __ldg(isrc + i);
     }
     __syncthreads();
-    const uint8_t* idx_n = a.idx + (size_t)n * nq * kFwCo;
-    // The arg-max tap and the gradient of pooled pixel q + 16 are fetched (L2 latency) while the 36
-    // FMAs of pixel q run: without this the loop is a chain of dependent global loads.
-    // (pooled row / column advance incrementally: one runtime division per unit, not per pixel;
-    //  32-bit element offsets)
-    const unsigned short* gh_n = gh + plane_off + (size_t)n * a.RHp * a.PWp * 8;
-    const int qend = r1 * a.Wo;
-    int q = r0 * a.Wo + ql;
-    int qh_n = q / a.Wo, qw_n = q - qh_n * a.Wo;
-    int t_n = 0;
-    uint32_t ghi_n = 0, glo_n = 0;
-    auto fetch = [&]() {
-      const int spo = ((qh_n + 1) * a.PWp + qw_n + 1) * 8;
-      t_n = idx_n[q * kFwCo + co];
-      ghi_n = gh_n[spo];
-      glo_n = gh_n[lo_off + spo];
-    };
-    if (q < qend) fetch();
-    while (q < qend) {
-      const int t = t_n, qh = qh_n, qw = qw_n;
-      const float gv = __uint_as_float(ghi_n << 16) + __uint_as_float(glo_n << 16);
-      q += kFwThreads / kFwCo;
-      qw_n += kFwThreads / kFwCo;
-      while (qw_n >= a.Wo) { qw_n -= a.Wo; ++qh_n; }
-      if (q < qend) fetch();
+    // ---- thread = (channel co, pooled-pixel lane): 9 x 8-byte patch loads + 36 FMAs per pixel ----
+    int qh = ql / a.Wo, qw = ql - qh * a.Wo;                    // band-local pooled row / column
+    for (int q = ql; q < nq; q += kFwThreads / kFwCo) {
+      const int t = s_t[q * kFwCo + co];
+      const float gv = s_g[q * kFwCo + co];
       const int kh = t / 3, kw = t - kh * 3;
-      // arg-max position in frame coordinates; its 3x3 patch starts at smem (ph, pw)
-      const int ph = qh * 2 - a.pt + kh, pw = qw * 2 - a.pl + kw;
+      // arg-max position (frame row 2*(r0+qh) - pt + kh); its 3x3 patch starts one row / column
+      // earlier = staged row 2*qh + kh, band column 2*qw - pl + kw
+      const uint2* patch = s_x + (2 * qh + kh) * SW + (2 * qw - a.pl + kw);
       accb += gv;
-      const uint2* patch = s_x + ph * SW + pw;
       uint2 v[9];
 #pragma unroll
       for (int dh = 0; dh < 3; ++dh)
@@ -112,11 +113,13 @@ __global__ void __launch_bounds__(kFwThreads, 3) first_wgrad_pooled_kernel(const
         c[2] = fmaf(gv, __uint_as_float(v[k].y << 16), c[2]);
         c[3] = fmaf(gv, __uint_as_float(v[k].y & 0xFFFF0000u), c[3]);
       }
+      qw += kFwThreads / kFwCo;
+      while (qw >= a.Wo) { qw -= a.Wo; ++qh; }
     }
-    __syncthreads();                       // the staged rows are rewritten by the next unit
+    __syncthreads();                       // the staged band is rewritten by the next unit
   }
   // ---- reduce the 16 pooled-pixel lanes per channel (fixed order) -> this CTA's partial ----------
-  float* s_red = reinterpret_cast<float*>(smem_raw);              // [16 ql][37][16 co] (frame buffer is free)
+  float* s_red = reinterpret_cast<float*>(smem_raw);              // [16 ql][37][16 co] (staging buffers are free)
 #pragma unroll
   for (int i = 0; i < 36; ++i) s_red[(ql * 37 + i) * kFwCo + co] = acc[i];
   s_red[(ql * 37 + 36) * kFwCo + co] = accb;
@@ -139,7 +142,9 @@ static void same_pad3s2_(int in, int* out, int* before) {
 }
 
 bool first_wgrad_pooled_supported(int cin, int cout, int H, int W) {
-  return cin == 4 && cout == 16 && (size_t)(H + 2) * (W + 2) * 8 <= 72 * 1024;
+  const int wo = (W + 1) / 2;
+  return cin == 4 && cout == 16 && H >= 3 && W >= 3 &&
+         (size_t)(2 * kFwRowsPerBand + 3) * (W + 2) * 8 + (size_t)kFwRowsPerBand * wo * kFwCo * 5 <= 70 * 1024;
 }
 
 // dW / db of the first convolution from the POOLED gradient planes + the pool's arg-max taps.
@@ -152,12 +157,15 @@ int first_wgrad_pooled(int N, int H, int W, const uint8_t* frames, const void* g
   a.N = N; a.H = H; a.W = W; a.Ho = Ho; a.Wo = Wo; a.pt = pt; a.pl = pl;
   a.Lpp = (int)planes_positions(N, Ho, Wo); a.PWp = Wo + 2; a.RHp = Ho + 1;
   a.frames = frames; a.g = reinterpret_cast<const uint4*>(g_planes); a.idx = idx;
-  size_t smem = (size_t)(H + 2) * (W + 2) * 8;
+  a.rb = kFwRowsPerBand < Ho ? kFwRowsPerBand : Ho;
+  size_t smem = (size_t)(2 * a.rb + 3) * (W + 2) * 8 + (size_t)a.rb * Wo * kFwCo * 5;
   const size_t red = (size_t)(kFwThreads / kFwCo) * 37 * kFwCo * 4;
   if (red > smem) smem = red;
+  smem = (smem + 127) / 128 * 128;
   const int NW = 36 * kFwCo + kFwCo;
+  const int units = N * ((Ho + a.rb - 1) / a.rb);
   int grid = 3 * kNumSMs;
-  if (grid > N * kFwBands) grid = N * kFwBands;
+  if (grid > units) grid = units;
   if (!batch || batch->n >= kMaxReduceJobs || batch->used + (size_t)grid * NW > batch->cap_floats)
     return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "first_wgrad_pooled: partial buffer too small");
   a.partial = batch->buf + batch->used;
@@ -269,25 +277,53 @@ __global__ void __launch_bounds__(kCpThreadsF, 2) conv0pool_kernel(const Conv0Po
   const int units = a.N * bands;
   uint32_t phase = 0;
   bool timed_out = false;
-  for (int u = blockIdx.x; u < units; u += gridDim.x) {
-    const int n = u / bands, band = u - n * bands;
-    const int r0 = band * kCpRows, r1 = min(a.Ho, r0 + kCpRows);
-    // conv rows this band's windows touch (clipped to the frame)
-    const int cr0 = max(0, 2 * r0 - a.pt), cr1 = min(H - 1, 2 * (r1 - 1) - a.pt + 2);
-    const int CR = cr1 - cr0 + 1, npos = CR * SW, nblk = (npos + 127) >> 7;
-    // ---- 1. pair array of band rows cr0-1 .. cr1+1 (band row lr, band column bc = frame column + 1) ----
+  // The raw pixels of the NEXT unit travel HBM -> registers while the current unit computes (the
+  // staging loop was a chain of exposed global-load latencies: 4 x ~700 clk of a 5 300-clk unit).
+  constexpr int kPre = 4;                                   // pair entries per thread: (2*rows+3)*SW <= 1024
+  uint32_t pre0[kPre], pre1[kPre];
+  auto unit_geom = [&](int u, int* n, int* r0, int* r1, int* cr0, int* cr1) {
+    *n = u / bands;
+    const int band = u - *n * bands;
+    *r0 = band * kCpRows; *r1 = min(a.Ho, *r0 + kCpRows);
+    *cr0 = max(0, 2 * *r0 - a.pt); *cr1 = min(H - 1, 2 * (*r1 - 1) - a.pt + 2);
+  };
+  auto prefetch = [&](int u) {
+    int n, r0, r1, cr0, cr1;
+    unit_geom(u, &n, &r0, &r1, &cr0, &cr1);
+    const int CR = cr1 - cr0 + 1;
     const uint32_t* src = reinterpret_cast<const uint32_t*>(a.frames) + (size_t)n * H * W;
-    for (int e = tid; e < (CR + 2) * SW; e += kCpThreadsF) {
-      const int lr = (int)(__umulhi((unsigned)e, a.sw_mul) >> a.sw_sh), bc = e - lr * SW;
-      const int fr = cr0 - 1 + lr;
-      uint2 p0 = make_uint2(0u, 0u), p1 = p0;
-      if (fr >= 0 && fr < H) {
-        const uint32_t* row = src + (size_t)fr * W;
-        if (bc >= 1 && bc <= W) p0 = u8x4_to_bf16x4(__ldg(row + bc - 1));
-        if (bc + 1 >= 1 && bc + 1 <= W) p1 = u8x4_to_bf16x4(__ldg(row + bc));        // e + 1 is the same row
+#pragma unroll
+    for (int k = 0; k < kPre; ++k) {
+      const int e = tid + k * kCpThreadsF;
+      pre0[k] = 0u; pre1[k] = 0u;
+      if (e < (CR + 2) * SW) {
+        const int lr = (int)(__umulhi((unsigned)e, a.sw_mul) >> a.sw_sh), bc = e - lr * SW;
+        const int fr = cr0 - 1 + lr;
+        if (fr >= 0 && fr < H) {
+          const uint32_t* row = src + (size_t)fr * W;
+          if (bc >= 1 && bc <= W) pre0[k] = __ldg(row + bc - 1);
+          if (bc + 1 <= W) pre1[k] = __ldg(row + bc);       // e + 1 is the same row; the last column pairs with zero
+        }
       }
-      s_p[e] = make_uint4(p0.x, p0.y, p1.x, p1.y);       // (the pair of a row's last column pairs with zero)
     }
+  };
+  if ((int)blockIdx.x < units) prefetch(blockIdx.x);
+  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+    int n, r0, r1, cr0, cr1;
+    unit_geom(u, &n, &r0, &r1, &cr0, &cr1);
+    const int band = u - n * bands;
+    const int CR = cr1 - cr0 + 1, npos = CR * SW, nblk = (npos + 127) >> 7;
+    // ---- 1. pair array of band rows cr0-1 .. cr1+1 (band row lr, band column bc = frame column + 1):
+    //      a zero byte quadruple converts to bf16 zeros, so out-of-frame entries need no special case ----
+#pragma unroll
+    for (int k = 0; k < kPre; ++k) {
+      const int e = tid + k * kCpThreadsF;
+      if (e < (CR + 2) * SW) {
+        const uint2 p0 = u8x4_to_bf16x4(pre0[k]), p1 = u8x4_to_bf16x4(pre1[k]);
+        s_p[e] = make_uint4(p0.x, p0.y, p1.x, p1.y);
+      }
+    }
+    if (u + (int)gridDim.x < units) prefetch(u + gridDim.x);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     // ---- 2. MMAs: one per kernel row and 128-position block -------------------------------------
