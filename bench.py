@@ -542,7 +542,8 @@ def main():
   cls = networks.ImpalaDeep if args.net == 'deep' else networks.ImpalaShallow
   agent = cls(A, OBS, seed=0, conv_mode=args.conv)   # same seed on every rank: replicas start identical
   opt = optimizers.Adam(optimizers.PolynomialDecay(4.8e-4, 10**6, 0.0), beta_1=0.0, epsilon=3.125e-7)
-  step = learner.LearnerStep(agent, opt, settings=learner.default_loss_settings(), grad_reduce='sum')
+  step = learner.LearnerStep(agent, opt, settings=learner.default_loss_settings(), grad_reduce='sum',
+                             overlap_reduce=os.environ.get('SEEDRL_OVERLAP_REDUCE', '1') != '0')
 
   def barrier():
     if world > 1:
@@ -640,8 +641,9 @@ def main():
     lo, hi = cs.clone(), cs.clone()
     dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     line['replicas_in_sync'] = bool((lo == hi).item())
-    line['grad_exchange'] = ('ncclAllReduce(SUM) in two buckets: heads+Dense+LSTM (94 %% of the %.2f MB arena) on a '
-                             'side stream during the conv backward, conv stacks after it' %
+    line['grad_exchange'] = (('ncclAllReduce(SUM) in two buckets: heads+Dense+LSTM (94 %% of the %.2f MB arena) on a '
+                              'side stream during the conv backward, conv stacks after it' if step.overlap_reduce else
+                              'one ncclAllReduce(SUM) of the %.2f MB arena after the backward') %
                              (agent.params.numel() * 4 / 1e6))
   peaks = {}
   try:

@@ -124,6 +124,7 @@ SIGNATURES = {
     'seedrl_r2d2_net_num_params': (c_size_t, [P]),
     'seedrl_r2d2_net_arena_floats': (c_size_t, [P]),
     'seedrl_r2d2_net_set_mode': (c_int, [P, c_int]),
+    'seedrl_r2d2_net_set_lstm_mode': (c_int, [P, c_int]),
     'seedrl_r2d2_net_param_info':
         (c_int, [P, c_int, ctypes.c_char_p, c_size_t, ctypes.POINTER(c_i64), ctypes.POINTER(c_int),
                  ctypes.POINTER(c_size_t)]),

@@ -201,4 +201,12 @@ int lstm_backward_persistent(int H, int T1, int B, const float* U, const uint8_t
                              const float* cs, const float* c0, const float* dhs, float* dz,
                              unsigned int* counter, int* err, cudaStream_t st);
 
+// lstm_tiled.cu: CTA = (batch tile, 16 hidden units), one barrier counter per batch tile
+int lstm_forward_tiled(int H, int T1, int B, const float* U, const uint8_t* done, float* z, const float* h0,
+                       const float* c0, float* hs, float* cs, float* hp, unsigned int* counter, int* err,
+                       cudaStream_t st);
+int lstm_backward_tiled(int H, int T1, int B, const float* U, const uint8_t* done, const float* gates,
+                        const float* cs, const float* c0, const float* dhs, float* dz, unsigned int* counter,
+                        int* err, cudaStream_t st);
+
 }  // namespace seedrl

@@ -48,7 +48,7 @@ struct seedrl_net {
   int sh_c0w, sh_c0b, sh_c1w, sh_c1b;      // shallow
   int sh_h1, sh_w1, sh_h2, sh_w2;
   int flat;                                // conv features fed to Dense(256)
-  int lstm_mode = 1;                       // 1 = persistent cooperative LSTM kernels, 0 = per-step launches
+  int lstm_mode = 2;                       // 2 = tiled persistent kernels (lstm_tiled.cu), 1 = first persistent form, 0 = per-step launches
   int conv_mode = 0;                       // 0 = fp32 SIMT, 1 = tcgen05 bf16, 2 = tcgen05 bf16x3 (fp32-faithful)
   int core_in;                             // 256 + 1 + A
 };
@@ -429,7 +429,7 @@ extern "C" int seedrl_net_num_param_tensors(const seedrl_net* net) {
 extern "C" size_t seedrl_net_num_params(const seedrl_net* net) { return net ? net->logical_params : 0; }
 extern "C" size_t seedrl_net_arena_floats(const seedrl_net* net) { return net ? net->arena_floats : 0; }
 extern "C" int seedrl_net_set_lstm_mode(seedrl_net* net, int mode) {
-  SEEDRL_CHECK_ARG(net && (mode == 0 || mode == 1), "mode must be 0 (per-step launches) or 1 (persistent)");
+  SEEDRL_CHECK_ARG(net && mode >= 0 && mode <= 2, "mode must be 0 (per-step launches), 1 (persistent, CTA = 2 units) or 2 (persistent, CTA = batch tile x 16 units)");
   net->lstm_mode = mode;
   return SEEDRL_OK;
 }
@@ -634,7 +634,11 @@ extern "C" int seedrl_net_forward(const seedrl_net* n, const float* prm, int T1,
   SEEDRL_CUDA(cudaMemcpyAsync(c0buf, c0, (size_t)B * kHidden * 4, cudaMemcpyDeviceToDevice, st));
   GemmEpi eacc = epi_none();
   eacc.accumulate = 1;
-  if (n->lstm_mode == 1) {
+  if (n->lstm_mode == 2) {
+    // one kernel for the whole recurrence, CTA = (batch tile, 16 units) (lstm_tiled.cu)
+    SEEDRL_TRY(lstm_forward_tiled(kHidden, T1, B, P(n, prm, n->p_core_u), done, z, h0, c0buf, hs, cs, hp,
+                                  W<unsigned int>(ws, pl.counter), W<int>(ws, pl.tcerr), st));
+  } else if (n->lstm_mode == 1) {
     // one cooperative kernel for the whole recurrence (lstm_persistent.cu)
     SEEDRL_TRY(lstm_forward_persistent(kHidden, T1, B, P(n, prm, n->p_core_u), done, z, h0, c0buf, hs, cs, hp,
                                        W<unsigned int>(ws, pl.counter), W<int>(ws, pl.tcerr), st));
@@ -856,6 +860,9 @@ extern "C" int seedrl_net_backward(const seedrl_net* n, const float* prm, int T1
   SEEDRL_TRY(run_gemm(n, ws, pl, false, true, N, kHidden, 1, dbaseline, 1, P(n, prm, n->p_base_w), 1, dhs, kHidden,
                    eacc, st));
   // BPTT
+  if (n->lstm_mode == 2)
+    SEEDRL_TRY(lstm_backward_tiled(kHidden, T1, B, P(n, prm, n->p_core_u), done, z, cs, c0buf, dhs, dz,
+                                   W<unsigned int>(ws, pl.counter), W<int>(ws, pl.tcerr), st));
   if (n->lstm_mode == 1)
     SEEDRL_TRY(lstm_backward_persistent(kHidden, T1, B, P(n, prm, n->p_core_u), done, z, cs, c0buf, dhs, dz,
                                         W<unsigned int>(ws, pl.counter), W<int>(ws, pl.tcerr), st));

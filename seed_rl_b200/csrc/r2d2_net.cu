@@ -40,6 +40,7 @@ struct RConv { int k, s, cin, cout, hin, win, hout, wout, w, b; };
 struct seedrl_r2d2_net {
   int A, H, W, C;
   int mode;                               // 0 = fp32 SIMT GEMMs, 2 = tcgen05 bf16x3
+  int lstm_mode = 2;                      // 2 = tiled persistent LSTM (lstm_tiled.cu), 1 = first persistent form
   std::vector<seedrl::RParam> params;
   size_t arena_floats, logical_params;
   seedrl::RConv conv[3];
@@ -347,6 +348,11 @@ extern "C" int seedrl_r2d2_net_set_mode(seedrl_r2d2_net* net, int mode) {
   net->mode = mode;
   return SEEDRL_OK;
 }
+extern "C" int seedrl_r2d2_net_set_lstm_mode(seedrl_r2d2_net* net, int mode) {
+  SEEDRL_CHECK_ARG(net && (mode == 1 || mode == 2), "mode must be 1 (persistent) or 2 (tiled persistent)");
+  net->lstm_mode = mode;
+  return SEEDRL_OK;
+}
 extern "C" int seedrl_r2d2_net_param_info(const seedrl_r2d2_net* net, int index, char* name_buf, size_t name_cap,
                                           int64_t* dims4, int* rank, size_t* offset_floats) {
   SEEDRL_CHECK_ARG(net && index >= 0 && index < (int)net->params.size(), "bad index");
@@ -411,8 +417,12 @@ extern "C" int seedrl_r2d2_net_forward(const seedrl_r2d2_net* n, const float* pr
   SEEDRL_TRY(r_gemm(n, ws, pl, false, false, N, 4 * kRH, CI, xc, CI, RP(n, prm, n->p_core_w), 4 * kRH, z, 4 * kRH, e,
                     st));
   SEEDRL_CUDA(cudaMemcpyAsync(c0buf, c0, (size_t)B * kRH * 4, cudaMemcpyDeviceToDevice, st));
-  SEEDRL_TRY(lstm_forward_persistent(kRH, T, B, RP(n, prm, n->p_core_u), done, z, h0, c0buf, hs, cs, hp,
-                                     RW<unsigned int>(ws, pl.counter), RW<int>(ws, pl.tcerr), st));
+  if (n->lstm_mode == 2)
+    SEEDRL_TRY(lstm_forward_tiled(kRH, T, B, RP(n, prm, n->p_core_u), done, z, h0, c0buf, hs, cs, hp,
+                                  RW<unsigned int>(ws, pl.counter), RW<int>(ws, pl.tcerr), st));
+  else
+    SEEDRL_TRY(lstm_forward_persistent(kRH, T, B, RP(n, prm, n->p_core_u), done, z, h0, c0buf, hs, cs, hp,
+                                       RW<unsigned int>(ws, pl.counter), RW<int>(ws, pl.tcerr), st));
   // dueling heads
   float* vh = RW<float>(ws, pl.vh); float* ah = RW<float>(ws, pl.ah);
   float* v = RW<float>(ws, pl.v); float* adv = RW<float>(ws, pl.adv);
@@ -480,8 +490,12 @@ extern "C" int seedrl_r2d2_net_backward(const seedrl_r2d2_net* n, const float* p
   SEEDRL_TRY(r_gemm(n, ws, pl, false, true, N, kRH, 512, dah, 512, RP(n, prm, n->p_ah_w), 512, dhs, kRH, e0, st));
   SEEDRL_TRY(r_gemm(n, ws, pl, false, true, N, kRH, 512, dvh, 512, RP(n, prm, n->p_vh_w), 512, dhs, kRH, eacc, st));
   // BPTT
-  SEEDRL_TRY(lstm_backward_persistent(kRH, T, B, RP(n, prm, n->p_core_u), done, z, cs, c0buf, dhs, dz,
-                                      RW<unsigned int>(ws, pl.counter), RW<int>(ws, pl.tcerr), st));
+  if (n->lstm_mode == 2)
+    SEEDRL_TRY(lstm_backward_tiled(kRH, T, B, RP(n, prm, n->p_core_u), done, z, cs, c0buf, dhs, dz,
+                                   RW<unsigned int>(ws, pl.counter), RW<int>(ws, pl.tcerr), st));
+  else
+    SEEDRL_TRY(lstm_backward_persistent(kRH, T, B, RP(n, prm, n->p_core_u), done, z, cs, c0buf, dhs, dz,
+                                        RW<unsigned int>(ws, pl.counter), RW<int>(ws, pl.tcerr), st));
   SEEDRL_TRY(r_gemm(n, ws, pl, true, false, kRH, 4 * kRH, N, hp, kRH, dz, 4 * kRH, RG(n, grd, n->p_core_u), 4 * kRH,
                     e0, st));
   SEEDRL_TRY(r_gemm(n, ws, pl, true, false, CI, 4 * kRH, N, xc, CI, dz, 4 * kRH, RG(n, grd, n->p_core_w), 4 * kRH, e0,

@@ -32,7 +32,7 @@ class _CudaAgent(object):
   _NET = None
 
   def __init__(self, num_actions, obs_shape=(84, 84, 4), seed=0, device=None, conv_mode='simt',
-               lstm_mode='persistent'):
+               lstm_mode='tiled'):
     """conv_mode selects the arithmetic of every contraction (3x3 convs, Dense, LSTM input
     projection, policy head): 'simt' = fp32 CUDA cores (the 2e-3 parity path), 'tc' = tcgen05
     tensor cores with bf16 operands and fp32 accumulation, 'tc3' = tcgen05 with bf16x3 split
@@ -52,10 +52,11 @@ class _CudaAgent(object):
       raise ValueError("conv_mode 'tc3p' is built for the deep net")
     self.conv_mode = conv_mode
     _lib.check(L.seedrl_net_set_conv_mode(h, modes[conv_mode]))
-    if lstm_mode not in ('persistent', 'stepwise'):
-      raise ValueError("lstm_mode must be 'persistent' or 'stepwise'")
+    lstm_modes = {'stepwise': 0, 'persistent': 1, 'tiled': 2}
+    if lstm_mode not in lstm_modes:
+      raise ValueError("lstm_mode must be 'tiled', 'persistent' or 'stepwise'")
     self.lstm_mode = lstm_mode
-    _lib.check(L.seedrl_net_set_lstm_mode(h, 1 if lstm_mode == 'persistent' else 0))
+    _lib.check(L.seedrl_net_set_lstm_mode(h, lstm_modes[lstm_mode]))
     self._n_tensors = L.seedrl_net_num_param_tensors(h)
     self.arena_floats = int(L.seedrl_net_arena_floats(h))
     self.num_params = int(L.seedrl_net_num_params(h))
