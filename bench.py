@@ -234,7 +234,7 @@ def conv_bytes_per_step_planes(N, cat):
   return tot, launches
 
 
-def inference_path_bench(agent, iters=200, warmup=30, N=64, num_envs=256, T=20, batch=64):
+def inference_path_bench(agent, iters=200, warmup=30, N=64, num_envs=256, T=20, batch=64, cuda_graph=None):
   """Hot path (1) of the north star: the batched central-inference step (reference
   agents/vtrace/learner.py:349-407) -- host batch -> H2D -> gather of the previous action / LSTM
   state -> T=1 ImpalaDeep forward -> in-kernel sampling -> write-back + unroll-store append ->
@@ -247,7 +247,7 @@ def inference_path_bench(agent, iters=200, warmup=30, N=64, num_envs=256, T=20, 
   from seed_rl_b200 import _lib
   from seed_rl_b200.agents.vtrace import learner_loop
   from seed_rl_b200.common import utils
-  host = learner_loop.InferenceHost(agent, num_envs, T, N, OBS, training_batch_size=batch)
+  host = learner_loop.InferenceHost(agent, num_envs, T, N, OBS, training_batch_size=batch, cuda_graph=cuda_graph)
   stop = []
 
   def drain():
@@ -287,16 +287,21 @@ def inference_path_bench(agent, iters=200, warmup=30, N=64, num_envs=256, T=20, 
   lat.sort()
   h2d = N * (28224 + 4 + 1 + 1 + 4) + N * 4 + N * 8
   return {
-      'what': 'central inference step (agents/vtrace/learner.py:349-407): host batch -> H2D -> gather prev '
-              'action/state -> T=1 ImpalaDeep forward (conv_mode %s) -> sample -> scatter + unroll-store append '
-              '-> actions D2H; public API InferenceHost.inference, no RPC transport' % agent.conv_mode,
+      'what': 'central inference step (agents/vtrace/learner.py:349-407): host batch -> pinned staging -> H2D -> '
+              '[gather prev action/state -> T=1 ImpalaDeep forward (conv_mode %s) -> sample -> scatter + '
+              'unroll-store append]%s -> actions D2H; public API InferenceHost.inference, no RPC transport' %
+              (agent.conv_mode, ' replayed as ONE CUDA graph' if host.use_graph else ''),
+      'cuda_graph': bool(host.use_graph),
       'inference_batch_size': N, 'num_envs': num_envs, 'iters': iters,
       'inferences_per_sec': N * iters / dt, 'us_per_batch_mean': dt / iters * 1e6,
       'us_per_batch_p50': lat[len(lat) // 2] * 1e6, 'us_per_batch_p99': lat[int(len(lat) * 0.99)] * 1e6,
       'library_launches_per_batch': launches, 'h2d_bytes_per_batch': h2d, 'd2h_bytes_per_batch': N * 8,
       'training_batches_assembled': len(stop),
       'bound': 'latency: 64 frames x 0.11 GFLOP = 7 GFLOP and 1.8 MB of frames per batch are ~10 us of '
-               'tensor / HBM time; the step is a chain of ~40 dependent small launches plus host glue',
+               'tensor / HBM time; the step is a chain of ~40 dependent small kernels (each pays its launch + '
+               'setup: TMEM allocation, weights into shared memory) + 1.8 MB H2D + host bookkeeping; replaying it '
+               'as a CUDA graph removes the CPU issue cost but not the dependent-kernel chain (measured: same '
+               'p50), so throughput scales with the inference batch size instead',
   }
 
 
@@ -764,6 +769,13 @@ def main():
     if rank == 0 and world == 1 and args.net == 'deep':
       try:
         line['inference_path'] = inference_path_bench(agent)
+        eager = inference_path_bench(agent, cuda_graph=False)
+        line['inference_path']['without_cuda_graph'] = {k: eager[k] for k in (
+            'inferences_per_sec', 'us_per_batch_mean', 'us_per_batch_p50', 'library_launches_per_batch')}
+        big = inference_path_bench(agent, N=256, num_envs=1024, iters=100, warmup=20)
+        line['inference_path']['at_inference_batch_256'] = {k: big[k] for k in (
+            'inference_batch_size', 'num_envs', 'inferences_per_sec', 'us_per_batch_mean', 'us_per_batch_p50',
+            'h2d_bytes_per_batch')}
       except Exception as exc:        # pylint: disable=broad-except
         line['inference_path'] = {'unavailable': repr(exc)[:300]}
 

@@ -72,6 +72,11 @@ int seedrl_categorical_sample(int N, int A, const float* logits,
                               const float* gumbel_noise, uint64_t seed,
                               uint64_t offset, int64_t* actions,
                               seedrl_stream_t stream);
+/* Same draw, with the Philox offset read from and then incremented in device memory (*counter_dev):
+ * capturable in a CUDA graph (central inference replays one graph per batch). */
+int seedrl_categorical_sample_counter(int N, int A, const float* logits, const float* gumbel_noise,
+                                      uint64_t seed, uint64_t* counter_dev, int64_t* actions,
+                                      seedrl_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * (a2) Fused V-trace loss: the part of agents/vtrace/learner.py:82-157

@@ -72,6 +72,7 @@ SIGNATURES = {
     'seedrl_categorical_log_prob': (c_int, [c_int, c_int, P, P, P, P]),
     'seedrl_categorical_entropy': (c_int, [c_int, c_int, P, P, P]),
     'seedrl_categorical_sample': (c_int, [c_int, c_int, P, P, c_u64, c_u64, P, P]),
+    'seedrl_categorical_sample_counter': (c_int, [c_int, c_int, P, P, c_u64, P, P, P]),
     'seedrl_vtrace_loss_scratch_bytes': (c_size_t, [c_int, c_int, c_int]),
     'seedrl_vtrace_loss_fwd_bwd':
         (c_int, [c_int, c_int, c_int, P, P, P, P, P, P, ctypes.POINTER(LossConfig), P,

@@ -36,7 +36,8 @@ class InferenceHost(object):
   """Everything `create_host` builds in the reference (learner.py:314-413) for one GPU."""
 
   def __init__(self, agent, num_envs, unroll_length, inference_batch_size, obs_shape,
-               num_action_repeats=1, device='cuda', info_queue=None, training_batch_size=None):
+               num_action_repeats=1, device='cuda', info_queue=None, training_batch_size=None,
+               cuda_graph=None):
     """training_batch_size: when given, completed unrolls are gathered straight into the columns
     of preallocated time-major training batches (`self.assembler`, utils.BatchAssembler: zero-copy
     minibatch assembly); otherwise they go through the reference's capacity-1 `unroll_queue` of
@@ -81,15 +82,121 @@ class InferenceHost(object):
         TS([N], 'float32', 'raw_reward'))
     self.output_specs = TS([N], 'int64', 'action')
     self.stream = torch.cuda.Stream(device=self.device) if self.device.type == 'cuda' else None
+    # CUDA-graph replay of the device side of a full inference batch (default with the assembler):
+    # gather -> T=1 forward -> sample -> write-back -> store append are ~40 small dependent launches
+    # whose CPU issue cost, not their GPU time, bounded the step.
+    self.use_graph = bool(cuda_graph if cuda_graph is not None else (self.assembler is not None))
+    self._graph = None
 
     @grpc.function(self.inference_specs, self.output_specs)
     def inference(env_ids, run_ids, env_outputs, raw_rewards):
       return self._inference(env_ids, run_ids, env_outputs, raw_rewards)
     self.inference = inference
 
+  # ---- CUDA-graph path ---------------------------------------------------------------------------
+  def _device_step(self, ids32, env_dev, rng_counter):
+    """Everything of one inference batch that runs on the device (learner.py:381-403), on static
+    buffers: captured once, replayed per batch."""
+    n = int(ids32.numel())
+    prev_actions = torch.empty([n], dtype=torch.int64, device=self.device)
+    prev_states = tuple(torch.empty([n, networks.LSTM_UNITS], dtype=torch.float32, device=self.device)
+                        for _ in range(2))
+    _lib.rows_multi([(self.actions._state[0], prev_actions, _lib.ROW_GATHER),
+                     (self.agent_states._state[0], prev_states[0], _lib.ROW_GATHER),
+                     (self.agent_states._state[1], prev_states[1], _lib.ROW_GATHER)], ids32)
+    agent_outputs, curr_states = self.agent(prev_actions, env_dev, prev_states, is_training=False,
+                                            rng_counter=rng_counter)
+    self.store.device_append(ids32, utils.flatten((prev_actions, env_dev, agent_outputs)))
+    _lib.rows_multi([(self.agent_states._state[0], curr_states[0].contiguous(), _lib.ROW_SCATTER),
+                     (self.agent_states._state[1], curr_states[1].contiguous(), _lib.ROW_SCATTER),
+                     (self.actions._state[0], agent_outputs.action.contiguous(), _lib.ROW_SCATTER)], ids32)
+    return prev_states, agent_outputs
+
+  def _build_graph(self):
+    N, dev = self.N, self.device
+    dt = utils.as_torch_dtype
+    self._g_ids = torch.zeros([N], dtype=torch.int32, device=dev)
+    self._g_env = utils.EnvOutput(*(torch.zeros([N] + list(s.shape), dtype=dt(s.dtype), device=dev)
+                                    for s in self.env_output_specs))
+    self._g_pin = [torch.zeros_like(t, device='cpu').pin_memory() for t in (self._g_ids,) + tuple(self._g_env)]
+    self._g_counter = torch.zeros([], dtype=torch.int64, device=dev)
+    with torch.cuda.stream(self.stream):
+      self._g_ids.copy_(torch.arange(N, dtype=torch.int32))       # distinct ids for the warm-up / capture
+      # warm-up on scratch copies of the mutable tables is not needed: the capture run below does
+      # not execute, and the one eager warm-up is undone by restoring the tables it touches
+      saved = [t.clone() for t in self.actions._state + self.agent_states._state + self.store._state] + \
+              [self.store._index.clone()]
+      self._device_step(self._g_ids, self._g_env, self._g_counter)   # eager: lazy inits (func attributes, workspaces)
+      for t, sv in zip(self.actions._state + self.agent_states._state + self.store._state + [self.store._index], saved):
+        t.copy_(sv)
+      self._g_counter.zero_()
+      self.stream.synchronize()
+      g = torch.cuda.CUDAGraph()
+      # thread_local: the learner thread may allocate / launch on its own stream during the capture
+      with torch.cuda.graph(g, stream=self.stream, capture_error_mode='thread_local'):
+        self._g_prev_states, self._g_out = self._device_step(self._g_ids, self._g_env, self._g_counter)
+      self._g_actions_pin = torch.zeros([N], dtype=torch.int64).pin_memory()
+    self._graph = g
+
+  def _inference_graph(self, env_ids, run_ids, env_outputs, raw_rewards):
+    """reference learner.py:351-405 with the device side as one graph replay."""
+    reward, done = np.asarray(env_outputs.reward), np.asarray(env_outputs.done)
+    previous = self.env_run_ids[env_ids]
+    self.env_run_ids[env_ids] = run_ids
+    reset_ids = env_ids[previous != run_ids]
+    if np.asarray(env_outputs.abandoned).any():                         # :368-370
+      raise ValueError('Abandoned done states are not supported in VTRACE.')
+    utils._check_no_duplicates(None, env_ids, 'inference batch')
+    with torch.cuda.stream(self.stream):
+      if self._graph is None:
+        self._build_graph()
+      if reset_ids.size:                                                # :353-366 (rare: eager)
+        logging.info('Environment ids needing reset: %s', reset_ids)
+        for t in self.env_infos:
+          t[reset_ids] = 0
+        self.store.reset(reset_ids)
+        init = self.agent.initial_state(len(reset_ids))
+        self.first_agent_states.replace(reset_ids, init)
+        self.agent_states.replace(reset_ids, init)
+        self.actions.reset(reset_ids)
+      self.env_infos[1][env_ids] += reward                              # :373-378
+      self.env_infos[2][env_ids] += np.asarray(raw_rewards)
+      done_ids = env_ids[done]
+      if self.info_queue is not None and done_ids.size:
+        self.info_queue.enqueue_many(tuple(torch.as_tensor(t[done_ids]) for t in self.env_infos))
+      for t in self.env_infos:
+        t[done_ids] = 0
+      self.env_infos[0][env_ids] += self.num_action_repeats
+      # inputs: host arrays -> pinned staging -> the graph's static device buffers
+      srcs = (env_ids.astype(np.int32),) + tuple(np.asarray(x) for x in env_outputs)
+      for pin, dst, src in zip(self._g_pin, (self._g_ids,) + tuple(self._g_env), srcs):
+        t = torch.from_numpy(np.ascontiguousarray(src))
+        if t.numel() >= 65536 and t.is_pinned():
+          dst.copy_(t, non_blocking=True)        # the batcher's slabs are pinned: DMA straight from them
+        else:
+          pin.numpy()[...] = src                 # small fields / pageable memory: own pinned staging
+          dst.copy_(pin, non_blocking=True)
+      self._graph.replay()
+      # completed unrolls (known on the host) -> columns of the training batch; first agent states
+      done_host, pos = self.store.host_advance(env_ids)
+      if done_host.size:
+        pos_dev = torch.as_tensor(pos.astype(np.int64)).to(self.device, non_blocking=True)
+        def on_placed(slot, col0, ids):
+          first = self.first_agent_states.read(ids.to(torch.int64))
+          for dst, src in zip(self.assembler._states[slot], first):
+            dst[col0:col0 + int(ids.numel())].copy_(src)
+        completed_ids, _ = self.store.complete_into(int(done_host.size), self.assembler, on_placed)
+        # the state the next unroll starts from = the state this step started from (:400-401)
+        self.first_agent_states.replace(completed_ids, tuple(s.index_select(0, pos_dev) for s in self._g_prev_states))
+      self._g_actions_pin.copy_(self._g_out.action, non_blocking=True)
+      self.stream.synchronize()
+    return self._g_actions_pin.numpy().copy()
+
   def _inference(self, env_ids, run_ids, env_outputs, raw_rewards):
     """reference learner.py:351-405."""
     env_ids = np.asarray(env_ids); run_ids = np.asarray(run_ids)
+    if self.use_graph and self.assembler is not None and len(env_ids) == self.N:
+      return self._inference_graph(env_ids, run_ids, env_outputs, raw_rewards)
     reward, done = np.asarray(env_outputs.reward), np.asarray(env_outputs.done)
     # Reset the environments that had their first run or crashed (:353-366).
     previous = self.env_run_ids[env_ids]

@@ -148,13 +148,25 @@ class UnrollStore(object):
   def append(self, env_ids, values, check_duplicates=True, into=None, on_placed=None):
     """Appends values; returns (completed env ids int64 [n], completed unrolls) -- or, with
     `into` (a BatchAssembler), (completed env ids, [(slot, first column, count)])."""
-    L = _lib.lib()
     ids, host = _ids_to_device(env_ids, self._device)
     if check_duplicates:
       _check_no_duplicates(ids, host, 'store %s' % self.name)
-    flat_values = flatten(values)
     assert_same_structure(values, self._specs)
-    n = int(ids.numel())
+    self.device_append(ids, flatten(values))
+    nc = None
+    if host is not None and self._host_index is not None:
+      nc = int(self.host_advance(host)[0].size)
+    else:
+      self._host_index = None          # ids live on the device only: fall back to reading the counter
+    if into is not None:
+      return self._complete_unrolls_into(nc, into, on_placed)
+    return self._complete_unrolls(nc)
+
+  def device_append(self, ids_i32, flat_values):
+    """The device half of `append` (:187-194): every field of the step into its ring row (ONE
+    launch) + the index advance / completed-id compaction.  No host work: capturable in a CUDA graph."""
+    L = _lib.lib()
+    n = int(ids_i32.numel())
     st = _lib.stream_ptr()
     keep = []
     for i, (s, v) in enumerate(zip(self._state, flat_values)):
@@ -164,28 +176,30 @@ class UnrollStore(object):
                          % self.name)
       keep.append(v)
     if n and len(keep) <= 16:
-      # every field of the step in ONE launch (seedrl_rows_multi, mode append)   :187-190
-      _lib.rows_multi([(s, v, _lib.ROW_APPEND) for s, v in zip(self._state, keep)], ids, index=self._index)
+      _lib.rows_multi([(s, v, _lib.ROW_APPEND) for s, v in zip(self._state, keep)], ids_i32, index=self._index)
     else:
       for i, (s, v) in enumerate(zip(self._state, keep)):
         _lib.check(L.seedrl_store_append_field(
-            _lib.ptr(s), _lib.ptr(self._index), _lib.ptr(ids), n, self._full_length,
+            _lib.ptr(s), _lib.ptr(self._index), _lib.ptr(ids_i32), n, self._full_length,
             self._row_bytes(i), _lib.ptr(v), st))
     _lib.check(L.seedrl_store_advance(
-        _lib.ptr(self._index), _lib.ptr(ids), n, self._full_length,
+        _lib.ptr(self._index), _lib.ptr(ids_i32), n, self._full_length,
         _lib.ptr(self._completed), _lib.ptr(self._ncomp), st))        # :194
-    nc = None
-    if host is not None and self._host_index is not None:
-      hid = np.asarray(host).astype(np.int64).reshape(-1)
-      self._host_index[hid] += 1
-      done_host = hid[self._host_index[hid] == self._full_length]      # in env_ids order, like the kernel
-      self._host_index[done_host] = 1 + self._num_overlapping_steps   # :254-255
-      nc = int(done_host.size)
-    else:
-      self._host_index = None          # ids live on the device only: fall back to reading the counter
-    if into is not None:
-      return self._complete_unrolls_into(nc, into, on_placed)
-    return self._complete_unrolls(nc)
+
+  def host_advance(self, host_ids):
+    """The host half: which of these environments complete an unroll with this step (a pure
+    function of the ids appended so far).  Returns (completed env ids, their positions in the
+    batch), in batch order -- the order the device kernel compacts them in."""
+    hid = np.asarray(host_ids).astype(np.int64).reshape(-1)
+    self._host_index[hid] += 1
+    pos = np.nonzero(self._host_index[hid] == self._full_length)[0]
+    done_host = hid[pos]
+    self._host_index[done_host] = 1 + self._num_overlapping_steps     # :254-255
+    return done_host, pos
+
+  def complete_into(self, nc, into, on_placed=None):
+    """Gathers the `nc` unrolls completed by the last device_append into `into`."""
+    return self._complete_unrolls_into(nc, into, on_placed)
 
   def _complete_unrolls_into(self, nc, into, on_placed=None):
     """Gathers the completed unrolls straight into free columns of `into` (a BatchAssembler): no

@@ -118,9 +118,11 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 // one thread per row (A is small); first max wins ties like np.argmax.
 __global__ void categorical_sample_kernel(int N, int A, const float* __restrict__ logits,
                                           const float* __restrict__ noise, uint64_t seed,
-                                          uint64_t offset, int64_t* __restrict__ actions) {
+                                          uint64_t offset, const uint64_t* __restrict__ offset_dev,
+                                          int64_t* __restrict__ actions) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
+  if (offset_dev) offset = *offset_dev;      // device-resident call counter (CUDA-graph replays)
   const float* l = logits + (size_t)n * A;
   float best = -INFINITY;
   int arg = 0;
@@ -1059,7 +1061,26 @@ extern "C" int seedrl_categorical_sample(int N, int A, const float* logits,
   if (N == 0) return SEEDRL_OK;
   SEEDRL_CHECK_ARG(logits && actions, "null pointer");
   categorical_sample_kernel<<<ceil_div(N, 128), 128, 0, (cudaStream_t)stream>>>(
-      N, A, logits, gumbel_noise, seed, offset, actions);
+      N, A, logits, gumbel_noise, seed, offset, nullptr, actions);
+  count_launch(PC_MISC, (cudaStream_t)stream);
+  SEEDRL_CHECK_LAUNCH();
+  return SEEDRL_OK;
+}
+
+__global__ void bump_counter_kernel(uint64_t* c) { *c += 1; }
+
+// Same, with the Philox offset read from (and then incremented in) device memory: the call can be
+// captured in a CUDA graph and still draw fresh noise on every replay.
+extern "C" int seedrl_categorical_sample_counter(int N, int A, const float* logits, const float* gumbel_noise,
+                                                 uint64_t seed, uint64_t* counter_dev, int64_t* actions,
+                                                 seedrl_stream_t stream) {
+  SEEDRL_CHECK_ARG(N >= 0 && A > 0, "bad N/A");
+  if (N == 0) return SEEDRL_OK;
+  SEEDRL_CHECK_ARG(logits && actions && counter_dev, "null pointer");
+  categorical_sample_kernel<<<ceil_div(N, 128), 128, 0, (cudaStream_t)stream>>>(
+      N, A, logits, gumbel_noise, seed, 0, counter_dev, actions);
+  count_launch(PC_MISC, (cudaStream_t)stream);
+  bump_counter_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter_dev);
   count_launch(PC_MISC, (cudaStream_t)stream);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;

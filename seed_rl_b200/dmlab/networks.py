@@ -191,7 +191,10 @@ class _CudaAgent(object):
     return self.__call__(*args, **kwargs)
 
   def __call__(self, prev_actions, env_outputs, core_state, unroll=False,
-               is_training=False, gumbel_noise=None):
+               is_training=False, gumbel_noise=None, rng_counter=None):
+    """rng_counter: optional int64 CUDA scalar tensor holding the Philox offset of the sampling
+    kernel; it is read and incremented ON THE DEVICE, which makes the whole call capturable in a
+    CUDA graph (InferenceHost replays one graph per inference batch)."""
     reward, done, frame = env_outputs[0], env_outputs[1], env_outputs[2]
     prev_actions = _lib.require_cuda(prev_actions, torch.int64, 'prev_actions')
     reward = _lib.require_cuda(reward, torch.float32, 'reward')
@@ -221,9 +224,13 @@ class _CudaAgent(object):
     noise = None
     if gumbel_noise is not None:
       noise = _lib.require_cuda(gumbel_noise, torch.float32, 'gumbel_noise')
-    _lib.check(L.seedrl_categorical_sample(
-        T1 * B, A, _lib.ptr(logits), _lib.ptr(noise), int(self._seed), int(self._next_rng_offset()),
-        _lib.ptr(action), st))
+    if rng_counter is not None:
+      _lib.check(L.seedrl_categorical_sample_counter(
+          T1 * B, A, _lib.ptr(logits), _lib.ptr(noise), int(self._seed), _lib.ptr(rng_counter), _lib.ptr(action), st))
+    else:
+      _lib.check(L.seedrl_categorical_sample(
+          T1 * B, A, _lib.ptr(logits), _lib.ptr(noise), int(self._seed), int(self._next_rng_offset()),
+          _lib.ptr(action), st))
     action = action.view(T1, B)
     if is_training:
       self._saved = (T1, B, prev_actions, reward, done, frame, ws)
