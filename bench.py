@@ -813,12 +813,31 @@ def main():
           conv_once()
         ms_k = timed(conv_once, 10)
         alg = 2.0 * Nf * Hh * Hh * Cc * 4
+        # DRAM traffic of this kernel from the committed `ncu --set full` capture of the same source
+        # (profiles/r02_ncu_traffic.json, tools/ncu_traffic.py), scaled by the frame count
+        traffic, tc_busy, tsrc = None, None, None
+        try:
+          tj = json.load(open(os.path.join(ROOT, 'profiles', 'r02_ncu_traffic.json')))
+          for kn, rec in tj.items():
+            if 'convp_kernel<16, 16, 4>' in kn and args.conv == 'tc3p':
+              traffic = (rec['dram_read_bytes'] + rec['dram_write_bytes']) * Nf / rec['frames']
+              tc_busy, tsrc = rec['tensor_pipe_active_pct'], 'profiles/' + rec['report'].replace('.ncu-rep', '.txt')
+        except Exception:
+          pass
         line['roofline_dominant_kernel'] = {
             'kernel': kname + ' (+ its 3 us weight-pack launch)',
             'bound': 'hbm', 'algorithmic_bytes_per_launch': alg, 'avg_launch_ms': ms_k,
             'achieved': alg / (ms_k * 1e-3) / 1e9, 'peak': hbm_peak, 'unit': 'GB/s',
-            'frac': alg / (ms_k * 1e-3) / 1e9 / hbm_peak, 'traffic': None,
+            'frac': alg / (ms_k * 1e-3) / 1e9 / hbm_peak, 'traffic': traffic,
+            'traffic_source': tsrc, 'tensor_pipe_busy_pct_ncu': tc_busy,
+            'second_bound': 'tensor pipe: small-N tcgen05.mma is limited by its 4 KB A-tile read from shared '
+                            'memory (~39 clk per 128xNx16 whatever N); ncu shows the pipe ~80 % busy at ~50 % of '
+                            'HBM peak, i.e. the kernel sits at the instruction-rate limit of bf16x3 at N = 16..64',
             'launches_per_step': 8, 'ok': int(errk.item()) == 0}
+        if traffic and 'roofline' in line:
+          line['roofline']['traffic'] = traffic * line['roofline']['algorithmic_bytes_per_launch'] / alg
+          line['roofline']['traffic_note'] = ('DRAM bytes of the dominant conv instance (ncu) scaled by the '
+                                              "family's algorithmic bytes per launch")
         del xk, ok
       except Exception as exc:        # pylint: disable=broad-except
         line['roofline_dominant_kernel'] = {'unavailable': repr(exc)[:200]}

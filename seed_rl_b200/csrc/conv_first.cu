@@ -13,6 +13,8 @@
 // A CTA stages one frame at a time in shared memory as bf16 (exact for 0..255) with a zero border;
 // thread = (channel co, pooled-pixel lane): 9 x 8-byte patch loads + 36 FMAs per (q, co) into 36
 // register accumulators; per-CTA partials go through the deterministic deferred reduce.
+#include <cuda.h>
+
 #include "kernels.h"
 #include "tc_common.cuh"
 
@@ -228,7 +230,13 @@ __device__ __forceinline__ uint2 u8x4_to_bf16x4(uint32_t w32) {
   return make_uint2(__byte_perm(f0, f1, 0x7632), __byte_perm(f2, f3, 0x7632));
 }
 
-__global__ void __launch_bounds__(kCpThreadsF, 2) conv0pool_kernel(const Conv0PoolArgs a) {
+// The observation tile of a unit -- frame rows cr0-1 .. cr0+7 of frame n, all W pixels x 4 channels --
+// arrives by ONE TMA tensor copy (cp.async.bulk.tensor.3d over the [N][H][W] uint32 view of the
+// frames; rows above / below the frame are zero-filled by the TMA unit: the 'same' padding costs
+// nothing) into one of two raw stages; the copy of the NEXT unit's tile is in flight while this
+// unit converts, multiplies and pools.
+__global__ void __launch_bounds__(kCpThreadsF, 2) conv0pool_kernel(const __grid_constant__ CUtensorMap tm_frames,
+                                                                    const Conv0PoolArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int W = a.W, H = a.H, SW = W + 2;
@@ -239,7 +247,12 @@ __global__ void __launch_bounds__(kCpThreadsF, 2) conv0pool_kernel(const Conv0Po
   s_bq = reinterpret_cast<uint8_t*>(((uintptr_t)s_bq + 127) & ~(uintptr_t)127);     // B: 48 x 32 bf16 = 3 KB
   float* s_bias = reinterpret_cast<float*>(s_bq + 48 * 32 * 2);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + 16);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
+  uint64_t* s_full = s_bar + 1;                               // [2] TMA stage filled
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_full + 2);
+  constexpr int kRawRows = 2 * kCpRows + 3;                   // frame rows per tile (incl. the halo rows)
+  uint32_t* s_raw = reinterpret_cast<uint32_t*>(((uintptr_t)(s_tmem + 4) + 127) & ~(uintptr_t)127);   // [2][kRawRows][W]
+  const uint32_t raw_bytes = (uint32_t)(kRawRows * W) * 4u;
+  const uint32_t raw_stride = (raw_bytes + 127u) & ~127u;     // stage pitch (TMA destinations are 128-byte aligned)
 
   // ---- one-time setup: B operand (K-major, [N = 32][K = 48]: hi(w) | lo(w); k = kh*16 + kw*4 + ci,
   //      the 4th tap of a row has zero weights), bias, barrier, TMEM -------------------------------
@@ -259,7 +272,10 @@ __global__ void __launch_bounds__(kCpThreadsF, 2) conv0pool_kernel(const Conv0Po
   for (int i = tid; i < npair; i += kCpThreadsF) s_p[i] = make_uint4(0u, 0u, 0u, 0u);
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_bar)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_full)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s_full + 1)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_frames)) : "memory");
   }
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256));
@@ -277,53 +293,45 @@ __global__ void __launch_bounds__(kCpThreadsF, 2) conv0pool_kernel(const Conv0Po
   const int units = a.N * bands;
   uint32_t phase = 0;
   bool timed_out = false;
-  // The raw pixels of the NEXT unit travel HBM -> registers while the current unit computes (the
-  // staging loop was a chain of exposed global-load latencies: 4 x ~700 clk of a 5 300-clk unit).
-  constexpr int kPre = 4;                                   // pair entries per thread: (2*rows+3)*SW <= 1024
-  uint32_t pre0[kPre], pre1[kPre];
   auto unit_geom = [&](int u, int* n, int* r0, int* r1, int* cr0, int* cr1) {
     *n = u / bands;
     const int band = u - *n * bands;
     *r0 = band * kCpRows; *r1 = min(a.Ho, *r0 + kCpRows);
     *cr0 = max(0, 2 * *r0 - a.pt); *cr1 = min(H - 1, 2 * (*r1 - 1) - a.pt + 2);
   };
-  auto prefetch = [&](int u) {
+  // one thread issues the tile copy of unit u into stage st: box = W pixels x kRawRows rows x 1 frame
+  // starting one row above the band's first conv row (negative / >= H rows come back as zeros)
+  auto issue_tile = [&](int u, int st) {
     int n, r0, r1, cr0, cr1;
     unit_geom(u, &n, &r0, &r1, &cr0, &cr1);
-    const int CR = cr1 - cr0 + 1;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.frames) + (size_t)n * H * W;
-#pragma unroll
-    for (int k = 0; k < kPre; ++k) {
-      const int e = tid + k * kCpThreadsF;
-      pre0[k] = 0u; pre1[k] = 0u;
-      if (e < (CR + 2) * SW) {
-        const int lr = (int)(__umulhi((unsigned)e, a.sw_mul) >> a.sw_sh), bc = e - lr * SW;
-        const int fr = cr0 - 1 + lr;
-        if (fr >= 0 && fr < H) {
-          const uint32_t* row = src + (size_t)fr * W;
-          if (bc >= 1 && bc <= W) pre0[k] = __ldg(row + bc - 1);
-          if (bc + 1 <= W) pre1[k] = __ldg(row + bc);       // e + 1 is the same row; the last column pairs with zero
-        }
-      }
-    }
+    const uint32_t dst = smem_u32(s_raw) + (uint32_t)st * raw_stride, bar = smem_u32(s_full + st);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(raw_bytes) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::
+            "r"(dst), "l"(reinterpret_cast<uint64_t>(&tm_frames)), "r"(0), "r"(cr0 - 1), "r"(n), "r"(bar)
+        : "memory");
   };
-  if ((int)blockIdx.x < units) prefetch(blockIdx.x);
-  for (int u = blockIdx.x; u < units; u += gridDim.x) {
+  if (tid == 0 && (int)blockIdx.x < units) issue_tile(blockIdx.x, 0);
+  int it = 0;
+  for (int u = blockIdx.x; u < units; u += gridDim.x, ++it) {
     int n, r0, r1, cr0, cr1;
     unit_geom(u, &n, &r0, &r1, &cr0, &cr1);
     const int band = u - n * bands;
     const int CR = cr1 - cr0 + 1, npos = CR * SW, nblk = (npos + 127) >> 7;
-    // ---- 1. pair array of band rows cr0-1 .. cr1+1 (band row lr, band column bc = frame column + 1):
-    //      a zero byte quadruple converts to bf16 zeros, so out-of-frame entries need no special case ----
-#pragma unroll
-    for (int k = 0; k < kPre; ++k) {
-      const int e = tid + k * kCpThreadsF;
-      if (e < (CR + 2) * SW) {
-        const uint2 p0 = u8x4_to_bf16x4(pre0[k]), p1 = u8x4_to_bf16x4(pre1[k]);
-        s_p[e] = make_uint4(p0.x, p0.y, p1.x, p1.y);
-      }
+    const int st = it & 1;
+    // the next unit's tile goes into the other stage (its previous contents were converted one unit ago)
+    if (tid == 0 && u + (int)gridDim.x < units) issue_tile(u + gridDim.x, st ^ 1);
+    if (!mbar_wait_bounded(s_full + st, (uint32_t)((it >> 1) & 1))) timed_out = true;
+    // ---- 1. raw tile (row lr = frame row cr0-1+lr, W pixels) -> pair array: entry (lr, bc) =
+    //      [pixel bc-1, pixel bc] of that row as bf16 x 4 each, zero at the two border columns ----
+    const uint32_t* raw = s_raw + (size_t)st * (raw_stride / 4);
+    for (int e = tid; e < (CR + 2) * SW; e += kCpThreadsF) {
+      const int lr = (int)(__umulhi((unsigned)e, a.sw_mul) >> a.sw_sh), bc = e - lr * SW;
+      const uint32_t w0 = (bc >= 1 && bc <= W) ? raw[lr * W + bc - 1] : 0u;
+      const uint32_t w1 = (bc + 1 <= W) ? raw[lr * W + bc] : 0u;
+      const uint2 p0 = u8x4_to_bf16x4(w0), p1 = u8x4_to_bf16x4(w1);
+      s_p[e] = make_uint4(p0.x, p0.y, p1.x, p1.y);
     }
-    if (u + (int)gridDim.x < units) prefetch(u + gridDim.x);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     // ---- 2. MMAs: one per kernel row and 128-position block -------------------------------------
@@ -443,7 +451,8 @@ __global__ void __launch_bounds__(kCpThreadsF, 2) conv0pool_kernel(const Conv0Po
 }
 
 bool conv0pool_supported(int cin, int cout, int H, int W) {
-  return cin == 4 && cout == 16 && (2 * kCpRows + 1) * (W + 2) <= kCpMaxBlocks * 128 && H >= 3 && W >= 3;
+  // (W % 4: the TMA row pitch W*4 bytes must be a multiple of 16; W <= 256: box width)
+  return cin == 4 && cout == 16 && W % 4 == 0 && W <= 256 && (2 * kCpRows + 1) * (W + 2) <= kCpMaxBlocks * 128 && H >= 3 && W >= 3;
 }
 
 int conv0pool_forward(int N, int H, int W, const uint8_t* frames, const float* w, const float* bias, void* praw,
@@ -456,17 +465,40 @@ int conv0pool_forward(int N, int H, int W, const uint8_t* frames, const float* w
   fast_div_setup((unsigned int)(W + 2), &a.sw_mul, &a.sw_sh);
   a.frames = frames; a.w = w; a.bias = bias;
   a.praw = reinterpret_cast<uint4*>(praw); a.prelu = reinterpret_cast<uint4*>(prelu); a.idx = idx; a.err = err;
+  const size_t raw_stride = (((size_t)(2 * kCpRows + 3) * W * 4) + 127) / 128 * 128;
   const size_t smem = (size_t)(kCpMaxBlocks * 128 + 2 * (W + 2) + 8) * 16 +
-                      (size_t)kCpMaxBlocks * 128 * kCpOutStride * 4 + 128 + 48 * 32 * 2 + 16 * 4 + 64;
+                      (size_t)kCpMaxBlocks * 128 * kCpOutStride * 4 + 128 + 48 * 32 * 2 + 16 * 4 + 64 + 128 + 2 * raw_stride;
   static bool attr = false;
   if (!attr) {
-    SEEDRL_CUDA(cudaFuncSetAttribute(conv0pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    SEEDRL_CUDA(cudaFuncSetAttribute(conv0pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     attr = true;
   }
-  if (smem > 110 * 1024) return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "conv0pool: image too wide");
+  if (smem > 112 * 1024) return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "conv0pool: image too wide");
+  // [N][H][W] view of the frames with one uint32 (= 4 uint8 channels) per pixel
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeTiledFn enc = nullptr;
+  if (!enc) {
+    void* q = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &q, cudaEnableDefault, &qr) != cudaSuccess ||
+        qr != cudaDriverEntryPointSuccess)
+      return set_error(SEEDRL_ERR_INTERNAL, "cuTensorMapEncodeTiled is not available");
+    enc = reinterpret_cast<EncodeTiledFn>(q);
+  }
+  CUtensorMap tm;
+  const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  const cuuint64_t gstr[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)W, (cuuint32_t)(2 * kCpRows + 3), 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(frames), gdim, gstr, box, estr,
+          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return set_error(SEEDRL_ERR_INTERNAL, "conv0pool: cuTensorMapEncodeTiled failed");
   const int units = N * ((a.Ho + kCpRows - 1) / kCpRows);
   const int grid = units < 2 * kNumSMs ? units : 2 * kNumSMs;
-  conv0pool_kernel<<<grid, kCpThreadsF, smem, st>>>(a);
+  conv0pool_kernel<<<grid, kCpThreadsF, smem, st>>>(tm, a);
   count_launch(PC_CONV_FWD, st);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;

@@ -1,0 +1,17 @@
+set +e
+O=gpurun_out/final; mkdir -p $O
+timeout 1500 python -m pytest tests -m gpu -q > $O/pytest_gpu.log 2>&1; echo "rc=$?" >> $O/pytest_gpu.log; tail -3 $O/pytest_gpu.log
+timeout 600 python bench.py --steps 50 --warmup 10 > $O/bench_cfg4_default.json 2> $O/bench_default.err; tail -2 $O/bench_default.err
+timeout 300 python bench.py --batch 256 --steps 20 --warmup 5 --no-extras > $O/bench_cfg3_b256.json 2> $O/bench_cfg3.err
+timeout 300 python bench.py --net shallow --steps 50 --warmup 10 --no-extras > $O/bench_cfg2_shallow.json 2> $O/bench_cfg2.err
+timeout 600 python bench.py --agent r2d2 --steps 10 --warmup 8 > $O/bench_cfg5_r2d2.json 2> $O/bench_cfg5.err; tail -2 $O/bench_cfg5.err
+timeout 900 python bench.py --impl reference --steps 5 --warmup 2 > $O/bench_reference_arm.json 2> $O/bench_ref.err
+python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; tail -2 $O/smoke.log
+python - <<'PY'
+import json, glob
+for f in sorted(glob.glob('gpurun_out/final/bench_*.json')):
+    try:
+        d = json.load(open(f)); print(f.split('/')[-1], round(d['ms_per_step'], 3), round(d['value']), round(d['e2e']['value']))
+    except Exception as e:
+        print(f, 'ERR', e)
+PY
