@@ -213,8 +213,12 @@ def conv_bytes_per_step_planes(N, cat):
     full_in = N * h * w * cin * (1 if si == 0 else 4)
     full_out = N * h * w * c * 4
     pooled = N * ho * wo * c * 4
+    taps = N * ho * wo * c                    # arg-max taps, 1 byte per pooled element
     if cat == 'conv3x3_fwd':
-      tot += full_in + full_out               # stack conv: frames / plane tensor in, fp32 NHWC out
+      if si == 0:
+        tot += full_in + 2 * pooled + taps    # fused conv + pool: frames in, raw + ReLU'd pooled planes + taps out
+      else:
+        tot += full_in + full_out             # stack conv: plane tensor in, fp32 NHWC out (pooled by poolp_fwd)
       tot += 2 * pooled                       # conv00: relu(p) in, relu(c0) out
       tot += 4 * pooled                       # conv01: relu(c0) + p in, o0 and relu(o0) out
       tot += 2 * pooled                       # conv10
@@ -227,7 +231,11 @@ def conv_bytes_per_step_planes(N, cat):
         tot += full_out + N * h * w * cin * 4
         launches += 1
     elif cat == 'conv3x3_wgrad':
-      tot += full_in + full_out + 4 * (2 * pooled)
+      if si == 0:
+        tot += full_in + pooled + taps        # first layer: frames + POOLED gradient + taps (no full-resolution tensor)
+      else:
+        tot += full_in + full_out
+      tot += 4 * (2 * pooled)
       launches += 5
   if cat == 'conv3x3_wgrad':
     launches += 1                             # one deferred reduce of all partials
