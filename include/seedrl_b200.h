@@ -426,6 +426,7 @@ int seedrl_debug_set_wgrad_chunk(int kc);
 /* Output positions per tile of the tensor-core forward / data-gradient kernel: the largest
  * of 512 / 256 / 128 not above `mt` that keeps two CTAs per SM is used (default 512). */
 int seedrl_debug_set_conv_tile(int mt);
+int seedrl_debug_set_gemm_bk(int bk);     /* gemm_tc_kernel K elements per staged block: 64 or 32 */
 /* 1 = conv_mode 3 keeps the dense first-layer backward (pool backward + full-resolution weight
  * gradient) instead of csrc/conv_first.cu's gather from the pooled gradient (A/B parity tests). */
 int seedrl_debug_set_first_layer_dense(int on);

@@ -27,7 +27,9 @@ namespace seedrl {
 
 constexpr int kGtThreads = 256;
 constexpr int kGtBM = 128;
-constexpr int kGtBK = 64;
+// K elements per staged block = template parameter BK (64, 32 or 16): a smaller block shrinks the
+// stage so that several CTAs fit an SM and overlap each other's load / convert / MMA / epilogue phases
+// (measured on the learner's nine GEMM shapes: 322 us at BK = 64, 259 us at BK = 32)
 
 struct GemmTcParams {
   int M, N, K;
@@ -76,10 +78,11 @@ __device__ __forceinline__ void store_unit(RawUnit r, bool relu, uint4* hi_dst, 
   if (SPLIT) *lo_dst = pack8_bf16(bf16_resid4(r.a), bf16_resid4(r.b));
 }
 
-template <bool TA, bool TB, bool SPLIT>
+template <bool TA, bool TB, bool SPLIT, int kGtBK>
 __global__ void __launch_bounds__(kGtThreads)
 gemm_tc_kernel(const GemmTcParams p) {
   constexpr int S = SPLIT ? 2 : 1;
+  constexpr int KG = kGtBK / 8;                 // 16-byte K-groups per row of a block
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int BN = p.BN;
   // one stage: [A hi | A lo | B hi | B lo].  Plane strides are padded by one 16-byte unit so
@@ -133,7 +136,7 @@ gemm_tc_kernel(const GemmTcParams p) {
 #pragma unroll
     for (int r = 0; r < AI; ++r) {
       const int u = tid + r * kGtThreads;
-      if (!TA) ra[r] = load_raw(p.A, p.lda, m0 + (u >> 3), k0 + (u & 7) * 8, p.M, p.K, p.vecA != 0);   // A[M,K]
+      if (!TA) ra[r] = load_raw(p.A, p.lda, m0 + u / KG, k0 + (u % KG) * 8, p.M, p.K, p.vecA != 0);   // A[M,K]
       else     ra[r] = load_raw(p.A, p.lda, k0 + (u >> 4), m0 + (u & 15) * 8, p.K, p.M, p.vecA != 0);  // A stored [K,M]
     }
     const int bng = BN >> 3;
@@ -141,7 +144,7 @@ gemm_tc_kernel(const GemmTcParams p) {
     for (int r = 0; r < BI; ++r) {
       const int u = tid + r * kGtThreads;
       if (u < b_items) {
-        if (TB) rb[r] = load_raw(p.B, p.ldb, n0 + (u >> 3), k0 + (u & 7) * 8, p.N, p.K, p.vecB != 0);  // B stored [N,K]
+        if (TB) rb[r] = load_raw(p.B, p.ldb, n0 + u / KG, k0 + (u % KG) * 8, p.N, p.K, p.vecB != 0);  // B stored [N,K]
         else    rb[r] = load_raw(p.B, p.ldb, k0 + u / bng, n0 + (u % bng) * 8, p.K, p.N, p.vecB != 0); // B[K,N]
       }
     }
@@ -151,7 +154,7 @@ gemm_tc_kernel(const GemmTcParams p) {
     for (int r = 0; r < AI; ++r) {
       const int u = tid + r * kGtThreads;
       // K-major planes [8 kg][128 m] / MN-major planes [16 mg][64 k]
-      const uint32_t o = !TA ? (uint32_t)(u & 7) * a_ps + (u >> 3) : (uint32_t)(u & 15) * a_ps + (u >> 4);
+      const uint32_t o = !TA ? (uint32_t)(u % KG) * a_ps + u / KG : (uint32_t)(u & 15) * a_ps + (u >> 4);
       store_unit<SPLIT>(ra[r], p.e.a_relu != 0, sA + o, sA + a_units + o);
     }
 #pragma unroll
@@ -159,7 +162,7 @@ gemm_tc_kernel(const GemmTcParams p) {
       const int u = tid + r * kGtThreads;
       if (u < b_items) {
         // K-major planes [8 kg][BN n] / MN-major planes [BN/8 ng][64 k]
-        const uint32_t o = TB ? (uint32_t)(u & 7) * b_ps + (u >> 3) : (uint32_t)(u % bng) * b_ps + u / bng;
+        const uint32_t o = TB ? (uint32_t)(u % KG) * b_ps + u / KG : (uint32_t)(u % bng) * b_ps + u / bng;
         store_unit<SPLIT>(rb[r], false, sB + o, sB + b_units + o);
       }
     }
@@ -276,6 +279,10 @@ __global__ void gemm_tc_reduce_kernel(int M, int N, int splits, const float* __r
   }
 }
 
+static int norm_bk(int bk) { return bk == 64 ? 64 : (bk == 16 ? 16 : 32); }
+static int g_gemm_bk = norm_bk(getenv("SEEDRL_GEMM_BK") ? atoi(getenv("SEEDRL_GEMM_BK")) : 32);
+void gemm_tc_set_bk(int bk) { g_gemm_bk = norm_bk(bk); }
+
 bool gemm_tc_supported(int M, int N, int K) { return M >= 64 && N >= 16 && K >= 32; }
 
 size_t gemm_tc_workspace_bytes() { return (size_t)48 << 20; }
@@ -288,41 +295,52 @@ int gemm_tc(bool ta, bool tb, int split, int M, int N, int K, const float* A, in
   p.M = M; p.N = N; p.K = K; p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;
   p.e = e; p.error_flag = err;
   const int n16 = ((N + 15) / 16) * 16;
+  const int BK = g_gemm_bk;
   int bn = split ? 128 : 256;                           // shared memory: 2 stages x (hi + lo)
   if (bn > n16) bn = n16;
   // narrower tiles until the grid can cover the SMs (with split-K below)
-  const int nkb_all = ceil_div(K, kGtBK);
-  while (bn > 64 && ceil_div(M, kGtBM) * ceil_div(N, bn) * (nkb_all >= 4 ? nkb_all / 2 : 1) < kNumSMs) bn >>= 1;
+  const int nkb_all = ceil_div(K, BK);
+  const int kb256 = 256 / BK;                           // K-blocks per 256 elements of K
+  while (bn > 64 && ceil_div(M, kGtBM) * ceil_div(N, bn) * (nkb_all >= kb256 ? nkb_all / (kb256 / 2) : 1) < kNumSMs)
+    bn >>= 1;
   p.BN = ((bn + 15) / 16) * 16;
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
   p.vecA = al16(A) && (lda & 3) == 0;
   p.vecB = al16(B) && (ldb & 3) == 0;
   const int tiles = ceil_div(M, kGtBM) * ceil_div(N, p.BN);
-  const int nkb = ceil_div(K, kGtBK);
-  // split-K until the grid covers the SMs, keeping >= 4 K-blocks per slice and the
+  const int nkb = ceil_div(K, BK);
+  // split-K until the grid covers the SMs, keeping >= 128 elements of K per slice and the
   // partials inside the workspace
   int splits = 1;
   static const int waves = getenv("SEEDRL_GEMM_WAVES") ? atoi(getenv("SEEDRL_GEMM_WAVES")) : 1;   // tuning knob
-  while (tiles * splits < waves * kNumSMs && nkb / (splits * 2) >= 2 &&
+  while (tiles * splits < waves * kNumSMs && nkb / (splits * 2) >= 128 / BK &&
          (size_t)(splits * 2) * M * N * sizeof(float) <= ws_bytes && ws)
     splits *= 2;
   p.kblocks_per_split = ceil_div(nkb, splits);
   splits = ceil_div(nkb, p.kblocks_per_split);
   p.ws = splits > 1 ? ws : nullptr;
   const int S = split ? 2 : 1;
-  const size_t a_un = ta ? (size_t)(kGtBM / 8) * (kGtBK + 1) : (size_t)(kGtBK / 8) * (kGtBM + 1);
-  const size_t b_un = tb ? (size_t)(kGtBK / 8) * (p.BN + 1) : (size_t)(p.BN / 8) * (kGtBK + 1);
-  const size_t smem = (size_t)2 * S * (a_un + b_un) * 16 + 64;
+  const size_t a_un = ta ? (size_t)(kGtBM / 8) * (BK + 1) : (size_t)(BK / 8) * (kGtBM + 1);
+  const size_t b_un = tb ? (size_t)(BK / 8) * (p.BN + 1) : (size_t)(p.BN / 8) * (BK + 1);
+  size_t smem = (size_t)2 * S * (a_un + b_un) * 16 + 64;
+  const size_t epi = (size_t)(kGtThreads / 32) * 32 * 33 * 4;      // the epilogue's transpose scratch aliases the stages
+  if (smem < epi) smem = epi;
   dim3 grid(ceil_div(N, p.BN), ceil_div(M, kGtBM), splits);
-#define SEEDRL_GT_LAUNCH(TA_, TB_, SP_)                                                         \
+#define SEEDRL_GT_LAUNCH1(TA_, TB_, SP_, BK_)                                                   \
   do {                                                                                          \
     static bool attr = false;                                                                   \
     if (!attr) {                                                                                \
-      SEEDRL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<TA_, TB_, SP_>,                           \
+      SEEDRL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<TA_, TB_, SP_, BK_>,                      \
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
       attr = true;                                                                              \
     }                                                                                           \
-    gemm_tc_kernel<TA_, TB_, SP_><<<grid, kGtThreads, smem, st>>>(p);                           \
+    gemm_tc_kernel<TA_, TB_, SP_, BK_><<<grid, kGtThreads, smem, st>>>(p);                      \
+  } while (0)
+#define SEEDRL_GT_LAUNCH(TA_, TB_, SP_)                                                         \
+  do {                                                                                          \
+    if (BK == 32) SEEDRL_GT_LAUNCH1(TA_, TB_, SP_, 32);                                         \
+    else if (BK == 16) SEEDRL_GT_LAUNCH1(TA_, TB_, SP_, 16);                                    \
+    else SEEDRL_GT_LAUNCH1(TA_, TB_, SP_, 64);                                                  \
   } while (0)
   if (split) {
     if (!ta && !tb) SEEDRL_GT_LAUNCH(false, false, true);
@@ -336,6 +354,7 @@ int gemm_tc(bool ta, bool tb, int split, int M, int N, int K, const float* A, in
     else SEEDRL_GT_LAUNCH(true, true, false);
   }
 #undef SEEDRL_GT_LAUNCH
+#undef SEEDRL_GT_LAUNCH1
   count_launch(PC_GEMM, st);
   SEEDRL_CHECK_LAUNCH();
   if (splits > 1) {

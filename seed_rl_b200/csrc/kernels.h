@@ -176,6 +176,7 @@ int colsum(int M, int N, const float* X, int ld, float* out, cudaStream_t st);
 // gemm_tc_kernels.cu (tcgen05): same contract as sgemm; split = bf16x3 operands; `ws` holds
 // split-K partials (gemm_tc_workspace_bytes()); *err is set if a bounded mbarrier wait expires.
 bool gemm_tc_supported(int M, int N, int K);
+void gemm_tc_set_bk(int bk);                 // K elements per staged block: 64 or 32 (tuning knob)
 size_t gemm_tc_workspace_bytes();
 int gemm_tc(bool ta, bool tb, int split, int M, int N, int K, const float* A, int lda, const float* B,
             int ldb, float* C, int ldc, const GemmEpi& e, float* ws, size_t ws_bytes, int* err,

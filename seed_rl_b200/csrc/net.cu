@@ -1035,6 +1035,10 @@ extern "C" int seedrl_debug_set_first_layer_dense(int on) {
   g_first_dense = on ? 1 : 0;
   return SEEDRL_OK;
 }
+extern "C" int seedrl_debug_set_gemm_bk(int bk) {
+  gemm_tc_set_bk(bk);
+  return SEEDRL_OK;
+}
 extern "C" int seedrl_debug_set_conv_tile(int mt) {
   SEEDRL_CHECK_ARG(mt == 128 || mt == 256 || mt == 512, "tile must be 128, 256 or 512");
   conv3x3_tc_set_tile(mt);
