@@ -15,6 +15,8 @@
 // register accumulators; per-CTA partials go through the deterministic deferred reduce.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "kernels.h"
 #include "tc_common.cuh"
 
@@ -204,8 +206,8 @@ int first_wgrad_pooled(int N, int H, int W, const uint8_t* frames, const void* g
 //   4. pooling from shared memory, TF-SAME windows, first maximum wins; hi/lo split; coalesced
 //      16-byte plane stores; padding positions of the plane tensors written as zeros.
 // 2 CTAs / SM (TMEM 2 x 256 columns): the phases of one CTA overlap the other's.
-constexpr int kCpRows = 3;          // pooled rows per unit
-constexpr int kCpMaxBlocks = 6;     // 128-position blocks per unit (TMEM: 6 x 32 columns)
+// kCpRows pooled rows per unit (template parameter: 3 -> up to 6 blocks of 128 positions, TMEM 256 columns,
+// 2 CTAs / SM; 2 -> up to 4 blocks, TMEM 128 columns, 3 CTAs / SM).
 constexpr int kCpThreadsF = 256;
 constexpr int kCpOutStride = 20;    // floats per position in the fp32 tile (16 + 4: pool reads 2-way conflict)
 
@@ -235,8 +237,11 @@ __device__ __forceinline__ uint2 u8x4_to_bf16x4(uint32_t w32) {
 // frames; rows above / below the frame are zero-filled by the TMA unit: the 'same' padding costs
 // nothing) into one of two raw stages; the copy of the NEXT unit's tile is in flight while this
 // unit converts, multiplies and pools.
-__global__ void __launch_bounds__(kCpThreadsF, 2) conv0pool_kernel(const __grid_constant__ CUtensorMap tm_frames,
+template <int kCpRows>
+__global__ void __launch_bounds__(kCpThreadsF, kCpRows == 2 ? 3 : 2) conv0pool_kernel(const __grid_constant__ CUtensorMap tm_frames,
                                                                     const Conv0PoolArgs a) {
+  constexpr int kCpMaxBlocks = kCpRows == 2 ? 4 : 6;
+  constexpr uint32_t kTmemCols = kCpRows == 2 ? 128u : 256u;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int W = a.W, H = a.H, SW = W + 2;
@@ -278,7 +283,7 @@ __global__ void __launch_bounds__(kCpThreadsF, 2) conv0pool_kernel(const __grid_
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_frames)) : "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(256));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -446,31 +451,31 @@ __global__ void __launch_bounds__(kCpThreadsF, 2) conv0pool_kernel(const __grid_
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols));
   }
 }
 
+static int g_c0_rows = getenv("SEEDRL_C0_ROWS") ? (atoi(getenv("SEEDRL_C0_ROWS")) == 2 ? 2 : 3) : 3;
+void conv0pool_set_rows(int rows) { g_c0_rows = rows == 2 ? 2 : 3; }
+static int c0_rows(int W) {                      // pooled rows per unit that fit the block budget
+  if (g_c0_rows == 2 && 5 * (W + 2) <= 4 * 128) return 2;
+  return 3;
+}
 bool conv0pool_supported(int cin, int cout, int H, int W) {
   // (W % 4: the TMA row pitch W*4 bytes must be a multiple of 16; W <= 256: box width)
-  return cin == 4 && cout == 16 && W % 4 == 0 && W <= 256 && (2 * kCpRows + 1) * (W + 2) <= kCpMaxBlocks * 128 && H >= 3 && W >= 3;
+  return cin == 4 && cout == 16 && W % 4 == 0 && W <= 256 && 7 * (W + 2) <= 6 * 128 && H >= 3 && W >= 3;
 }
 
-int conv0pool_forward(int N, int H, int W, const uint8_t* frames, const float* w, const float* bias, void* praw,
-                      void* prelu, uint8_t* idx, int* err, cudaStream_t st) {
-  Conv0PoolArgs a;
-  a.N = N; a.H = H; a.W = W;
-  same_pad3s2_(H, &a.Ho, &a.pt);
-  same_pad3s2_(W, &a.Wo, &a.pl);
-  a.Lpp = (int)planes_positions(N, a.Ho, a.Wo); a.PWp = a.Wo + 2; a.RHp = a.Ho + 1;
-  fast_div_setup((unsigned int)(W + 2), &a.sw_mul, &a.sw_sh);
-  a.frames = frames; a.w = w; a.bias = bias;
-  a.praw = reinterpret_cast<uint4*>(praw); a.prelu = reinterpret_cast<uint4*>(prelu); a.idx = idx; a.err = err;
-  const size_t raw_stride = (((size_t)(2 * kCpRows + 3) * W * 4) + 127) / 128 * 128;
-  const size_t smem = (size_t)(kCpMaxBlocks * 128 + 2 * (W + 2) + 8) * 16 +
-                      (size_t)kCpMaxBlocks * 128 * kCpOutStride * 4 + 128 + 48 * 32 * 2 + 16 * 4 + 64 + 128 + 2 * raw_stride;
+template <int ROWS>
+static int launch_conv0pool(Conv0PoolArgs a, const uint8_t* frames, cudaStream_t st) {
+  constexpr int MAXB = ROWS == 2 ? 4 : 6;
+  const int N = a.N, H = a.H, W = a.W;
+  const size_t raw_stride = (((size_t)(2 * ROWS + 3) * W * 4) + 127) / 128 * 128;
+  const size_t smem = (size_t)(MAXB * 128 + 2 * (W + 2) + 8) * 16 + (size_t)MAXB * 128 * kCpOutStride * 4 + 128 +
+                      48 * 32 * 2 + 16 * 4 + 64 + 128 + 2 * raw_stride;
   static bool attr = false;
   if (!attr) {
-    SEEDRL_CUDA(cudaFuncSetAttribute(conv0pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    SEEDRL_CUDA(cudaFuncSetAttribute(conv0pool_kernel<ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     attr = true;
   }
   if (smem > 112 * 1024) return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "conv0pool: image too wide");
@@ -490,18 +495,32 @@ int conv0pool_forward(int N, int H, int W, const uint8_t* frames, const float* w
   CUtensorMap tm;
   const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   const cuuint64_t gstr[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
-  const cuuint32_t box[3] = {(cuuint32_t)W, (cuuint32_t)(2 * kCpRows + 3), 1};
+  const cuuint32_t box[3] = {(cuuint32_t)W, (cuuint32_t)(2 * ROWS + 3), 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(frames), gdim, gstr, box, estr,
           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
     return set_error(SEEDRL_ERR_INTERNAL, "conv0pool: cuTensorMapEncodeTiled failed");
-  const int units = N * ((a.Ho + kCpRows - 1) / kCpRows);
-  const int grid = units < 2 * kNumSMs ? units : 2 * kNumSMs;
-  conv0pool_kernel<<<grid, kCpThreadsF, smem, st>>>(tm, a);
+  const int units = N * ((a.Ho + ROWS - 1) / ROWS);
+  const int per_sm = ROWS == 2 ? 3 : 2;
+  const int grid = units < per_sm * kNumSMs ? units : per_sm * kNumSMs;
+  conv0pool_kernel<ROWS><<<grid, kCpThreadsF, smem, st>>>(tm, a);
   count_launch(PC_CONV_FWD, st);
   SEEDRL_CHECK_LAUNCH();
   return SEEDRL_OK;
+}
+
+int conv0pool_forward(int N, int H, int W, const uint8_t* frames, const float* w, const float* bias, void* praw,
+                      void* prelu, uint8_t* idx, int* err, cudaStream_t st) {
+  Conv0PoolArgs a;
+  a.N = N; a.H = H; a.W = W;
+  same_pad3s2_(H, &a.Ho, &a.pt);
+  same_pad3s2_(W, &a.Wo, &a.pl);
+  a.Lpp = (int)planes_positions(N, a.Ho, a.Wo); a.PWp = a.Wo + 2; a.RHp = a.Ho + 1;
+  fast_div_setup((unsigned int)(W + 2), &a.sw_mul, &a.sw_sh);
+  a.frames = frames; a.w = w; a.bias = bias;
+  a.praw = reinterpret_cast<uint4*>(praw); a.prelu = reinterpret_cast<uint4*>(prelu); a.idx = idx; a.err = err;
+  return c0_rows(W) == 2 ? launch_conv0pool<2>(a, frames, st) : launch_conv0pool<3>(a, frames, st);
 }
 
 }  // namespace seedrl

@@ -756,8 +756,20 @@ __global__ void wgrad_reduce_batch_kernel(const __grid_constant__ ReduceTable t)
   const ReduceJob j = t.jobs[blockIdx.y];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= j.nw + j.nb) return;
+  // fixed-order sum over the CTAs' partials; the loads of 8 partials are issued together (they are
+  // independent), the adds stay sequential => same result as the plain loop, ~4x less latency
   float s = 0.f;
-  for (int k = 0; k < j.nparts; ++k) s += j.partial[(size_t)k * (j.nw + j.nb) + i];   // fixed order
+  const size_t stride = (size_t)(j.nw + j.nb);
+  const float* src = j.partial + i;
+  int k = 0;
+  for (; k + 8 <= j.nparts; k += 8) {
+    float v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = __ldcs(src + (size_t)(k + q) * stride);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s += v[q];
+  }
+  for (; k < j.nparts; ++k) s += __ldcs(src + (size_t)k * stride);
   if (i < j.nw) j.dw[i] = s; else j.db[i - j.nw] = s;
 }
 
