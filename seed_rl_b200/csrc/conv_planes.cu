@@ -466,6 +466,9 @@ __global__ void __launch_bounds__(kWpThreads, 1)
 wgradp_kernel(const __grid_constant__ WgradMaps tm, const WgradpArgs a) {
   constexpr int G = CP / 8, GO = COUT / 8;
   constexpr int XG = 3 * G + 1;                          // M groups per half: (kw, g) planes + ones/zeros plane
+  // 16-channel inputs fill only 49 of an M = 128 instruction's rows; M = 64 (8 row groups >= XG = 7)
+  // reads half the A tile per instruction -- the small-N MMA is bound by that read
+  constexpr int MROWS = XG <= 8 ? 64 : 128;
   constexpr int TCOLS = 6 * COUT <= 128 ? 128 : 256;
   constexpr int NW = 9 * CP * COUT + COUT;
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -529,8 +532,8 @@ wgradp_kernel(const __grid_constant__ WgradMaps tm, const WgradpArgs a) {
     __syncwarp();
   } else if (warp == 1) {
     // both operands MN-major
-    constexpr uint32_t idesc6 = umma_idesc(128, 6 * COUT) | (1u << 15) | (1u << 16);
-    constexpr uint32_t idesc3 = umma_idesc(128, 3 * COUT) | (1u << 15) | (1u << 16);
+    constexpr uint32_t idesc6 = umma_idesc(MROWS, 6 * COUT) | (1u << 15) | (1u << 16);
+    constexpr uint32_t idesc3 = umma_idesc(MROWS, 3 * COUT) | (1u << 15) | (1u << 16);
     for (int it = 0; it < my_chunks; ++it) {
       const int s = it % nb;
       if (!mbar_wait_bounded(s_full + s, (uint32_t)((it / nb) & 1))) { timed_out = true; break; }
@@ -565,7 +568,9 @@ wgradp_kernel(const __grid_constant__ WgradMaps tm, const WgradpArgs a) {
   __syncthreads();
   float* dst = a.partial + (size_t)blockIdx.x * NW;
   if (warp >= 2) {
-    const int row = (warp & 3) * 32 + lane;              // TMEM lane = accumulator row
+    // TMEM lane -> accumulator row: M = 128: lane = row; M = 64 (cute tmem_frg_1sm, M_MMA == 64): row m
+    // lives in lane (m % 16) + 32 * (m / 16), i.e. 16 rows per 32-lane sub-partition
+    const int row = MROWS == 128 ? (warp & 3) * 32 + lane : (lane < 16 ? (warp & 3) * 16 + lane : 1 << 20);
     const int kw = row / CP, ci = row - kw * CP;
     const uint32_t lane_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
 #pragma unroll 1
