@@ -259,3 +259,83 @@ def test_prioritized_replay_and_feeder():
                                       2, 1, 0.0, 18)
   frac = float((acts != 7).float().mean())
   assert abs(frac - 0.4 * 17 / 18) < 0.05
+
+
+def test_r2d2_inference_host_feeds_replay_and_learner():
+  """R2D2InferenceHost._inference == reference agents/r2d2/learner.py:711-790 (run-id resets, T=1
+  forward with frame stacking, epsilon-greedy, store with burn_in overlapping steps for training
+  environments only, initial priorities from the behaviour Q values, first-state bookkeeping), then
+  the replay feed + one learner step (create_dataset :410-461, minimize, priority write-back)."""
+  from seed_rl_b200.agents.r2d2 import learner, learner_loop
+  from seed_rl_b200.atari import networks
+  from seed_rl_b200.common import optimizers, utils
+  A, obs, S = 6, (36, 36, 1), 4
+  st = learner.default_settings(batch_size=6, replay_ratio=1.5, unroll_length=4, burn_in=2, replay_buffer_size=16,
+                                replay_buffer_min_size=4, update_target_every_n_step=10**9)
+  agent = networks.DuelingLSTMDQNNet(A, obs, S, seed=1, gemm_mode='simt')
+  target = networks.DuelingLSTMDQNNet(A, obs, S, seed=1, gemm_mode='simt')
+  host = learner_loop.R2D2InferenceHost(agent, num_envs=6, num_eval_envs=1, inference_batch_size=3,
+                                        observation_shape=obs, settings=st,
+                                        generator=torch.Generator(device='cuda').manual_seed(0))
+  rng = np.random.default_rng(0)
+  run_ids = rng.integers(1, 2**40, 6)
+  returned = {e: [] for e in range(6)}
+  for step_i in range(13):
+    for ids in (np.array([0, 1, 2], np.int32), np.array([5, 3, 4], np.int32)):
+      n = len(ids)
+      env = utils.EnvOutput(rng.normal(size=n).astype(np.float32), rng.random(n) < 0.1,
+                            rng.integers(0, 256, (n,) + obs, dtype=np.uint8), np.zeros(n, bool), np.full(n, step_i, np.int32))
+      act = host.inference(ids, run_ids[ids], env, np.zeros(n, np.float32))
+      assert act.shape == (3,) and act.dtype == np.int32 and (0 <= act).all() and (act < A).all()
+      for e, a in zip(ids, act):
+        returned[int(e)].append(int(a))
+  torch.cuda.synchronize()
+  # full_length = burn_in + unroll_length + 1 = 7 and the index starts at burn_in (the first unroll's
+  # first burn_in rows are zero padding, UnrollStore :142-145): unrolls complete at steps 4, 8 and 12
+  # for each of the 5 training environments; the eval environment (id 5) never reaches the store
+  assert host.unroll_queue.size() == 15
+  items = [host.unroll_queue.dequeue() for _ in range(15)]
+  for k, u in enumerate(items):
+    assert tuple(u.prev_actions.shape) == (7,) and tuple(u.env_outputs.observation.shape) == (7,) + obs
+    lo = st.burn_in if k < 5 else 0
+    assert torch.equal(u.agent_outputs.action[lo:-1], u.prev_actions[lo + 1:])  # :829-830
+    assert float(u.priority) > 0
+    # initial priority (:807-821) against the numpy oracle on the suffix
+    q = u.agent_outputs.q_values[st.burn_in:].cpu().numpy()[:, None]
+    _, prio, _ = R.loss_and_priorities(q, q.argmax(-1), q, u.agent_outputs.action[st.burn_in:].cpu().numpy()[:, None],
+                                       u.env_outputs.reward[st.burn_in:].cpu().numpy()[:, None],
+                                       u.env_outputs.done[st.burn_in:].cpu().numpy()[:, None], st.discounting,
+                                       n_steps=st.n_steps)
+    np.testing.assert_allclose(float(u.priority), float(prio[0]), rtol=1e-4, atol=1e-6)
+  for k, u in enumerate(items[:5]):
+    # first unroll of environment k: zero padding, then the behaviour Q values == a training-mode
+    # unroll of the real steps from the initial state (the state the environment was reset to)
+    assert float(u.agent_outputs.q_values[:st.burn_in].abs().max()) == 0.0
+    assert float(u.agent_state.core_state[0].abs().max()) == 0.0
+    tm = lambda t: t[st.burn_in:].unsqueeze(1)
+    env = utils.EnvOutput(*(tm(x) for x in u.env_outputs))
+    out, _ = agent((tm(u.prev_actions), env), agent.initial_state(1), unroll=True)
+    np.testing.assert_allclose(out.q_values[:, 0].cpu().numpy(), u.agent_outputs.q_values[st.burn_in:].cpu().numpy(),
+                               rtol=2e-4, atol=2e-5)
+    # the actions handed back to the actors are the ones recorded (after epsilon-greedy)
+    assert returned[k][:5] == u.agent_outputs.action[st.burn_in:].cpu().tolist()
+  # consecutive unrolls of an environment overlap on burn_in + 1 rows (UnrollStore :234-252)
+  for k in range(5):
+    a, b = items[k], items[k + 5]
+    for x, y in zip(utils.flatten(tuple(a[2:])), utils.flatten(tuple(b[2:]))):
+      assert torch.equal(x[-(st.burn_in + 1):], y[:st.burn_in + 1])
+  for u in items:
+    host.unroll_queue.enqueue(u)
+  replay = utils.PrioritizedReplay(st.replay_buffer_size, host.unroll_specs, st.importance_sampling_exponent)
+  feeder = learner.ReplayFeeder(replay, st, generator=torch.Generator(device='cuda').manual_seed(1))
+  assert learner.get_replay_insertion_batch_size(st) == 4
+  assert learner_loop.fill_replay(host, feeder) and feeder.ready() and replay.num_inserted == 4
+  assert learner_loop.fill_replay(host, feeder) and replay.num_inserted == 8
+  step = learner.R2D2LearnerStep(agent, target, optimizers.Adam(1e-3, epsilon=1e-3), settings=st)
+  sampled = feeder.sample()
+  assert tuple(sampled.unrolls.env_outputs.observation.shape) == (7, 6) + obs      # time-major
+  loss, priorities, indices, norm = step.minimize(sampled)
+  feeder.update_priorities(indices, priorities)
+  agent.check_errors()
+  assert np.isfinite(float(loss)) and np.isfinite(float(norm)) and bool((priorities >= 0).all())
+  assert torch.equal(replay._priorities[indices], priorities) or len(set(indices.tolist())) < len(indices)
