@@ -160,7 +160,7 @@ class R2D2InferenceHost(object):
               ao, ao, utils.EnvOutput(*env_suf), ao, s.discounting, n_steps=s.n_steps,
               value_function_rescaling_epsilon=s.value_function_rescaling_epsilon)
           pending = learner.Unroll(first, priorities, *unrolls)
-          self.first_agent_states.replace(completed_ids, self.agent_states.read(completed_ids))   # :825-826
+          self.first_agent_states.replace(completed_ids, self.agent_states.read(completed_ids), check_unique=False)   # :825-826
       # update the current state and action (:829-830): one scatter launch
       curr_flat = [t.contiguous() for t in utils.flatten(curr_states)]
       _lib.rows_multi([(t, r, _lib.ROW_SCATTER) for t, r in zip(tables, curr_flat)] +

@@ -187,7 +187,8 @@ class InferenceHost(object):
             dst[col0:col0 + int(ids.numel())].copy_(src)
         completed_ids, _ = self.store.complete_into(int(done_host.size), self.assembler, on_placed)
         # the state the next unroll starts from = the state this step started from (:400-401)
-        self.first_agent_states.replace(completed_ids, tuple(s.index_select(0, pos_dev) for s in self._g_prev_states))
+        self.first_agent_states.replace(completed_ids, tuple(s.index_select(0, pos_dev) for s in self._g_prev_states),
+                                        check_unique=False)
       self._g_actions_pin.copy_(self._g_out.action, non_blocking=True)
       self.stream.synchronize()
     return self._g_actions_pin.numpy().copy()
@@ -249,7 +250,7 @@ class InferenceHost(object):
                                                   on_placed=on_placed)
         n_done = 0
         if placed:
-          self.first_agent_states.replace(completed_ids, self.agent_states.read(completed_ids))
+          self.first_agent_states.replace(completed_ids, self.agent_states.read(completed_ids), check_unique=False)
       else:
         completed_ids, unrolls = self.store.append(env_ids, (prev_actions, env_dev, agent_outputs),
                                                    check_duplicates=True)
@@ -260,7 +261,7 @@ class InferenceHost(object):
         for i in range(n_done):     # one queue element per unroll, as in the reference
           u = utils.pack_sequence_as(self.store._specs, [f[:, i] for f in flat])
           pending.append(Unroll((first[0][i], first[1][i]), *u))
-        self.first_agent_states.replace(completed_ids, self.agent_states.read(completed_ids))
+        self.first_agent_states.replace(completed_ids, self.agent_states.read(completed_ids), check_unique=False)
       # Update current state (:402-403) and return the actions (:405).
       # (ids are unique: UnrollStore.append checked them)  ONE scatter launch
       _lib.rows_multi([(self.agent_states._state[0], curr_states[0].contiguous(), _lib.ROW_SCATTER),

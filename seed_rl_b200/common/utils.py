@@ -397,11 +397,13 @@ class Aggregator(object):
     ids = self._ids(env_ids)
     return pack_sequence_as(self._specs, [s.index_select(0, ids) for s in self._state])
 
-  def replace(self, env_ids, values, debug_op_name='', debug_tensors=None):  # :519-543
+  def replace(self, env_ids, values, debug_op_name='', debug_tensors=None, check_unique=True):  # :519-543
+    """check_unique=False skips the duplicate-id assertion (a device sort + a host read-back) for
+    callers whose ids are unique by construction (ids the unroll store just reported complete)."""
     ids = self._ids(env_ids)
     if ids.dim() != 1:
       raise ValueError('Invalid rank for aggregator %s' % self.name)
-    if torch.unique(ids).numel() != ids.numel():
+    if check_unique and torch.unique(ids).numel() != ids.numel():
       raise ValueError('Duplicate environment ids in Aggregator: %s with op name "%s"' %
                        (self.name, debug_op_name))
     assert_same_structure(values, self._specs)

@@ -87,9 +87,29 @@ sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
 __global__ void colsum_kernel(int M, int N, const float* __restrict__ X, int ld, const float* __restrict__ w,
                               int ldw, float* __restrict__ out);
 
+// C[m] = bias + A[m, :] . b   (N == 1: the baseline / value heads).  One warp per row, fixed-order
+// shuffle reduction; the tiled kernel would run M/64 CTAs whose threads each loop over all of K.
+__global__ void __launch_bounds__(256) rowdot_kernel(int M, int K, const float* __restrict__ A, int lda,
+                                                      const float* __restrict__ b, const float* __restrict__ bias,
+                                                      float* __restrict__ C) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* a = A + (size_t)row * lda;
+  float s = 0.f;
+  for (int k = lane; k < K; k += 32) s = fmaf(a[k], __ldg(b + k), s);
+  s = warp_sum(s);
+  if (lane == 0) C[row] = s + (bias ? __ldg(bias) : 0.f);
+}
+
 int sgemm(bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
           float* C, int ldc, const GemmEpi& e, cudaStream_t st) {
   if (M <= 0 || N <= 0) return SEEDRL_OK;
+  if (!ta && !tb && N == 1 && ldb == 1 && ldc == 1 && !e.mask && !e.relu && !e.accumulate && !e.a_relu) {
+    rowdot_kernel<<<ceil_div(M, 8), 256, 0, st>>>(M, K, A, lda, B, e.bias, C);
+    count_launch(PC_GEMM, st);
+    SEEDRL_CHECK_LAUNCH();
+    return SEEDRL_OK;
+  }
   if (ta && N == 1 && ldc == 1 && !e.bias && !e.mask && !e.relu && !e.accumulate && !e.a_relu) {
     // C[M,1] = A^T b: a weighted column sum spread over M/32 CTAs (the tiled kernel would run 4 CTAs)
     colsum_kernel<<<ceil_div(M, 32), 1024, 0, st>>>(K, M, A, lda, B, ldb, C);
