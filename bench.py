@@ -409,7 +409,7 @@ def run_r2d2(args):
       fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / k
-  for _ in range(max(args.warmup, 8)):      # the caching allocator settles after a few sample/gather shapes
+  for _ in range(max(args.warmup, 16)):     # the caching allocator settles after a dozen sample/gather shapes
     one_step(False)
   sampler = ClockSampler(torch.cuda.current_device())
   n0 = _lib.launch_count()
@@ -420,7 +420,7 @@ def run_r2d2(args):
   ms_e2e = timed(lambda: float(one_step(True)), args.steps)
   frames = B * st.unroll_length
   line = {'metric': R2D2_METRIC, 'value': frames / (ms * 1e-3), 'unit': UNIT, 'n_gpus': 1, 'steps': args.steps,
-          'warmup': max(args.warmup, 8), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+          'warmup': max(args.warmup, 16), 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
           'vs_baseline': None, 'dtype': 'bf16x3 (fp32-faithful tensor-core contraction), f32 elsewhere',
           'data': 'synthetic', 'config': r2d2_config(args), 'clocks': clocks,
           'e2e': {'value': frames / (ms_e2e * 1e-3), 'unit': UNIT, 'ms_per_step': ms_e2e,

@@ -363,9 +363,11 @@ int seedrl_r2d2_net_forward(const seedrl_r2d2_net* net, const float* params, int
                             const uint8_t* frames, const float* h0, const float* c0, float* q_values,
                             int32_t* action, float* h_out, float* c_out, void* workspace,
                             size_t workspace_bytes, seedrl_stream_t stream);
+/* `frames`: the stacked frames the forward of this unroll ran on (the first convolution's weight
+ * gradient gathers its operand from them; nothing is kept of them in the workspace). */
 int seedrl_r2d2_net_backward(const seedrl_r2d2_net* net, const float* params, int T, int B,
-                             const uint8_t* done, const float* dq, float* grads, void* workspace,
-                             size_t workspace_bytes, seedrl_stream_t stream);
+                             const uint8_t* frames, const uint8_t* done, const float* dq, float* grads,
+                             void* workspace, size_t workspace_bytes, seedrl_stream_t stream);
 int seedrl_r2d2_net_check_error(const seedrl_r2d2_net* net, int T, int B, void* workspace,
                                 size_t workspace_bytes, seedrl_stream_t stream);
 
@@ -427,6 +429,9 @@ int seedrl_debug_set_wgrad_chunk(int kc);
  * of 512 / 256 / 128 not above `mt` that keeps two CTAs per SM is used (default 512). */
 int seedrl_debug_set_conv_tile(int mt);
 int seedrl_debug_set_gemm_bk(int bk);     /* gemm_tc_kernel K elements per staged block: 64 or 32 */
+/* 0 = the im2col convolutions (IMPALA shallow net, R2D2 body) materialise their matrices instead of
+ * gathering them while the GEMM stages its operand (default 1; bit-identical results). */
+int seedrl_debug_set_gemm_gather(int on);
 /* 1 = conv_mode 3 keeps the dense first-layer backward (pool backward + full-resolution weight
  * gradient) instead of csrc/conv_first.cu's gather from the pooled gradient (A/B parity tests). */
 int seedrl_debug_set_first_layer_dense(int on);
@@ -462,6 +467,10 @@ int seedrl_debug_gemm_tc(int ta, int tb, int split, int M, int N, int K, const f
                          const float* B, int ldb, float* C, int ldc, const float* bias,
                          const float* mask, int ldm, int relu, int accumulate, int a_relu,
                          float* ws, size_t ws_bytes, int* error_flag, seedrl_stream_t stream);
+/* out[n] = sum_m X[m*ld + n] (the bias gradients, reference Dense / Conv2D bias variables); ws (may be
+ * NULL) is scratch for the row-slab path taken by tall dense matrices (ld == N, N a power of two). */
+int seedrl_debug_colsum(int M, int N, const float* X, int ld, float* out, float* ws, size_t ws_bytes,
+                        seedrl_stream_t stream);
 int seedrl_debug_sgemm(int ta, int tb, int M, int N, int K, const float* A, int lda,
                        const float* B, int ldb, float* C, int ldc, const float* bias,
                        const float* mask, int ldm, int relu, int accumulate, int a_relu,

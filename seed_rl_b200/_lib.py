@@ -132,7 +132,7 @@ SIGNATURES = {
     'seedrl_r2d2_net_workspace_bytes': (c_size_t, [P, c_int, c_int]),
     'seedrl_r2d2_net_forward':
         (c_int, [P, P, c_int, c_int, P, P, P, P, P, P, P, P, P, P, P, c_size_t, P]),
-    'seedrl_r2d2_net_backward': (c_int, [P, P, c_int, c_int, P, P, P, P, c_size_t, P]),
+    'seedrl_r2d2_net_backward': (c_int, [P, P, c_int, c_int, P, P, P, P, P, c_size_t, P]),
     'seedrl_r2d2_net_check_error': (c_int, [P, c_int, c_int, P, c_size_t, P]),
     'seedrl_r2d2_stack_frames': (c_int, [c_int, c_int, c_int, c_int, P, P, P, P, P, P]),
     'seedrl_r2d2_loss_scratch_bytes': (c_size_t, [c_int, c_int, c_int]),
@@ -171,6 +171,8 @@ SIGNATURES = {
     'seedrl_debug_gemm_tc':
         (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_int, P, c_int, P, P, c_int, c_int, c_int,
                  c_int, P, c_size_t, P, P]),
+    'seedrl_debug_set_gemm_gather': (c_int, [c_int]),
+    'seedrl_debug_colsum': (c_int, [c_int, c_int, P, c_int, P, P, c_size_t, P]),
     'seedrl_debug_sgemm':
         (c_int, [c_int, c_int, c_int, c_int, c_int, P, c_int, P, c_int, P, c_int, P, P, c_int,
                  c_int, c_int, c_int, P]),

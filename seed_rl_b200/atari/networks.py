@@ -197,7 +197,7 @@ class DuelingLSTMDQNNet(object):
   def check_errors(self):
     if self._saved is None:
       return
-    T, B, _, ws = self._saved
+    T, B, _, ws, _ = self._saved
     _lib.check(_lib.lib().seedrl_r2d2_net_check_error(self._h, T, B, _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
 
   def __call__(self, input_, agent_state, unroll=False, is_training=False):
@@ -226,7 +226,7 @@ class DuelingLSTMDQNNet(object):
         _lib.ptr(stacked), _lib.ptr(h0), _lib.ptr(c0), _lib.ptr(q), _lib.ptr(action), _lib.ptr(h), _lib.ptr(c),
         _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
     if is_training:
-      self._saved = (T, B, done, ws)
+      self._saved = (T, B, done, ws, stacked)
     out = AgentOutput(action, q)
     if not unroll:
       out = AgentOutput(*(t.squeeze(0) for t in out))
@@ -236,13 +236,13 @@ class DuelingLSTMDQNNet(object):
     """d loss / d parameters of the last is_training unroll -> self.grads (overwritten)."""
     if self._saved is None:
       raise RuntimeError('backward() needs a preceding __call__(..., unroll=True, is_training=True)')
-    T, B, done, ws = self._saved
+    T, B, done, ws, stacked = self._saved
     dq = _lib.require_cuda(dq, torch.float32, 'dq')
     if tuple(dq.shape) != (T, B, self._num_actions):
       raise ValueError('dq must be [T, B, num_actions] of the training unroll')
     _lib.check(_lib.lib().seedrl_r2d2_net_backward(
-        self._h, _lib.ptr(self.params), T, B, _lib.ptr(done), _lib.ptr(dq), _lib.ptr(self.grads), _lib.ptr(ws),
-        ws.numel(), _lib.stream_ptr()))
+        self._h, _lib.ptr(self.params), T, B, _lib.ptr(stacked), _lib.ptr(done), _lib.ptr(dq), _lib.ptr(self.grads),
+        _lib.ptr(ws), ws.numel(), _lib.stream_ptr()))
     return self.grads
 
   def state_dict(self):

@@ -162,7 +162,65 @@ colsum_kernel(int M, int N, const float* __restrict__ X, int ld, const float* __
   }
 }
 
-int colsum(int M, int N, const float* X, int ld, float* out, cudaStream_t st) {
+// Stage 1 of the tall column sum (bias gradients of the im2col convolutions: M = frames x positions
+// rows, N = 16..64 columns -- one CTA per 32 columns would leave a single CTA walking the whole
+// matrix).  CTA s reduces rows [s*rps, (s+1)*rps) of a dense [M][N] matrix (ld == N, N a power of two
+// <= 2048).  512 threads sweep 2048 consecutive floats per step and rps*N is a multiple of 2048, so a
+// thread meets the same four columns every step; four 16-byte streaming loads in flight per thread.
+// Fixed slab map and fixed-order adds => deterministic.
+__global__ void __launch_bounds__(512)
+colsum_slab_kernel(int M, int N, int rps, const float* __restrict__ X, float* __restrict__ part) {
+  __shared__ float4 red[512];
+  const int t = threadIdx.x;
+  const size_t r0 = (size_t)blockIdx.x * rps;
+  const size_t r1 = r0 + rps < (size_t)M ? r0 + rps : (size_t)M;
+  const float4* x4 = reinterpret_cast<const float4*>(X);
+  const size_t e4 = r1 * N / 4;
+  size_t j = r0 * N / 4 + t;
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+  for (; j + 3 * 512 < e4; j += 4 * 512) {
+    const float4 v0 = __ldcs(x4 + j), v1 = __ldcs(x4 + j + 512), v2 = __ldcs(x4 + j + 1024), v3 = __ldcs(x4 + j + 1536);
+    a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+    a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+    a2.x += v2.x; a2.y += v2.y; a2.z += v2.z; a2.w += v2.w;
+    a3.x += v3.x; a3.y += v3.y; a3.z += v3.z; a3.w += v3.w;
+  }
+  for (; j < e4; j += 512) {
+    const float4 v0 = __ldcs(x4 + j);
+    a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+  }
+  red[t] = make_float4((a0.x + a1.x) + (a2.x + a3.x), (a0.y + a1.y) + (a2.y + a3.y),
+                       (a0.z + a1.z) + (a2.z + a3.z), (a0.w + a1.w) + (a2.w + a3.w));
+  __syncthreads();
+  const int G = N >> 2;            // column groups; thread t owns group t % G
+  if (t < G) {
+    float4 s = red[t];
+    for (int k = t + G; k < 512; k += G) {
+      const float4 v = red[k];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    reinterpret_cast<float4*>(part + (size_t)blockIdx.x * N)[t] = s;
+  }
+}
+
+int colsum(int M, int N, const float* X, int ld, float* out, cudaStream_t st, float* ws, size_t ws_bytes) {
+  // tall dense matrices: row slabs over ~4 CTAs per SM, then the column sum of the slab partials
+  const bool pow2 = N >= 4 && N <= 2048 && (N & (N - 1)) == 0;
+  if (ws && pow2 && ld == N && (size_t)M * N >= ((size_t)1 << 20) && (reinterpret_cast<uintptr_t>(X) & 15) == 0) {
+    const int sweep = 2048 / N;                                   // rows per 512-thread sweep
+    int rps = ceil_div(ceil_div(M, 4 * kNumSMs), sweep) * sweep;   // rows per slab
+    if (rps < 8 * sweep) rps = 8 * sweep;
+    const int S = ceil_div(M, rps);
+    if ((size_t)S * N * sizeof(float) <= ws_bytes && S > 1) {
+      colsum_slab_kernel<<<S, 512, 0, st>>>(M, N, rps, X, ws);
+      count_launch(PC_GEMM, st);
+      SEEDRL_CHECK_LAUNCH();
+      colsum_kernel<<<ceil_div(N, 32), 1024, 0, st>>>(S, N, ws, N, nullptr, 0, out);
+      count_launch(PC_GEMM, st);
+      SEEDRL_CHECK_LAUNCH();
+      return SEEDRL_OK;
+    }
+  }
   colsum_kernel<<<ceil_div(N, 32), 1024, 0, st>>>(M, N, X, ld, nullptr, 0, out);
   count_launch(PC_GEMM, st);
   SEEDRL_CHECK_LAUNCH();

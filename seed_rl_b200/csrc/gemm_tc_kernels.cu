@@ -42,6 +42,7 @@ struct GemmTcParams {
   int vecA, vecB;               // 16-byte aligned rows: float4 loads
   GemmEpi e;
   int* error_flag;
+  ConvGather cg;                // GATHER kernels: op(A) = im2col(cg.x)
 };
 
 // 8 consecutive elements along the contiguous direction of a row-major matrix (raw fp32, two
@@ -67,6 +68,36 @@ __device__ __forceinline__ RawUnit load_raw(const float* __restrict__ P, int ld,
   }
   return r;
 }
+// 8 consecutive columns (kh, kw, c) of row `pos` = (n, ho, wo) of the im2col matrix, read from the
+// NHWC tensor itself: x[n][ho*S + kh][wo*S ...][...] is contiguous over (kw, c) for a fixed kh.
+// kc0 % 8 == 0 and KC % 8 == 0 (host-checked), so a unit never straddles two kernel rows.
+__device__ __forceinline__ RawUnit load_gather(const ConvGather& g, int pos, int kc0, int R, int Cn) {
+  RawUnit r;
+  r.a = make_float4(0.f, 0.f, 0.f, 0.f);
+  r.b = r.a;
+  if (pos < R && kc0 < Cn) {
+    const unsigned int t = fast_div((unsigned int)pos, g.wo_mul, g.wo_sh);
+    const int wo = pos - (int)t * g.Wo;
+    const unsigned int n = fast_div(t, g.ho_mul, g.ho_sh);
+    const int ho = (int)t - (int)n * g.Ho;
+    const int kh = (int)fast_div((unsigned int)kc0, g.kc_mul, g.kc_sh);
+    const int rem = kc0 - kh * g.KC;
+    const size_t off = (((size_t)n * g.H + (size_t)(ho * g.S + kh)) * g.W + (size_t)(wo * g.S)) * g.C + rem;
+    if (g.u8) {
+      const uint2 v = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const uint8_t*>(g.x) + off));
+      const float k = 1.0f / 255.0f;
+      r.a = make_float4((float)(v.x & 0xffu) * k, (float)((v.x >> 8) & 0xffu) * k,
+                        (float)((v.x >> 16) & 0xffu) * k, (float)(v.x >> 24) * k);
+      r.b = make_float4((float)(v.y & 0xffu) * k, (float)((v.y >> 8) & 0xffu) * k,
+                        (float)((v.y >> 16) & 0xffu) * k, (float)(v.y >> 24) * k);
+    } else {
+      const float4* src = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(g.x) + off);
+      r.a = __ldg(src);
+      r.b = __ldg(src + 1);
+    }
+  }
+  return r;
+}
 // -> one bf16x8 unit (+ the residual unit for bf16x3)
 template <bool SPLIT>
 __device__ __forceinline__ void store_unit(RawUnit r, bool relu, uint4* hi_dst, uint4* lo_dst) {
@@ -78,7 +109,7 @@ __device__ __forceinline__ void store_unit(RawUnit r, bool relu, uint4* hi_dst, 
   if (SPLIT) *lo_dst = pack8_bf16(bf16_resid4(r.a), bf16_resid4(r.b));
 }
 
-template <bool TA, bool TB, bool SPLIT, int kGtBK>
+template <bool TA, bool TB, bool SPLIT, int kGtBK, bool GATHER>
 __global__ void __launch_bounds__(kGtThreads)
 gemm_tc_kernel(const GemmTcParams p) {
   constexpr int S = SPLIT ? 2 : 1;
@@ -136,8 +167,13 @@ gemm_tc_kernel(const GemmTcParams p) {
 #pragma unroll
     for (int r = 0; r < AI; ++r) {
       const int u = tid + r * kGtThreads;
-      if (!TA) ra[r] = load_raw(p.A, p.lda, m0 + u / KG, k0 + (u % KG) * 8, p.M, p.K, p.vecA != 0);   // A[M,K]
-      else     ra[r] = load_raw(p.A, p.lda, k0 + (u >> 4), m0 + (u & 15) * 8, p.K, p.M, p.vecA != 0);  // A stored [K,M]
+      if (GATHER) {           // rows of the im2col matrix are positions: M of the forward, K of the weight gradient
+        if (!TA) ra[r] = load_gather(p.cg, m0 + u / KG, k0 + (u % KG) * 8, p.M, p.K);
+        else     ra[r] = load_gather(p.cg, k0 + (u >> 4), m0 + (u & 15) * 8, p.K, p.M);
+      } else {
+        if (!TA) ra[r] = load_raw(p.A, p.lda, m0 + u / KG, k0 + (u % KG) * 8, p.M, p.K, p.vecA != 0);   // A[M,K]
+        else     ra[r] = load_raw(p.A, p.lda, k0 + (u >> 4), m0 + (u & 15) * 8, p.K, p.M, p.vecA != 0);  // A stored [K,M]
+      }
     }
     const int bng = BN >> 3;
 #pragma unroll
@@ -287,11 +323,31 @@ bool gemm_tc_supported(int M, int N, int K) { return M >= 64 && N >= 16 && K >= 
 
 size_t gemm_tc_workspace_bytes() { return (size_t)48 << 20; }
 
+static int g_gemm_gather = getenv("SEEDRL_GEMM_GATHER") ? atoi(getenv("SEEDRL_GEMM_GATHER")) : 1;
+void gemm_tc_set_gather(int on) { g_gemm_gather = on; }
+bool gemm_tc_gather_enabled() { return g_gemm_gather != 0; }
+
+bool conv_gather_setup(const void* x, int u8, int N, int H, int W, int C, int K, int S, ConvGather* g) {
+  const int Ho = (H - K) / S + 1, Wo = (W - K) / S + 1, KC = K * C;
+  if (Ho < 2 || Wo < 2 || KC < 8 || (KC & 7)) return false;
+  if ((long long)N * Ho * Wo >= (1ll << 31)) return false;                 // fast_div domain
+  if (u8 ? (((W * C) & 7) || ((S * C) & 7) || (reinterpret_cast<uintptr_t>(x) & 7))
+         : ((C & 3) || (reinterpret_cast<uintptr_t>(x) & 15)))
+    return false;                                                            // 8-byte / 16-byte loads
+  g->x = x; g->u8 = u8; g->H = H; g->W = W; g->C = C; g->S = S; g->Ho = Ho; g->Wo = Wo; g->KC = KC;
+  fast_div_setup((unsigned int)Wo, &g->wo_mul, &g->wo_sh);
+  fast_div_setup((unsigned int)Ho, &g->ho_mul, &g->ho_sh);
+  fast_div_setup((unsigned int)KC, &g->kc_mul, &g->kc_sh);
+  return true;
+}
+
 int gemm_tc(bool ta, bool tb, int split, int M, int N, int K, const float* A, int lda, const float* B,
             int ldb, float* C, int ldc, const GemmEpi& e, float* ws, size_t ws_bytes, int* err,
-            cudaStream_t st) {
+            cudaStream_t st, const ConvGather* cg) {
   if (M <= 0 || N <= 0) return SEEDRL_OK;
+  SEEDRL_CHECK_ARG(!cg || (!tb && ((ta ? M : K) & 7) == 0), "gathered operand: tb or a ragged kernel row");
   GemmTcParams p;
+  if (cg) p.cg = *cg; else p.cg = ConvGather{};
   p.M = M; p.N = N; p.K = K; p.A = A; p.lda = lda; p.B = B; p.ldb = ldb; p.C = C; p.ldc = ldc;
   p.e = e; p.error_flag = err;
   const int n16 = ((N + 15) / 16) * 16;
@@ -326,15 +382,20 @@ int gemm_tc(bool ta, bool tb, int split, int M, int N, int K, const float* A, in
   const size_t epi = (size_t)(kGtThreads / 32) * 32 * 33 * 4;      // the epilogue's transpose scratch aliases the stages
   if (smem < epi) smem = epi;
   dim3 grid(ceil_div(N, p.BN), ceil_div(M, kGtBM), splits);
-#define SEEDRL_GT_LAUNCH1(TA_, TB_, SP_, BK_)                                                   \
+#define SEEDRL_GT_LAUNCH2(TA_, TB_, SP_, BK_, G_)                                               \
   do {                                                                                          \
     static bool attr = false;                                                                   \
     if (!attr) {                                                                                \
-      SEEDRL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<TA_, TB_, SP_, BK_>,                      \
+      SEEDRL_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<TA_, TB_, SP_, BK_, G_>,                  \
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); \
       attr = true;                                                                              \
     }                                                                                           \
-    gemm_tc_kernel<TA_, TB_, SP_, BK_><<<grid, kGtThreads, smem, st>>>(p);                      \
+    gemm_tc_kernel<TA_, TB_, SP_, BK_, G_><<<grid, kGtThreads, smem, st>>>(p);                  \
+  } while (0)
+#define SEEDRL_GT_LAUNCH1(TA_, TB_, SP_, BK_)                                                   \
+  do {                                                                                          \
+    if (cg && !(TB_)) SEEDRL_GT_LAUNCH2(TA_, false, SP_, BK_, true);                            \
+    else SEEDRL_GT_LAUNCH2(TA_, TB_, SP_, BK_, false);                                          \
   } while (0)
 #define SEEDRL_GT_LAUNCH(TA_, TB_, SP_)                                                         \
   do {                                                                                          \
@@ -355,6 +416,7 @@ int gemm_tc(bool ta, bool tb, int split, int M, int N, int K, const float* A, in
   }
 #undef SEEDRL_GT_LAUNCH
 #undef SEEDRL_GT_LAUNCH1
+#undef SEEDRL_GT_LAUNCH2
   count_launch(PC_GEMM, st);
   SEEDRL_CHECK_LAUNCH();
   if (splits > 1) {

@@ -172,15 +172,35 @@ struct GemmEpi {
 inline GemmEpi epi_none() { return GemmEpi{nullptr, nullptr, 0, 0, 0, 0}; }
 int sgemm(bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
           float* C, int ldc, const GemmEpi& e, cudaStream_t st);
-int colsum(int M, int N, const float* X, int ld, float* out, cudaStream_t st);
+// out[n] = sum_m X[m*ld + n].  `ws` (optional scratch, e.g. the split-K workspace -- stream-ordered reuse)
+// enables the row-slab path for tall matrices.
+int colsum(int M, int N, const float* X, int ld, float* out, cudaStream_t st, float* ws = nullptr,
+           size_t ws_bytes = 0);
 // gemm_tc_kernels.cu (tcgen05): same contract as sgemm; split = bf16x3 operands; `ws` holds
 // split-K partials (gemm_tc_workspace_bytes()); *err is set if a bounded mbarrier wait expires.
 bool gemm_tc_supported(int M, int N, int K);
 void gemm_tc_set_bk(int bk);                 // K elements per staged block: 64 or 32 (tuning knob)
 size_t gemm_tc_workspace_bytes();
+// op(A) = the im2col matrix of an NHWC tensor x[N][H][W][C] for a K x K / stride S 'valid' convolution
+// (rows = output positions (n, ho, wo), columns = (kh, kw, c)), gathered while the GEMM stages its A
+// blocks and never materialised: 8 consecutive columns of a row are 8 consecutive elements of x.
+struct ConvGather {
+  const void* x;
+  int u8;                    // uint8 frames, scaled by 1/255 (atari/networks.py:283, dmlab/networks.py:93)
+  int H, W, C, S, Ho, Wo;
+  int KC;                    // K * C: one kernel row, contiguous in x
+  unsigned int wo_mul, ho_mul, kc_mul;   // fast_div by Wo / Ho / KC
+  int wo_sh, ho_sh, kc_sh;
+};
+// False when the geometry does not give aligned 8-element groups (the caller materialises the matrix).
+bool conv_gather_setup(const void* x, int u8, int N, int H, int W, int C, int K, int S, ConvGather* g);
+void gemm_tc_set_gather(int on);             // 0: callers keep the explicit im2col (A/B tests)
+bool gemm_tc_gather_enabled();
+// cg != nullptr: op(A) is the gathered im2col matrix (A / lda ignored; tb must be false).  ta = false:
+// C[positions, N] = col * B (the convolution);  ta = true: C[K*K*C, N] = col^T * B (its weight gradient).
 int gemm_tc(bool ta, bool tb, int split, int M, int N, int K, const float* A, int lda, const float* B,
             int ldb, float* C, int ldc, const GemmEpi& e, float* ws, size_t ws_bytes, int* err,
-            cudaStream_t st);
+            cudaStream_t st, const ConvGather* cg = nullptr);
 int core_input_tail(int Nrows, int D, int A, const float* reward, const int64_t* prev_action,
                     float* core_in, cudaStream_t st);
 int lstm_mask_state(int B, int Hd, const uint8_t* done, const float* h_src, float* h_dst,

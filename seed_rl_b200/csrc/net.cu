@@ -550,6 +550,21 @@ static int torso_forward_planes(const seedrl_net* n, const float* prm, const Pla
   return SEEDRL_OK;
 }
 
+// Shallow net, tensor-core modes: layer 0 = conv 8x8/4 on the uint8 frames, layer 1 = conv 4x4/2 on a1.
+static bool shallow_gathered(const seedrl_net* n, int layer, int N, const void* x, ConvGather* cg) {
+  if (n->conv_mode < 1 || !gemm_tc_gather_enabled()) return false;
+  if (layer == 0)
+    return gemm_tc_supported(N * n->sh_h1 * n->sh_w1, 16, 64 * n->cfg.obs_c) &&
+           conv_gather_setup(x, 1, N, n->cfg.obs_h, n->cfg.obs_w, n->cfg.obs_c, 8, 4, cg);
+  return gemm_tc_supported(N * n->sh_h2 * n->sh_w2, 32, 256) && conv_gather_setup(x, 0, N, n->sh_h1, n->sh_w1, 16, 4, 2, cg);
+}
+static int run_gemm_gather(const seedrl_net* n, void* ws, const Plan& pl, bool ta, int M, int N, int K,
+                           const ConvGather& cg, const float* B, int ldb, float* C, int ldc, const GemmEpi& e,
+                           cudaStream_t st) {
+  return gemm_tc(ta, false, n->conv_mode >= 2, M, N, K, nullptr, 0, B, ldb, C, ldc, e, W<float>(ws, pl.gemm_ws),
+                 gemm_tc_workspace_bytes(), W<int>(ws, pl.tcerr), st, &cg);
+}
+
 static int torso_forward_shallow(const seedrl_net* n, const float* prm, const Plan& pl,
                                  const uint8_t* obs, void* ws, cudaStream_t st) {
   const int N = pl.N;
@@ -559,15 +574,25 @@ static int torso_forward_shallow(const seedrl_net* n, const float* prm, const Pl
     // tensor-core modes: im2col + tcgen05 GEMM with bias + ReLU in the epilogue (the R2D2 body's path)
     const int C = n->cfg.obs_c, K0 = 64 * C, K1 = 16 * 16;
     float* col0 = W<float>(ws, pl.sh_col0); float* col1 = W<float>(ws, pl.sh_col1);
-    SEEDRL_TRY(im2col_nhwc(N, n->cfg.obs_h, n->cfg.obs_w, C, 8, 4, 1, obs, col0, st));
     GemmEpi e = epi_none();
     e.bias = P(n, prm, n->sh_c0b); e.relu = 1;
-    SEEDRL_TRY(run_gemm(n, ws, pl, false, false, N * n->sh_h1 * n->sh_w1, 16, K0, col0, K0, P(n, prm, n->sh_c0w), 16, a1,
-                        16, e, st));
-    SEEDRL_TRY(im2col_nhwc(N, n->sh_h1, n->sh_w1, 16, 4, 2, 0, a1, col1, st));
+    const int M0 = N * n->sh_h1 * n->sh_w1, M1 = N * n->sh_h2 * n->sh_w2;
+    // the im2col matrices are gathered inside the GEMM's operand staging where the geometry allows it
+    // (kernels.h ConvGather); otherwise materialised (and kept for the weight gradient)
+    ConvGather cg;
+    if (shallow_gathered(n, 0, N, obs, &cg)) {
+      SEEDRL_TRY(run_gemm_gather(n, ws, pl, false, M0, 16, K0, cg, P(n, prm, n->sh_c0w), 16, a1, 16, e, st));
+    } else {
+      SEEDRL_TRY(im2col_nhwc(N, n->cfg.obs_h, n->cfg.obs_w, C, 8, 4, 1, obs, col0, st));
+      SEEDRL_TRY(run_gemm(n, ws, pl, false, false, M0, 16, K0, col0, K0, P(n, prm, n->sh_c0w), 16, a1, 16, e, st));
+    }
     e.bias = P(n, prm, n->sh_c1b);
-    SEEDRL_TRY(run_gemm(n, ws, pl, false, false, N * n->sh_h2 * n->sh_w2, 32, K1, col1, K1, P(n, prm, n->sh_c1w), 32, a2,
-                        32, e, st));
+    if (shallow_gathered(n, 1, N, a1, &cg)) {
+      SEEDRL_TRY(run_gemm_gather(n, ws, pl, false, M1, 32, K1, cg, P(n, prm, n->sh_c1w), 32, a2, 32, e, st));
+    } else {
+      SEEDRL_TRY(im2col_nhwc(N, n->sh_h1, n->sh_w1, 16, 4, 2, 0, a1, col1, st));
+      SEEDRL_TRY(run_gemm(n, ws, pl, false, false, M1, 32, K1, col1, K1, P(n, prm, n->sh_c1w), 32, a2, 32, e, st));
+    }
     return SEEDRL_OK;
   }
   SEEDRL_TRY(convgen_forward(N, n->cfg.obs_h, n->cfg.obs_w, n->cfg.obs_c, 16, 8, 4, 1, obs,
@@ -809,12 +834,19 @@ static int torso_backward_shallow(const seedrl_net* n, const float* prm, float* 
     const int M1 = N * n->sh_h2 * n->sh_w2, M0 = N * n->sh_h1 * n->sh_w1;
     float* col0 = W<float>(ws, pl.sh_col0); float* col1 = W<float>(ws, pl.sh_col1);
     const GemmEpi e0 = epi_none();
-    SEEDRL_TRY(run_gemm(n, ws, pl, true, false, K1, 32, M1, col1, K1, gA, 32, G(n, grd, n->sh_c1w), 32, e0, st));
-    SEEDRL_TRY(colsum(M1, 32, gA, 32, G(n, grd, n->sh_c1b), st));
+    ConvGather cg;
+    if (shallow_gathered(n, 1, N, a1, &cg))
+      SEEDRL_TRY(run_gemm_gather(n, ws, pl, true, K1, 32, M1, cg, gA, 32, G(n, grd, n->sh_c1w), 32, e0, st));
+    else
+      SEEDRL_TRY(run_gemm(n, ws, pl, true, false, K1, 32, M1, col1, K1, gA, 32, G(n, grd, n->sh_c1w), 32, e0, st));
+    SEEDRL_TRY(colsum(M1, 32, gA, 32, G(n, grd, n->sh_c1b), st, W<float>(ws, pl.gemm_ws), gemm_tc_workspace_bytes()));
     SEEDRL_TRY(run_gemm(n, ws, pl, false, true, M1, K1, 32, gA, 32, P(n, prm, n->sh_c1w), 32, col1, K1, e0, st));
     SEEDRL_TRY(col2im_nhwc(N, n->sh_h1, n->sh_w1, 16, 4, 2, col1, a1, gB, st));
-    SEEDRL_TRY(run_gemm(n, ws, pl, true, false, K0, 16, M0, col0, K0, gB, 16, G(n, grd, n->sh_c0w), 16, e0, st));
-    SEEDRL_TRY(colsum(M0, 16, gB, 16, G(n, grd, n->sh_c0b), st));
+    if (shallow_gathered(n, 0, N, obs, &cg))
+      SEEDRL_TRY(run_gemm_gather(n, ws, pl, true, K0, 16, M0, cg, gB, 16, G(n, grd, n->sh_c0w), 16, e0, st));
+    else
+      SEEDRL_TRY(run_gemm(n, ws, pl, true, false, K0, 16, M0, col0, K0, gB, 16, G(n, grd, n->sh_c0w), 16, e0, st));
+    SEEDRL_TRY(colsum(M0, 16, gB, 16, G(n, grd, n->sh_c0b), st, W<float>(ws, pl.gemm_ws), gemm_tc_workspace_bytes()));
     return SEEDRL_OK;
   }
   SEEDRL_TRY(convgen_wgrad(N, n->sh_h1, n->sh_w1, 16, 32, 4, 2, 0, a1, gA, G(n, grd, n->sh_c1w),
@@ -851,9 +883,9 @@ extern "C" int seedrl_net_backward(const seedrl_net* n, const float* prm, int T1
   // heads
   GemmEpi e = epi_none();
   SEEDRL_TRY(run_gemm(n, ws, pl, true, false, kHidden, A, N, hs, kHidden, dlogits, A, G(n, grd, n->p_pol_w), A, e, st));
-  SEEDRL_TRY(colsum(N, A, dlogits, A, G(n, grd, n->p_pol_b), st));
+  SEEDRL_TRY(colsum(N, A, dlogits, A, G(n, grd, n->p_pol_b), st, W<float>(ws, pl.gemm_ws), gemm_tc_workspace_bytes()));
   SEEDRL_TRY(run_gemm(n, ws, pl, true, false, kHidden, 1, N, hs, kHidden, dbaseline, 1, G(n, grd, n->p_base_w), 1, e, st));
-  SEEDRL_TRY(colsum(N, 1, dbaseline, 1, G(n, grd, n->p_base_b), st));
+  SEEDRL_TRY(colsum(N, 1, dbaseline, 1, G(n, grd, n->p_base_b), st, W<float>(ws, pl.gemm_ws), gemm_tc_workspace_bytes()));
   SEEDRL_TRY(run_gemm(n, ws, pl, false, true, N, kHidden, A, dlogits, A, P(n, prm, n->p_pol_w), A, dhs, kHidden, e, st));
   GemmEpi eacc = epi_none();
   eacc.accumulate = 1;
@@ -882,7 +914,7 @@ extern "C" int seedrl_net_backward(const seedrl_net* n, const float* prm, int T1
                    G(n, grd, n->p_core_u), 4 * kHidden, e, st));
   SEEDRL_TRY(run_gemm(n, ws, pl, true, false, CI, 4 * kHidden, N, xc, CI, dz, 4 * kHidden, G(n, grd, n->p_core_w),
                    4 * kHidden, e, st));
-  SEEDRL_TRY(colsum(N, 4 * kHidden, dz, 4 * kHidden, G(n, grd, n->p_core_b), st));
+  SEEDRL_TRY(colsum(N, 4 * kHidden, dz, 4 * kHidden, G(n, grd, n->p_core_b), st, W<float>(ws, pl.gemm_ws), gemm_tc_workspace_bytes()));
   // d dense_out = (dz W[:256,:]^T) * (dense_out > 0)
   GemmEpi em = epi_none();
   em.mask = xc; em.ldm = CI;
@@ -895,7 +927,7 @@ extern "C" int seedrl_net_backward(const seedrl_net* n, const float* prm, int T1
   ea.a_relu = n->cfg.net == SEEDRL_NET_DEEP ? 1 : 0;
   SEEDRL_TRY(run_gemm(n, ws, pl, true, false, n->flat, kHidden, N, flat_src, n->flat, dd, kHidden,
                    G(n, grd, n->p_dense_w), kHidden, ea, st));
-  SEEDRL_TRY(colsum(N, kHidden, dd, kHidden, G(n, grd, n->p_dense_b), st));
+  SEEDRL_TRY(colsum(N, kHidden, dd, kHidden, G(n, grd, n->p_dense_b), st, W<float>(ws, pl.gemm_ws), gemm_tc_workspace_bytes()));
   // every gradient of the arena's first bucket (heads, Dense, LSTM: floats [0, seedrl_net_grad_split))
   // is final here -- the conv torso's backward below only writes the second bucket
   if (t_head_ready) SEEDRL_CUDA(cudaEventRecord((cudaEvent_t)t_head_ready, st));
@@ -992,6 +1024,20 @@ extern "C" int seedrl_debug_sgemm(int ta, int tb, int M, int N, int K, const flo
                                   seedrl_stream_t stream) {
   GemmEpi e{bias, mask, ldm, relu, accumulate, a_relu};
   return sgemm(ta != 0, tb != 0, M, N, K, A, lda, B, ldb, C, ldc, e, (cudaStream_t)stream);
+}
+
+// 0: the im2col convolutions (shallow net, R2D2 body) materialise their matrices instead of gathering
+// them inside the GEMM (A/B parity tests; results are bit-identical).
+extern "C" int seedrl_debug_set_gemm_gather(int on) {
+  gemm_tc_set_gather(on);
+  return SEEDRL_OK;
+}
+
+// Column-sum test hook (bias gradients): out[n] = sum_m X[m*ld + n]; `ws` enables the row-slab path.
+extern "C" int seedrl_debug_colsum(int M, int N, const float* X, int ld, float* out, float* ws, size_t ws_bytes,
+                                   seedrl_stream_t stream) {
+  SEEDRL_CHECK_ARG(M >= 1 && N >= 1 && X && out && ld >= N, "bad arguments");
+  return colsum(M, N, X, ld, out, (cudaStream_t)stream, ws, ws_bytes);
 }
 
 // tcgen05 conv test hook: packs fp32 HWIO weights (optionally flipped/transposed for the

@@ -139,6 +139,21 @@ static int r_gemm(const seedrl_r2d2_net* n, void* ws, const RPlan& pl, bool ta, 
   return sgemm(ta, tb, M, N, K, A, lda, B, ldb, C, ldc, e, st);
 }
 
+// Tensor-core modes read the im2col matrix of a convolution straight from its NHWC input while the
+// GEMM stages its A blocks (kernels.h ConvGather): nothing is materialised for the forward or the
+// weight gradient.  False: geometry without aligned 8-element groups, SIMT mode, or switched off.
+static bool conv_gathered(const seedrl_r2d2_net* n, int N, const RConv& c, bool u8, const void* x, ConvGather* cg) {
+  const int K = c.k * c.k * c.cin, M = N * c.hout * c.wout;
+  return n->mode >= 1 && gemm_tc_gather_enabled() && gemm_tc_supported(M, c.cout, K) &&
+         gemm_tc_supported(K, c.cout, M) && conv_gather_setup(x, u8 ? 1 : 0, N, c.hin, c.win, c.cin, c.k, c.s, cg);
+}
+static int r_gemm_gather(const seedrl_r2d2_net* n, void* ws, const RPlan& pl, bool ta, int M, int N, int K,
+                         const ConvGather& cg, const float* B, int ldb, float* C, int ldc, const GemmEpi& e,
+                         cudaStream_t st) {
+  return gemm_tc(ta, false, n->mode >= 2, M, N, K, nullptr, 0, B, ldb, C, ldc, e, RW<float>(ws, pl.gemm_ws),
+                 gemm_tc_workspace_bytes(), RW<int>(ws, pl.tcerr), st, &cg);
+}
+
 // ------------------------------------------------------------------------------------------------
 // im2col: col[(n*Ho + ho)*Wo + wo][(kh*K + kw)*C + c] = x[n][ho*S + kh][wo*S + kw][c]  (* 1/255 for
 // uint8 frames).  Thread = VEC consecutive channels of one col element (VEC = 4 when C % 4 == 0).
@@ -392,12 +407,18 @@ extern "C" int seedrl_r2d2_net_forward(const seedrl_r2d2_net* n, const float* pr
     const RConv& c = n->conv[i];
     float* col = RW<float>(ws, pl.col[i]);
     float* act = RW<float>(ws, pl.act[i]);
-    SEEDRL_TRY(im2col(N, c, i == 0, x, col, st));
     GemmEpi e = epi_none();
     e.bias = RP(n, prm, c.b); e.relu = 1;
     const int K = c.k * c.k * c.cin;
-    SEEDRL_TRY(r_gemm(n, ws, pl, false, false, N * c.hout * c.wout, c.cout, K, col, K, RP(n, prm, c.w), c.cout, act,
-                      c.cout, e, st));
+    ConvGather cg;
+    if (conv_gathered(n, N, c, i == 0, x, &cg)) {
+      SEEDRL_TRY(r_gemm_gather(n, ws, pl, false, N * c.hout * c.wout, c.cout, K, cg, RP(n, prm, c.w), c.cout, act,
+                               c.cout, e, st));
+    } else {
+      SEEDRL_TRY(im2col(N, c, i == 0, x, col, st));
+      SEEDRL_TRY(r_gemm(n, ws, pl, false, false, N * c.hout * c.wout, c.cout, K, col, K, RP(n, prm, c.w), c.cout,
+                        act, c.cout, e, st));
+    }
     x = act;
   }
   float* xc = RW<float>(ws, pl.xc); float* z = RW<float>(ws, pl.z);
@@ -448,11 +469,11 @@ extern "C" int seedrl_r2d2_net_forward(const seedrl_r2d2_net* n, const float* pr
   return SEEDRL_OK;
 }
 
-// Backward of the unroll whose forward last used `ws` (same T, B).  grads = flat arena (overwritten).
+// Backward of the unroll whose forward last used `ws` (same T, B, frames).  grads = flat arena (overwritten).
 extern "C" int seedrl_r2d2_net_backward(const seedrl_r2d2_net* n, const float* prm, int T, int B,
-                                        const uint8_t* done, const float* dq, float* grd, void* ws, size_t ws_bytes,
-                                        seedrl_stream_t stream) {
-  SEEDRL_CHECK_ARG(n && prm && done && dq && grd && ws, "null pointer");
+                                        const uint8_t* frames, const uint8_t* done, const float* dq, float* grd,
+                                        void* ws, size_t ws_bytes, seedrl_stream_t stream) {
+  SEEDRL_CHECK_ARG(n && prm && frames && done && dq && grd && ws, "null pointer");
   const RPlan pl = r_plan(n, T, B);
   SEEDRL_CHECK_ARG(ws_bytes >= pl.total, "workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
@@ -478,14 +499,14 @@ extern "C" int seedrl_r2d2_net_backward(const seedrl_r2d2_net* n, const float* p
   em.mask = ah; em.ldm = 512;
   SEEDRL_TRY(r_gemm(n, ws, pl, false, true, N, 512, A, dadv, A, RP(n, prm, n->p_a_w), A, dah, 512, em, st));
   SEEDRL_TRY(r_gemm(n, ws, pl, true, false, kRH, 512, N, hs, kRH, dah, 512, RG(n, grd, n->p_ah_w), 512, e0, st));
-  SEEDRL_TRY(colsum(N, 512, dah, 512, RG(n, grd, n->p_ah_b), st));
+  SEEDRL_TRY(colsum(N, 512, dah, 512, RG(n, grd, n->p_ah_b), st, RW<float>(ws, pl.gemm_ws), gemm_tc_workspace_bytes()));
   // value stream
   SEEDRL_TRY(r_gemm(n, ws, pl, true, false, 512, 1, N, vh, 512, dv, 1, RG(n, grd, n->p_v_w), 1, e0, st));
-  SEEDRL_TRY(colsum(N, 1, dv, 1, RG(n, grd, n->p_v_b), st));
+  SEEDRL_TRY(colsum(N, 1, dv, 1, RG(n, grd, n->p_v_b), st, RW<float>(ws, pl.gemm_ws), gemm_tc_workspace_bytes()));
   em.mask = vh;
   SEEDRL_TRY(r_gemm(n, ws, pl, false, true, N, 512, 1, dv, 1, RP(n, prm, n->p_v_w), 1, dvh, 512, em, st));
   SEEDRL_TRY(r_gemm(n, ws, pl, true, false, kRH, 512, N, hs, kRH, dvh, 512, RG(n, grd, n->p_vh_w), 512, e0, st));
-  SEEDRL_TRY(colsum(N, 512, dvh, 512, RG(n, grd, n->p_vh_b), st));
+  SEEDRL_TRY(colsum(N, 512, dvh, 512, RG(n, grd, n->p_vh_b), st, RW<float>(ws, pl.gemm_ws), gemm_tc_workspace_bytes()));
   // d core output
   SEEDRL_TRY(r_gemm(n, ws, pl, false, true, N, kRH, 512, dah, 512, RP(n, prm, n->p_ah_w), 512, dhs, kRH, e0, st));
   SEEDRL_TRY(r_gemm(n, ws, pl, false, true, N, kRH, 512, dvh, 512, RP(n, prm, n->p_vh_w), 512, dhs, kRH, eacc, st));
@@ -500,7 +521,7 @@ extern "C" int seedrl_r2d2_net_backward(const seedrl_r2d2_net* n, const float* p
                     e0, st));
   SEEDRL_TRY(r_gemm(n, ws, pl, true, false, CI, 4 * kRH, N, xc, CI, dz, 4 * kRH, RG(n, grd, n->p_core_w), 4 * kRH, e0,
                     st));
-  SEEDRL_TRY(colsum(N, 4 * kRH, dz, 4 * kRH, RG(n, grd, n->p_core_b), st));
+  SEEDRL_TRY(colsum(N, 4 * kRH, dz, 4 * kRH, RG(n, grd, n->p_core_b), st, RW<float>(ws, pl.gemm_ws), gemm_tc_workspace_bytes()));
   // d dense_out = (dz W[:512,:]^T) * (dense_out > 0)
   em.mask = xc; em.ldm = CI;
   SEEDRL_TRY(r_gemm(n, ws, pl, false, true, N, kRH, 4 * kRH, dz, 4 * kRH, RP(n, prm, n->p_core_w), 4 * kRH, dd, kRH,
@@ -508,7 +529,7 @@ extern "C" int seedrl_r2d2_net_backward(const seedrl_r2d2_net* n, const float* p
   const float* flat = RW<float>(ws, pl.act[2]);
   SEEDRL_TRY(r_gemm(n, ws, pl, true, false, n->flat, kRH, N, flat, n->flat, dd, kRH, RG(n, grd, n->p_dense_w), kRH,
                     e0, st));
-  SEEDRL_TRY(colsum(N, kRH, dd, kRH, RG(n, grd, n->p_dense_b), st));
+  SEEDRL_TRY(colsum(N, kRH, dd, kRH, RG(n, grd, n->p_dense_b), st, RW<float>(ws, pl.gemm_ws), gemm_tc_workspace_bytes()));
   em.mask = flat; em.ldm = n->flat;
   SEEDRL_TRY(r_gemm(n, ws, pl, false, true, N, n->flat, kRH, dd, kRH, RP(n, prm, n->p_dense_w), kRH,
                     RW<float>(ws, pl.g[2]), n->flat, em, st));
@@ -518,8 +539,14 @@ extern "C" int seedrl_r2d2_net_backward(const seedrl_r2d2_net* n, const float* p
     const int K = c.k * c.k * c.cin, M = N * c.hout * c.wout;
     float* col = RW<float>(ws, pl.col[i]);
     const float* g = RW<float>(ws, pl.g[i]);
-    SEEDRL_TRY(r_gemm(n, ws, pl, true, false, K, c.cout, M, col, K, g, c.cout, RG(n, grd, c.w), c.cout, e0, st));
-    SEEDRL_TRY(colsum(M, c.cout, g, c.cout, RG(n, grd, c.b), st));
+    // weight gradient = im2col(input)^T g: gathered from the layer's input, or from the matrix the forward kept
+    const void* xin = i == 0 ? (const void*)frames : (const void*)RW<float>(ws, pl.act[i - 1]);
+    ConvGather cg;
+    if (conv_gathered(n, N, c, i == 0, xin, &cg))
+      SEEDRL_TRY(r_gemm_gather(n, ws, pl, true, K, c.cout, M, cg, g, c.cout, RG(n, grd, c.w), c.cout, e0, st));
+    else
+      SEEDRL_TRY(r_gemm(n, ws, pl, true, false, K, c.cout, M, col, K, g, c.cout, RG(n, grd, c.w), c.cout, e0, st));
+    SEEDRL_TRY(colsum(M, c.cout, g, c.cout, RG(n, grd, c.b), st, RW<float>(ws, pl.gemm_ws), gemm_tc_workspace_bytes()));
     if (i > 0) {
       SEEDRL_TRY(r_gemm(n, ws, pl, false, true, M, K, c.cout, g, c.cout, RP(n, prm, c.w), c.cout, col, K, e0, st));
       SEEDRL_TRY(col2im(N, c, col, RW<float>(ws, pl.act[i - 1]), RW<float>(ws, pl.g[i - 1]), st));

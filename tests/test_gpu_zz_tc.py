@@ -256,3 +256,32 @@ def test_gemm_tc_matches_numpy(ta, tb, M, N, K, epi, split):
   assert np.array_equal(got[:, N:], C0[:, N:])                  # nothing written past column N
   assert np.array_equal(outs[0], outs[1])                       # deterministic (split-K in slice order)
   assert np.abs(got[:, :N] - want).max() < TOL[split] * scale
+
+
+# ---------------------------------------------------------------- bias gradients (column sums)
+@pytest.mark.parametrize('M,N,ld,use_ws', [
+    (537600, 16, 16, True),      # shallow net conv 8x8/4 bias gradient at T=20, B=64 (row-slab path)
+    (108864, 32, 32, True), (6464, 2048, 2048, True), (1344, 1024, 1024, True), (100003, 64, 64, True),
+    (9024 * 49, 64, 64, True), (70001, 4, 4, True),
+    (537600, 16, 16, False),     # same matrix without scratch: one CTA per 32 columns
+    (1344, 18, 18, True), (1000, 32, 40, True), (21, 1, 1, True)])
+def test_colsum_matches_float64(M, N, ld, use_ws):
+  """out[n] = sum_m X[m, n] against a float64 sum; the slab path is deterministic and never writes
+  outside its partials."""
+  from seed_rl_b200 import _lib
+  L = _lib.lib()
+  g = torch.Generator(device='cuda').manual_seed(M + N)
+  X = torch.randn(M, ld, device='cuda', generator=g) + 0.25
+  ws = torch.full((1 << 20,), float('nan'), device='cuda') if use_ws else None
+  outs = []
+  for _ in range(2):
+    out = torch.full((N + 3,), 7.0, device='cuda')
+    _lib.check(L.seedrl_debug_colsum(M, N, _lib.ptr(X), ld, _lib.ptr(out), _lib.ptr(ws),
+                                     ws.numel() * 4 if use_ws else 0, _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    outs.append(out.cpu().numpy().copy())
+  want = X[:, :N].double().sum(0).cpu().numpy()
+  scale = float(X[:, :N].double().abs().sum(0).max())
+  assert np.array_equal(outs[0], outs[1])
+  assert np.all(outs[0][N:] == 7.0)
+  assert np.abs(outs[0][:N] - want).max() < 2e-6 * scale
