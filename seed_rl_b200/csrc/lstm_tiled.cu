@@ -256,9 +256,15 @@ __global__ void __launch_bounds__(kTlThreads, 1) lstm2_bwd_kernel(const Lstm2Arg
 }
 
 // ------------------------------------------------------------------------------------------------
-static int tile_rows(int B) {
-  // 8 batch tiles when the batch allows it, rows per tile a multiple of 8, at most kTlMaxRB
-  int rb = ((B + 7) / 8 + 7) / 8 * 8;
+static int tile_rows(int B, int nug) {
+  // up to 8 batch tiles, but no more than keep the whole grid (tiles x unit groups) co-resident: every
+  // further tile only starts when an earlier one has finished all T steps (H = 512: 32 unit groups =>
+  // 4 tiles of 16 rows at B = 64 instead of two waves of 8-row tiles).  Rows per tile: a multiple of 8,
+  // at most kTlMaxRB.
+  int tiles = kNumSMs / nug;
+  if (tiles > 8) tiles = 8;
+  if (tiles < 1) tiles = 1;
+  int rb = ((B + tiles - 1) / tiles + 7) / 8 * 8;
   if (rb < 8) rb = 8;
   if (rb > kTlMaxRB) rb = kTlMaxRB;
   return rb;
@@ -273,7 +279,7 @@ static size_t bwd_smem(int H, int RB) {
 
 template <int H>
 static int launch_lstm2(bool bwd, Lstm2Args a, cudaStream_t st) {
-  int RB = tile_rows(a.B);
+  int RB = tile_rows(a.B, H / kTlNU);
   while (RB > 8 && (bwd ? bwd_smem(H, RB) : fwd_smem(H, RB)) > 220 * 1024) RB -= 8;
   const size_t smem = bwd ? bwd_smem(H, RB) : fwd_smem(H, RB);
   if (smem > 220 * 1024) return set_error(SEEDRL_ERR_INVALID_ARGUMENT, "lstm (tiled): does not fit shared memory");
