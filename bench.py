@@ -135,12 +135,17 @@ def workload_config(args, n):
 
 # ----------------------------------------------------------------------------------------
 class ClockSampler(object):
+  """`nvidia-smi -lms 20` beside the benchmark.  Started BEFORE the warm-up steps: the tool's own
+  start-up (NVML initialisation) can stall the GPU for tens of milliseconds, its 20 ms polls do not --
+  `ready()` waits for the first sample, `begin()` marks the start of the timed region, and `stop()`
+  keeps the samples taken between `begin()` and `stop()` (the timed region)."""
   Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
        'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
-       'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+       'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,timestamp')
 
   def __init__(self, gpu_index):
     self.gpu = gpu_index
+    self.t0 = None
     self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
     try:
       self.p = subprocess.Popen(['nvidia-smi', '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
@@ -148,10 +153,33 @@ class ClockSampler(object):
     except Exception:
       self.p = None
 
+  def ready(self, timeout=5.0):
+    t_end = time.time() + timeout
+    while self.p is not None and time.time() < t_end:
+      try:
+        if os.path.getsize(self.f.name) > 0:
+          return True
+      except OSError:
+        pass
+      time.sleep(0.01)
+    return False
+
+  def begin(self):
+    self.t0 = time.time()
+
+  @staticmethod
+  def _stamp(text):
+    import datetime
+    try:
+      return datetime.datetime.strptime(text.strip(), '%Y/%m/%d %H:%M:%S.%f').timestamp()
+    except Exception:
+      return None
+
   def stop(self):
     out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
     if self.p is None:
       return out
+    t1 = time.time()
     self.p.terminate()
     try:
       self.p.wait(5)
@@ -160,6 +188,11 @@ class ClockSampler(object):
     self.f.flush()
     rows = [l.strip().split(', ') for l in open(self.f.name) if l.strip()]
     os.unlink(self.f.name)
+    if self.t0 is not None:
+      inside = [r for r in rows if len(r) > 9 and self._stamp(r[9]) is not None and
+                self.t0 - 0.02 <= self._stamp(r[9]) <= t1 + 0.02]
+      if inside:
+        rows = inside
     sm, reasons, mx = [], set(), None
     for r in rows:
       try:
@@ -409,9 +442,11 @@ def run_r2d2(args):
       fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / k
+  sampler = ClockSampler(torch.cuda.current_device())
   for _ in range(max(args.warmup, 16)):     # the caching allocator settles after a dozen sample/gather shapes
     one_step(False)
-  sampler = ClockSampler(torch.cuda.current_device())
+  sampler.ready()
+  sampler.begin()
   n0 = _lib.launch_count()
   ms = timed(lambda: one_step(False), args.steps)
   launches = (_lib.launch_count() - n0) // args.steps
@@ -584,9 +619,12 @@ def main():
     return float(ms) / k
 
   # ---- kernel-only (inputs resident in HBM) --------------------------------------------
+  sampler = ClockSampler(local) if rank == 0 else None       # its start-up overlaps the warm-up, not the timed steps
   for _ in range(max(args.warmup, 3)):
     step.minimize(unroll)
-  sampler = ClockSampler(local) if rank == 0 else None
+  if sampler:
+    sampler.ready()
+    sampler.begin()
   n0 = _lib.launch_count()
   ms_step = timed(lambda: step.minimize(unroll), args.steps)
   launches = (_lib.launch_count() - n0) // args.steps

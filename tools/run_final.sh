@@ -17,7 +17,7 @@ if [ "$1" != "quick" ]; then
     python tools/r2d2_time.py > $O/r2d2_ncu.log 2>&1
   # the four gathered-operand GEMMs of one shallow-net step: conv0 / conv1 forward, conv1 / conv0 weight gradient
   timeout 400 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-    -k 'regex:gemm_tc_kernel<[01], 0, 1, 32, 1>' -c 4 -o $O/gemm_gather -f \
+    -k 'regex:gemm_tc_kernel<\(bool\)[01], \(bool\)0, \(bool\)1, \(int\)32, \(bool\)1>' -c 4 -o $O/gemm_gather -f \
     python bench.py --net shallow --steps 2 --warmup 3 --no-extras > $O/gemm_gather_ncu.log 2>&1
 fi
 python - <<'PY'
