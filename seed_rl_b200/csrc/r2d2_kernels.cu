@@ -7,9 +7,10 @@
 //                              importance weights normalised by their max
 //   global-norm clip           tf.clip_by_global_norm, learner.py:608 (clip_norm = 40)
 //
-// STATUS (round 1): written against oracle/r2d2_oracle.py, compiled for sm_100a, exported through
-// the C-ABI, NOT yet executed on hardware (the round's GPU budget was spent before this row);
-// its GPU tests are gated (tests/test_gpu_r2d2.py).  Nothing on the V-trace path calls it.
+// Parity: tests/test_gpu_r2d2.py against oracle/r2d2_oracle.py / oracle/r2d2_learner_oracle.py (frame
+// stacking and replay indices bit-exact, loss / priorities / dq within fp32 rounding), on a B200.
+// The network itself (DuelingLSTMDQNNet forward / backward) is csrc/r2d2_net.cu.  Nothing on the
+// V-trace path calls these kernels.
 //
 // All of it is HBM-/latency-bound byte and elementwise work: coalesced accesses across the
 // pixel or batch axis, sequential walks along time in registers.

@@ -1,7 +1,7 @@
 """CPU: the per-thread bodies of the R2D2 CUDA kernels (seed_rl_b200/csrc/r2d2_thread.inl -- the
 same source text the GPU executes) compiled as host C++ and run thread by thread against
-oracle/r2d2_oracle.py.  This validates the algorithm and indexing of kernels that have not yet
-run on hardware (tests/test_gpu_r2d2.py is gated); it is a test harness, not a product path."""
+oracle/r2d2_oracle.py.  This validates the algorithm and indexing of those kernels where no GPU is
+present (their GPU parity tests are tests/test_gpu_r2d2.py); it is a test harness, not a product path."""
 import ctypes
 import os
 import subprocess
