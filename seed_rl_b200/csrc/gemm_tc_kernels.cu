@@ -315,6 +315,52 @@ __global__ void gemm_tc_reduce_kernel(int M, int N, int splits, const float* __r
   }
 }
 
+// Same reduction for many slices (the im2col weight gradients: 64-128 slices of a small M x N): the slices
+// of an output are spread over 8 lanes (lane zl sums z = zl, zl + 8, ... in order), the 8 partial sums are
+// combined in lane order through shared memory => still a fixed summation order.  CTA = 32 float4 outputs.
+__global__ void __launch_bounds__(256)
+gemm_tc_reduce_wide_kernel(int M, int N, int splits, const float* __restrict__ ws, float* __restrict__ C, int ldc,
+                           GemmEpi e) {
+  __shared__ float4 part[8][32];
+  const int o = threadIdx.x & 31, zl = threadIdx.x >> 5;
+  const int i = (blockIdx.x * 32 + o) * 4;
+  const bool in = i < M * N;
+  const size_t plane = (size_t)M * N;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+  if (in) {
+    int z = zl;
+    for (; z + 8 < splits; z += 16) {
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(ws + (size_t)z * plane + i));
+      const float4 w = __ldcs(reinterpret_cast<const float4*>(ws + (size_t)(z + 8) * plane + i));
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      b.x += w.x; b.y += w.y; b.z += w.z; b.w += w.w;
+    }
+    if (z < splits) {
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(ws + (size_t)z * plane + i));
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+  }
+  part[zl][o] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+  __syncthreads();
+  if (zl != 0 || !in) return;
+  float x[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float4 v = part[k][o];
+    x[0] += v.x; x[1] += v.y; x[2] += v.z; x[3] += v.w;
+  }
+  const int m = i / N, n = i - m * N;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float v = x[j];
+    if (e.bias) v += __ldg(e.bias + n + j);
+    if (e.relu) v = fmaxf(v, 0.f);
+    if (e.mask) v = __ldg(e.mask + (size_t)m * e.ldm + n + j) > 0.f ? v : 0.f;
+    float* c = C + (size_t)m * ldc + n + j;
+    *c = e.accumulate ? *c + v : v;
+  }
+}
+
 static int norm_bk(int bk) { return bk == 64 ? 64 : (bk == 16 ? 16 : 32); }
 static int g_gemm_bk = norm_bk(getenv("SEEDRL_GEMM_BK") ? atoi(getenv("SEEDRL_GEMM_BK")) : 32);
 void gemm_tc_set_bk(int bk) { g_gemm_bk = norm_bk(bk); }
@@ -420,7 +466,9 @@ int gemm_tc(bool ta, bool tb, int split, int M, int N, int K, const float* A, in
   count_launch(PC_GEMM, st);
   SEEDRL_CHECK_LAUNCH();
   if (splits > 1) {
-    if ((N & 3) == 0)
+    if ((N & 3) == 0 && splits >= 16)
+      gemm_tc_reduce_wide_kernel<<<ceil_div(M * N / 4, 32), 256, 0, st>>>(M, N, splits, ws, C, ldc, e);
+    else if ((N & 3) == 0)
       gemm_tc_reduce_kernel<true><<<ceil_div(M * N / 4, 256), 256, 0, st>>>(M, N, splits, ws, C, ldc, e);
     else
       gemm_tc_reduce_kernel<false><<<ceil_div(M * N, 256), 256, 0, st>>>(M, N, splits, ws, C, ldc, e);

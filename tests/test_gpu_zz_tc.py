@@ -207,7 +207,9 @@ GEMM_CASES = [
     (0, 1, 1344, 3872, 256, dict(mask=True)),                              # Dense data gradient (TB)
     (0, 1, 200, 256, 1024, dict(mask=True, accumulate=True)),
     (1, 1, 129, 40, 100, dict(bias=True)),
-    (0, 0, 64, 16, 32, {}), (0, 0, 130, 19, 70, dict(relu=True)), (0, 1, 65, 300, 33, {})]
+    (0, 0, 64, 16, 32, {}), (0, 0, 130, 19, 70, dict(relu=True)), (0, 1, 65, 300, 33, {}),
+    (1, 0, 256, 16, 60000, {}),                                            # im2col weight gradient: 128 K-slices (wide reduce)
+    (0, 0, 128, 32, 40000, dict(bias=True, relu=True, accumulate=True))]
 
 
 @pytest.mark.parametrize('split', [0, 1])
