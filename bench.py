@@ -346,6 +346,80 @@ def inference_path_bench(agent, iters=200, warmup=30, N=64, num_envs=256, T=20, 
   }
 
 
+def inference_lanes_bench(agent, lanes=2, iters=150, warmup=30, N=64, num_envs=256, T=20, batch=64):
+  """Aggregate central-inference throughput of `lanes` independent InferenceHosts on ONE GPU, each
+  with its own environment shard, unroll store, CUDA graph and stream, driven by its own host thread
+  (the reference builds one such host per core group, agents/vtrace/learner.py:314-416): the host
+  side of one lane's call overlaps the other lane's graph replay.  Wall clock over all lanes."""
+  import threading
+  import numpy as np
+  import torch
+  from seed_rl_b200.agents.vtrace import learner_loop
+  from seed_rl_b200.common import utils
+  dev = torch.cuda.current_device()
+  capture_lock = threading.Lock()
+  gate = threading.Barrier(lanes + 1)
+  errors, lat = [], [[] for _ in range(lanes)]
+
+  def lane(k):
+    host = None
+    try:
+      torch.cuda.set_device(dev)
+      host = learner_loop.InferenceHost(agent, num_envs, T, N, OBS, training_batch_size=batch, cuda_graph=True)
+
+      def drain():
+        try:
+          while True:
+            slot, _ = learner_loop.assembled_batch(host.assembler)
+            host.assembler.release(slot)
+        except utils.QueueClosedError:
+          return
+      threading.Thread(target=drain, daemon=True).start()
+      rng = np.random.default_rng(100 + k)
+      run_ids = rng.integers(1, 2**40, num_envs)
+      groups = [np.arange(g * N, (g + 1) * N, dtype=np.int32) for g in range(num_envs // N)]
+      obs = [torch.from_numpy(rng.integers(0, 256, (N,) + OBS, dtype=np.uint8)).pin_memory().numpy() for _ in groups]
+      zeros = np.zeros(N, np.float32)
+
+      def one(i):
+        ids = groups[i % len(groups)]
+        env = utils.EnvOutput(rng.normal(size=N).astype(np.float32), rng.random(N) < 0.01, obs[i % len(groups)],
+                              np.zeros(N, bool), np.full(N, i, np.int32))
+        return host.inference(ids, run_ids[ids], env, zeros)
+      with capture_lock:                       # one lane captures its graph at a time
+        for i in range(warmup):
+          one(i)
+      gate.wait(120)
+      for i in range(iters):
+        t1 = time.perf_counter()
+        one(warmup + i)
+        lat[k].append(time.perf_counter() - t1)
+      gate.wait(120)
+    except Exception as exc:                   # pylint: disable=broad-except
+      errors.append(repr(exc)[:200])
+      gate.abort()
+    finally:
+      if host is not None and host.assembler is not None:
+        host.assembler.close()
+  threads = [threading.Thread(target=lane, args=(k,), daemon=True) for k in range(lanes)]
+  for th in threads:
+    th.start()
+  try:
+    gate.wait(180)
+    t0 = time.perf_counter()
+    gate.wait(180)
+    wall = time.perf_counter() - t0
+  except threading.BrokenBarrierError:
+    return {'unavailable': '; '.join(errors) or 'barrier broken'}
+  for th in threads:
+    th.join(10)
+  allat = sorted(x for l in lat for x in l)
+  return {'lanes': lanes, 'inference_batch_size': N, 'envs_per_lane': num_envs, 'iters_per_lane': iters,
+          'inferences_per_sec': lanes * N * iters / wall, 'us_per_batch_p50': allat[len(allat) // 2] * 1e6,
+          'what': '%d independent InferenceHosts (own env shard / store / CUDA graph / stream / host thread) on one '
+                  'GPU sharing the agent; aggregate wall-clock throughput' % lanes}
+
+
 def r2d2_cpu_throughput(B, steps, warmup, burn_in=40, unroll=100):
   """The reference's R2D2 learner step (oracle port, torch-CPU fp32) on a bounded sample."""
   import torch
@@ -824,6 +898,11 @@ def main():
             'h2d_bytes_per_batch')}
       except Exception as exc:        # pylint: disable=broad-except
         line['inference_path'] = {'unavailable': repr(exc)[:300]}
+      try:
+        if isinstance(line.get('inference_path'), dict) and 'unavailable' not in line['inference_path']:
+          line['inference_path']['two_lanes'] = inference_lanes_bench(agent, lanes=2)
+      except Exception as exc:        # pylint: disable=broad-except
+        line['inference_path']['two_lanes'] = {'unavailable': repr(exc)[:300]}
 
     if rank == 0 and world == 1 and args.net == 'deep' and args.conv != 'simt':
       # ---- the most time-consuming single kernel instance of the step, alone: the 16->16 conv
