@@ -179,6 +179,14 @@ def fill_replay(host, feeder, timeout=None):
     unrolls = host.unroll_queue.dequeue_many(n)
   except utils.QueueClosedError:
     return False
+  if torch.cuda.is_available():
+    # the unrolls were allocated on the inference stream and are copied into the replay buffer on THIS
+    # thread's stream: tell the caching allocator, so that their blocks are not handed back to the
+    # inference stream (and overwritten by the next unrolls) while that copy is still queued
+    cur = torch.cuda.current_stream()
+    for t in utils.flatten(unrolls):
+      if isinstance(t, torch.Tensor) and t.is_cuda:
+        t.record_stream(cur)
   feeder.insert(learner.Unroll(*unrolls))
   return True
 
